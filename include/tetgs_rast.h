@@ -1,0 +1,177 @@
+/*
+ * tetgs_rast.h — C ABI of the B200-native (sm_100a) differentiable Gaussian rasterizer for TetGS.
+ *
+ * This is the drop-in boundary for the hot path named in BASELINE.json: every entry point takes
+ * plain pointers / sizes / a cudaStream_t (as void*), returns an int status (0 = ok) and never
+ * touches torch types.  The reference interfaces each function replaces are cited as
+ * file:line relative to /root/reference/Edit_core/thirdparties/.
+ *
+ * Conventions (same as the reference):
+ *   - all tensors are fp32, contiguous, device memory unless stated;
+ *   - viewmatrix / projmatrix are the TRANSPOSED 4x4 matrices (flat memory is column-major,
+ *     element (row r, col c) at m[4*c + r]; diff-gaussian-rasterization/cuda_rasterizer/auxiliary.h:58-77);
+ *   - quaternions are (r,x,y,z) and are NOT normalised by the kernels (forward.cu:127);
+ *   - cov3D is packed upper-triangular (xx,xy,xz,yy,yz,zz);
+ *   - an absent optional input is a NULL pointer;
+ *   - the three workspace buffers (geom / binning / image) are owned by the caller, opaque, and
+ *     must be handed back unchanged to tgr_backward (rasterizer_impl.cu:371-373 does the same).
+ */
+#ifndef TETGS_RAST_H_
+#define TETGS_RAST_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TGR_ABI_VERSION 1
+#define TGR_TILE 16 /* 16x16 pixel tiles, config.h:16-17 */
+
+/* Per-call description of one view and one set of Gaussians.  POD only. */
+typedef struct tgr_params {
+  /* sizes */
+  int32_t P;            /* number of Gaussians */
+  int32_t D;            /* active SH degree (0..3) */
+  int32_t M;            /* SH coefficients per channel stored in `shs` (0 when colours are precomputed) */
+  int32_t W, H;         /* image width / height */
+  float tan_fovx, tan_fovy;
+  float scale_modifier;
+  int32_t prefiltered;  /* accepted for API parity; a culled point is simply skipped */
+  int32_t debug;        /* 1: synchronise + report CUDA errors after every stage (auxiliary.h:166-173) */
+  int32_t extras;       /* 1: also produce depth/alpha images (new) */
+  int32_t reserved0;
+  /* camera (device pointers) */
+  const float* background; /* [3] */
+  const float* viewmatrix; /* [16] */
+  const float* projmatrix; /* [16] */
+  const float* campos;     /* [3] */
+  /* Gaussians (device pointers) */
+  const float* means3D;        /* [P,3] */
+  const float* shs;            /* [P,M,3] or NULL */
+  const float* colors_precomp; /* [P,3]   or NULL */
+  const float* opacities;      /* [P,1] */
+  const float* scales;         /* [P,3]   or NULL */
+  const float* rotations;      /* [P,4]   or NULL */
+  const float* cov3D_precomp;  /* [P,6]   or NULL */
+  /* workspaces (device pointers, sizes from tgr_*_bytes) */
+  void* geom_buffer;
+  void* binning_buffer;
+  void* image_buffer;
+  uint64_t geom_bytes, binning_bytes, image_bytes;
+  /* forward outputs */
+  float* out_color;   /* [3,H,W] */
+  int32_t* radii;     /* [P] */
+  float* out_depth;   /* [H,W] or NULL (extras) */
+  float* out_alpha;   /* [H,W] or NULL (extras) */
+  /* backward inputs */
+  const float* dL_dout_color; /* [3,H,W] */
+  const float* dL_dout_depth; /* [H,W] or NULL */
+  const float* dL_dout_alpha; /* [H,W] or NULL */
+  /* backward outputs: every element is written by the kernels, no pre-zeroing needed */
+  float* dL_dmeans2D;   /* [P,3] */
+  float* dL_dcolors;    /* [P,3] */
+  float* dL_dopacity;   /* [P,1] */
+  float* dL_dmeans3D;   /* [P,3] */
+  float* dL_dcov3D;     /* [P,6] */
+  float* dL_dsh;        /* [P,M,3] or NULL when M == 0 */
+  float* dL_dscales;    /* [P,3] or NULL */
+  float* dL_drotations; /* [P,4] or NULL */
+  /* pinned host mirror of num_rendered written asynchronously by tgr_forward_preprocess (may be NULL) */
+  uint32_t* host_num_rendered;
+} tgr_params;
+
+/* Optional mesh binding fused into the preprocess kernels (replaces the eager PyTorch binding in
+ * Edit_core/tetgs_scene/tetgs_model.py:252-286 — points = ori + n*delta, exp/sigmoid/normalize
+ * activations).  When passed (non-NULL) to the *_bound entry points, means3D/opacities/scales/rotations
+ * in tgr_params are ignored and derived from these raw parameters instead. */
+typedef struct tgr_binding {
+  int32_t n_verts, n_faces;
+  const float* verts;          /* [n_verts,3] mesh (tet-surface) vertices */
+  const float* vert_normals;   /* [n_verts,3] unit vertex normals */
+  const int32_t* faces;        /* [n_faces,3] */
+  const int32_t* face_index;   /* [P] face each Gaussian is bound to */
+  const float* bary;           /* [P,3] barycentric coordinates */
+  const float* delta;          /* [P]  learnable offset along the interpolated normal */
+  const float* log_scales;     /* [P,3] pre-activation scales   (exp) */
+  const float* raw_quats;      /* [P,4] pre-normalisation quats (normalize) */
+  const float* opacity_logits; /* [P]   pre-activation opacity  (sigmoid) */
+  /* activated values written by the forward (needed by the drop-in callers and the backward) */
+  float* out_means3D;          /* [P,3] */
+  float* out_scales;           /* [P,3] */
+  float* out_rotations;        /* [P,4] */
+  float* out_opacities;        /* [P]   */
+  /* gradients wrt the raw parameters (backward outputs, fully written) */
+  float* dL_ddelta;            /* [P]   */
+  float* dL_dlog_scales;       /* [P,3] */
+  float* dL_draw_quats;        /* [P,4] */
+  float* dL_dopacity_logits;   /* [P]   */
+  float* dL_dverts;            /* [n_verts,3] or NULL; accumulated with atomics, caller zeroes */
+} tgr_binding;
+
+/* ---- library ---- */
+int tgr_abi_version(void);
+const char* tgr_last_error(void);     /* thread-local message of the last non-zero status */
+
+/* ---- workspace sizes (pure functions of the arguments; rasterizer_impl.h:66-72 `required<T>`) ---- */
+uint64_t tgr_geom_bytes(int32_t P);
+uint64_t tgr_image_bytes(int32_t W, int32_t H);
+uint64_t tgr_binning_bytes(int32_t P, uint64_t num_rendered_capacity);
+
+/* ---- forward: replaces CudaRasterizer::Rasterizer::forward (rasterizer_impl.cu:198-336) ----
+ * Stage 1: per-Gaussian preprocess (forward.cu:155-256), depth ordering, total instance count.
+ *          Needs geom_buffer (and out radii).  The instance count R lands in the geom header on the
+ *          device and, if host_num_rendered != NULL, is copied there asynchronously.
+ * Stage 2: key emission + tile sort + tile ranges + alpha blending
+ *          (rasterizer_impl.cu:70-138, 289-333; forward.cu:261-374).  `num_rendered_capacity` is the
+ *          number of instances binning_buffer was sized for.  If the true R exceeds it the call
+ *          renders nothing, sets the overflow flag (tgr_read_header) and returns 0; the caller retries.
+ */
+int tgr_forward_preprocess(const tgr_params* p, const tgr_binding* bind, void* stream);
+int tgr_forward_render(const tgr_params* p, uint64_t num_rendered_capacity, void* stream);
+/* Blocks the host until the asynchronous host_num_rendered copy of the calling thread's most recent
+ * tgr_forward_preprocess has landed (the GPU keeps running the depth sort meanwhile). This is the only
+ * host<->device synchronisation of a forward; the reference has the same one at rasterizer_impl.cu:281. */
+int tgr_wait_num_rendered(void);
+
+/* ---- backward: replaces CudaRasterizer::Rasterizer::backward (rasterizer_impl.cu:340-434) ---- */
+int tgr_backward(const tgr_params* p, const tgr_binding* bind, uint64_t num_rendered_capacity, void* stream);
+
+/* Synchronously reads {num_rendered, overflow, num_visible, reserved} from a geom buffer header. */
+int tgr_read_header(const void* geom_buffer, uint32_t out[4], void* stream);
+
+/* ---- mark_visible: replaces Rasterizer::markVisible (rasterizer_impl.cu:141-153) ---- */
+int tgr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, void* stream);
+
+/* ---- distCUDA2: replaces SimpleKNN::knn (simple-knn/simple_knn.cu:185-221) ----
+ * mean squared distance to the 3 nearest other points; `workspace` of tgr_knn_bytes(P) bytes. */
+uint64_t tgr_knn_bytes(int32_t P);
+int tgr_dist2(int32_t P, const float* points, float* mean_dist2, void* workspace, uint64_t workspace_bytes,
+              void* stream);
+
+/* ---- parity / debugging helpers (used by tests; not on the hot path) ----
+ * Reconstructs the reference's sorted 64-bit keys (tile << 32 | depth bits, rasterizer_impl.cu:102-104),
+ * the sorted Gaussian ids and the per-tile ranges from the opaque buffers. keys/ids have R entries,
+ * ranges 2*T entries.  Any output pointer may be NULL. */
+int tgr_export_binning(const tgr_params* p, uint64_t num_rendered, uint64_t* keys, uint32_t* ids,
+                       uint32_t* ranges, void* stream);
+/* Copies per-Gaussian preprocess records out of the geom buffer: depth[P], xy[2P], conic_opacity[4P],
+ * rgb[3P], tiles_touched[P].  Any output pointer may be NULL. */
+int tgr_export_geom(const tgr_params* p, float* depth, float* xy, float* conic_opacity, float* rgb,
+                    uint32_t* tiles_touched, void* stream);
+/* Copies per-pixel blend state: final_T[H*W], n_contrib[H*W]. */
+int tgr_export_image_state(const tgr_params* p, float* final_T, uint32_t* n_contrib, void* stream);
+
+/* Stand-alone stable LSD radix sort of (u32 key, u32 value) pairs on bits [begin_bit, end_bit) — the
+ * hand-written onesweep that replaces cub::DeviceRadixSort::SortPairs (rasterizer_impl.cu:303-308,
+ * simple_knn.cu:207-213).  Exposed for tests and micro-benchmarks. Result is in keys_out/vals_out. */
+uint64_t tgr_sort_temp_bytes(uint64_t n);
+int tgr_sort_pairs_u32(uint64_t n, uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
+                       int begin_bit, int end_bit, void* temp, uint64_t temp_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TETGS_RAST_H_ */

@@ -1,0 +1,268 @@
+"""GPU parity tests (run with `-m gpu` on the B200 box).  Everything goes through the C ABI via the host-side
+mirror of the reference operator API.  Three checkers, all test infrastructure:
+  * the UNMODIFIED reference CUDA rasterizer built into oracle/_ref (bit-exact integer artefacts, images,
+    gradients) — skipped if it was not built;
+  * the float64 CPU oracle (oracle/oracle.py);
+  * committed golden fixtures (tests/golden), see test_golden.py.
+Tolerances (BASELINE.json north_star): keys / sort order / tile ranges bit-exact; images max-abs 1e-4;
+gradients relative L2 1e-3.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import (export_binning, export_geom, export_image_state, ours_backward, ours_forward, random_cloud,
+                     rel_l2, small_scene, to_dev)
+
+pytestmark = pytest.mark.gpu
+
+IMG_TOL = 1e-4
+GRAD_TOL = 1e-3
+
+
+def _ref():
+    from oracle import ref_cuda
+    if not ref_cuda.available():
+        pytest.skip("reference CUDA build (oracle/_ref) not present")
+    return ref_cuda
+
+
+def _cases():
+    # (name, builder) — avatar shells at several sizes plus unstructured clouds with ragged image sizes
+    return [
+        ("shell_3k_128", lambda: small_scene(3000, 32, 128, 0)[1:]),
+        ("shell_10k_256", lambda: small_scene(10000, 32, 256, 1)[1:]),
+        ("shell_50k_512", lambda: small_scene(50000, 96, 512, 2)[1:]),
+        ("cloud_5k_200x120", lambda: random_cloud(5000, 200, 120, seed=3)),
+        ("cloud_big_2k_77x45", lambda: random_cloud(2000, 77, 45, seed=4, big=True)),
+    ]
+
+
+@pytest.mark.parametrize("name,build", _cases())
+@pytest.mark.parametrize("degree", [3, 0])
+def test_forward_bitexact_vs_reference(name, build, degree):
+    ref = _ref()
+    inp, cam = build()
+    P, W, H = inp["means3D"].shape[0], cam["image_width"], cam["image_height"]
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    ours = ours_forward(inp, cam, degree)
+    theirs = ref.forward(inp, cam, degree)
+    torch.cuda.synchronize()
+    R_o, color_o, radii_o = ours[0], ours[1], ours[2]
+    R_r, color_r, radii_r = theirs[0], theirs[1], theirs[2]
+
+    # --- per-Gaussian records: bit-exact where visible ------------------------------------------
+    assert torch.equal(radii_o, radii_r), "radii differ at %d Gaussians" % int((radii_o != radii_r).sum())
+    vis = radii_r > 0
+    go, gr = export_geom(P, W, H, ours), ref.decode_geom(theirs[3], P)
+    assert torch.equal(go["tiles_touched"], gr["tiles_touched"].to(torch.int32))
+    assert torch.equal(go["depths"][vis].view(torch.int32), gr["depths"][vis].view(torch.int32)), "depth bits"
+    assert torch.equal(go["means2D"][vis].view(torch.int32), gr["means2D"][vis].view(torch.int32)), "means2D bits"
+    assert torch.equal(go["conic_opacity"][vis].view(torch.int32), gr["conic_opacity"][vis].view(torch.int32)), "conic"
+    assert (go["rgb"][vis] - gr["rgb"][vis]).abs().max().item() <= 1e-6
+    assert R_o == R_r
+
+    # --- keys, sorted order, tile ranges: bit-exact ----------------------------------------------
+    keys_o, ids_o, ranges_o = export_binning(P, W, H, ours)
+    keys_r, ids_r = ref.decode_binning(theirs[4], R_r)
+    _, ncon_r, ranges_r = ref.decode_image(theirs[5], W * H, T)
+    assert torch.equal(keys_o, keys_r), "sorted 64-bit keys differ"
+    assert torch.equal(ids_o, ids_r), "sorted Gaussian ids differ"
+    assert torch.equal(ranges_o, ranges_r), "tile ranges differ"
+
+    # --- image + per-pixel state -------------------------------------------------------------------
+    fT_o, ncon_o = export_image_state(P, W, H, ours)
+    assert torch.equal(ncon_o, ncon_r), "n_contrib differs"
+    err = (color_o - color_r).abs().max().item()
+    assert err <= IMG_TOL, "image max-abs %g" % err
+
+
+@pytest.mark.parametrize("name,build", _cases())
+def test_backward_vs_reference(name, build):
+    ref = _ref()
+    inp, cam = build()
+    W, H = cam["image_width"], cam["image_height"]
+    g = torch.Generator().manual_seed(1)
+    dL = (torch.randn(3, H, W, generator=g) / (3 * H * W)).cuda()
+    fo = ours_forward(inp, cam, 3)
+    fr = ref.forward(inp, cam, 3)
+    go = ours_backward(inp, cam, 3, fo, dL)
+    gr = ref.backward(inp, cam, 3, fr, dL)
+    torch.cuda.synchronize()
+    names = ["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dscales", "dL_drotations"]
+    for n, a, b in zip(names, go, gr):
+        assert a.shape == b.shape, n
+        assert torch.isfinite(a).all(), n
+        e = rel_l2(a, b)
+        assert e <= GRAD_TOL, "%s rel-L2 %g" % (n, e)
+
+
+@pytest.mark.parametrize("variant", ["sh", "colors", "cov3d"])
+def test_vs_float64_oracle(variant):
+    from oracle import oracle
+    _, inp, cam = small_scene(2500, 32, 96, 1)
+    W, H = cam["image_width"], cam["image_height"]
+    P = inp["means3D"].shape[0]
+    inp = dict(inp)
+    degree = 3
+    if variant == "colors":
+        inp["colors_precomp"] = torch.rand(P, 3, generator=torch.Generator().manual_seed(5)).cuda()
+        inp.pop("shs")
+    if variant == "cov3d":
+        rec = oracle.preprocess(inp["means3D"].cpu(), inp["opacities"].cpu(), cam["viewmatrix"].cpu(),
+                                cam["projmatrix"].cpu(), cam["campos"].cpu(), W, H, cam["tanfovx"], cam["tanfovy"],
+                                scales=inp["scales"].cpu(), rotations=inp["rotations"].cpu(), shs=inp["shs"].cpu(),
+                                degree=degree)
+        s = inp["scales"].double().cpu()
+        q = inp["rotations"].double().cpu()
+        r, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+        Rm = torch.stack([torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y)], -1),
+                          torch.stack([2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x)], -1),
+                          torch.stack([2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], -1)], -2)
+        S = Rm @ torch.diag_embed(s * s) @ Rm.transpose(1, 2)
+        inp["cov3D_precomp"] = torch.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], -1).float().cuda()
+        inp.pop("scales"); inp.pop("rotations")
+
+    g = torch.Generator().manual_seed(1)
+    dLc = torch.randn(3, H, W, generator=g) / (3 * H * W)
+    dLd = torch.randn(1, H, W, generator=g) / (H * W)
+    dLa = torch.randn(1, H, W, generator=g) / (H * W)
+
+    fo = ours_forward(inp, cam, degree, extras=True)
+    go = ours_backward(inp, cam, degree, fo, dLc.cuda(), dLd.cuda(), dLa.cuda())
+    torch.cuda.synchronize()
+    geo = export_geom(P, W, H, fo)
+
+    oin = {k: v.detach().double().cpu().requires_grad_(True) for k, v in inp.items()}
+    out = oracle.rasterize(oin, to_dev(cam, "cpu"), degree,
+                           xy_radii_override=(geo["means2D"].cpu().numpy(), fo[2].cpu().numpy()),
+                           depth_override=geo["depths"].cpu().numpy())
+    # integer artefacts given the same fp32 records: bit-exact
+    keys_o, ids_o, ranges_o = export_binning(P, W, H, fo)
+    assert np.array_equal(keys_o.cpu().numpy().view(np.uint64), out["keys"])
+    assert np.array_equal(ids_o.cpu().numpy().view(np.uint32), out["ids"])
+    assert np.array_equal(ranges_o.cpu().numpy().view(np.uint32), out["ranges"])
+    assert fo[0] == out["num_rendered"]
+    # the oracle's own radii agree except at fp32/fp64 ceil boundaries (none expected at this size)
+    assert (fo[2].cpu().numpy() != out["radii"]).mean() <= 1e-3
+
+    def img_ok(a, b, what):
+        d = (a.double().cpu() - b.detach()).abs()
+        # a pair whose alpha sits within fp32 rounding of the 1/255 cut-off may flip: allow <= 1e-4 of pixels
+        assert (d > IMG_TOL).double().mean().item() <= 1e-4 and d.max().item() <= 1e-2, "%s max %g" % (what, d.max())
+
+    img_ok(fo[1], out["color"], "color")
+    img_ok(fo[6], out["depth"], "depth")
+    img_ok(fo[7], out["alpha"], "alpha")
+    loss = (out["color"] * dLc.double()).sum() + (out["depth"] * dLd.double()).sum() + (out["alpha"] * dLa.double()).sum()
+    loss.backward()
+    pairs = [("dL_dmeans3D", go[3], oin["means3D"].grad)]
+    if variant != "cov3d":
+        pairs += [("dL_dscales", go[6], oin["scales"].grad), ("dL_drotations", go[7], oin["rotations"].grad)]
+    else:
+        pairs += [("dL_dcov3D", go[4], oin["cov3D_precomp"].grad)]
+    if variant == "colors":
+        pairs += [("dL_dcolors", go[1], oin["colors_precomp"].grad)]
+    else:
+        pairs += [("dL_dsh", go[5], oin["shs"].grad)]
+    pairs += [("dL_dopacity", go[2], oin["opacities"].grad)]
+    for n, a, b in pairs:
+        e = rel_l2(a, b)
+        assert e <= 3 * GRAD_TOL, "%s rel-L2 vs oracle %g" % (n, e)
+
+
+def test_extras_do_not_change_colour():
+    _, inp, cam = small_scene(3000, 32, 128, 0)
+    a = ours_forward(inp, cam, 3, extras=False)
+    b = ours_forward(inp, cam, 3, extras=True)
+    assert torch.equal(a[1], b[1])
+    assert b[6].shape == (1, 128, 128) and b[7].shape == (1, 128, 128)
+    assert float(b[7].min()) >= 0 and float(b[7].max()) <= 1
+
+
+def test_empty_and_fully_culled():
+    _, inp, cam = small_scene(3000, 32, 64, 0)
+    dev = inp["means3D"].device
+    # P = 0: zeros image, empty buffers, nothing launched (rasterize_points.cu:81)
+    empty = {k: v[:0] for k, v in inp.items()}
+    out = ours_forward(empty, cam, 3)
+    assert out[0] == 0 and out[1].shape == (3, 64, 64) and float(out[1].abs().max()) == 0 and out[2].numel() == 0
+    # everything behind the camera: background only, R = 0, gradients all zero
+    behind = dict(inp)
+    behind["means3D"] = inp["means3D"] + cam["campos"][None] * 3.0
+    out = ours_forward(behind, cam, 3)
+    assert out[0] == 0 and int(out[2].abs().sum()) == 0
+    assert torch.allclose(out[1], cam["bg"][:, None, None].expand(3, 64, 64))
+    grads = ours_backward(behind, cam, 3, out, torch.ones(3, 64, 64, device=dev))
+    for g in grads:
+        assert float(g.abs().max()) == 0
+
+
+def test_dropin_module_autograd():
+    """The call the Edit_core scene models make (tetgs_model.py:605-614), gradients through autograd."""
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    _, inp, cam = small_scene(3000, 32, 128, 0)
+    P = inp["means3D"].shape[0]
+    settings = GaussianRasterizationSettings(
+        image_height=128, image_width=128, tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"], bg=cam["bg"],
+        scale_modifier=1.0, viewmatrix=cam["viewmatrix"], projmatrix=cam["projmatrix"], sh_degree=3,
+        campos=cam["campos"], prefiltered=False, debug=False)
+    rasterizer = GaussianRasterizer(raster_settings=settings)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in inp.items()}
+    means2D = torch.zeros(P, 3, device="cuda", requires_grad=True)
+    image, radii = rasterizer(means3D=leaves["means3D"], means2D=means2D, shs=leaves["shs"], colors_precomp=None,
+                              opacities=leaves["opacities"], scales=leaves["scales"], rotations=leaves["rotations"],
+                              cov3D_precomp=None)
+    assert image.shape == (3, 128, 128) and radii.shape == (P,) and radii.dtype == torch.int32
+    image.square().mean().backward()
+    for k, v in leaves.items():
+        assert v.grad is not None and torch.isfinite(v.grad).all(), k
+    assert means2D.grad is not None and float(means2D.grad.abs().sum()) > 0
+    assert rasterizer.markVisible(inp["means3D"]).dtype == torch.bool
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        rasterizer(means3D=inp["means3D"], means2D=means2D, opacities=inp["opacities"], scales=inp["scales"],
+                   rotations=inp["rotations"])
+    with pytest.raises(RuntimeError, match="means3D must have dimensions"):
+        rasterizer(means3D=inp["means3D"].reshape(-1), means2D=means2D, shs=inp["shs"], opacities=inp["opacities"],
+                   scales=inp["scales"], rotations=inp["rotations"])
+
+
+@pytest.mark.parametrize("n,bits", [(1, 32), (1000, 32), (4096, 12), (4097, 8), (1 << 20, 32), (3_000_001, 13), (50000, 31)])
+def test_radix_sort_stable(n, bits):
+    import ctypes as C
+    from youreditableavatar_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(n)
+    keys = torch.randint(0, 2 ** min(bits, 31), (n,), generator=g, dtype=torch.int64).to(torch.int32).cuda()
+    if bits <= 16:   # many duplicates: stability matters
+        keys = keys % (1 << bits)
+    vals = torch.arange(n, dtype=torch.int32, device="cuda")
+    ko, vo = torch.empty_like(keys), torch.empty_like(vals)
+    temp = torch.empty(L.tgr_sort_temp_bytes(n), dtype=torch.uint8, device="cuda")
+    kin, vin = keys.clone(), vals.clone()
+    rc = L.tgr_sort_pairs_u32(n, kin.data_ptr(), vin.data_ptr(), ko.data_ptr(), vo.data_ptr(), 0, bits, temp.data_ptr(),
+                              temp.numel(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, L.tgr_last_error()
+    torch.cuda.synchronize()
+    ks, order = torch.sort(keys.long() & ((1 << bits) - 1), stable=True)
+    assert torch.equal(vo.long(), order), "not the stable order"
+    assert torch.equal(ko.long() & ((1 << bits) - 1), ks)
+
+
+def test_dist2_vs_reference_and_oracle():
+    from oracle import oracle
+    from simple_knn._C import distCUDA2
+    g = torch.Generator().manual_seed(7)
+    pts = torch.randn(20000, 3, generator=g).cuda()
+    mine = distCUDA2(pts)
+    want = oracle.dist2_knn3(pts.cpu()).float()
+    assert torch.allclose(mine.cpu(), want, rtol=1e-4, atol=1e-9)
+    from oracle import ref_cuda
+    if ref_cuda.available():
+        theirs = ref_cuda.knn().distCUDA2(pts)
+        assert torch.allclose(mine, theirs, rtol=1e-5, atol=1e-9)
+    # mesh-bound points (clustered, duplicates possible)
+    _, inp, _ = small_scene(30000, 64, 64, 0)
+    m = distCUDA2(inp["means3D"])
+    w = oracle.dist2_knn3(inp["means3D"].cpu()).float()
+    assert torch.allclose(m.cpu(), w, rtol=1e-4, atol=1e-10)

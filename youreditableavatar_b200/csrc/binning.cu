@@ -1,0 +1,168 @@
+// binning.cu — instance emission and tile ranges.
+//
+//   emit_kernel   replaces duplicateWithKeys (rasterizer_impl.cu:70-111) *and* the InclusiveSum that
+//                 feeds it (rasterizer_impl.cu:277): Gaussians are visited in (depth, id) order, a chained
+//                 scan (decoupled look-back, one word per CTA) gives every Gaussian its output offset,
+//                 and each (Gaussian, tile) instance is written as a 32-bit tile id + 32-bit Gaussian id.
+//                 The tile rectangle was stored by the preprocess kernel, so getRect is not re-evaluated.
+//   ranges_kernel replaces identifyTileRanges (rasterizer_impl.cu:116-138) on the tile-sorted ids.
+#include <algorithm>
+#include "common.cuh"
+
+namespace tgr {
+
+constexpr uint32_t SC_FLAG_AGG = 1u << 30;
+constexpr uint32_t SC_FLAG_INC = 2u << 30;
+constexpr uint32_t SC_VALUE = (1u << 30) - 1;
+constexpr uint32_t COOP_THRESHOLD = 24;  // rectangles with more tiles than this are written by the whole warp
+
+__device__ __forceinline__ uint32_t ldv(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void stv(uint32_t* p, uint32_t v) {
+  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(EMIT_THREADS) emit_kernel(int P, const uint32_t* __restrict__ order,
+                                                            const ushort4* __restrict__ rect, uint32_t grid_w,
+                                                            uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                            uint32_t cap, GeomHeader* __restrict__ header,
+                                                            uint32_t* __restrict__ scan_state) {
+  __shared__ uint32_t s_tile, s_prefix;
+  __shared__ uint32_t s_warp[EMIT_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(&header->emit_ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint32_t slot0 = tile * EMIT_TILE + tid * EMIT_IPT;
+
+  uint32_t gid[EMIT_IPT];
+  ushort4 rc[EMIT_IPT];
+  uint32_t cnt[EMIT_IPT];
+  uint32_t tsum = 0;
+#pragma unroll
+  for (int i = 0; i < EMIT_IPT; ++i) {
+    const uint32_t slot = slot0 + i;
+    if (slot < (uint32_t)P) {
+      gid[i] = order[slot];
+      rc[i] = rect[gid[i]];
+      cnt[i] = (uint32_t)(rc[i].z - rc[i].x) * (uint32_t)(rc[i].w - rc[i].y);
+    } else {
+      gid[i] = 0; rc[i] = make_ushort4(0, 0, 0, 0); cnt[i] = 0;
+    }
+    tsum += cnt[i];
+  }
+  // block exclusive scan of tsum
+  uint32_t inc = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  uint32_t woff = 0, btotal = 0;
+#pragma unroll
+  for (int w = 0; w < EMIT_THREADS / 32; ++w) {
+    if (w < warp) woff += s_warp[w];
+    btotal += s_warp[w];
+  }
+  // chained scan across CTAs
+  if (tid == 0) {
+    uint32_t excl = 0;
+    if (tile == 0) {
+      stv(&scan_state[0], SC_FLAG_INC | btotal);
+    } else {
+      stv(&scan_state[tile], SC_FLAG_AGG | btotal);
+      const uint32_t* q = &scan_state[tile - 1];
+      while (true) {
+        uint32_t v = ldv(q);
+        if ((v & ~SC_VALUE) == 0) continue;
+        excl += v & SC_VALUE;
+        if (v & SC_FLAG_INC) break;
+        --q;
+      }
+      stv(&scan_state[tile], SC_FLAG_INC | (excl + btotal));
+    }
+    s_prefix = excl;
+    const uint32_t ntiles = ((uint32_t)P + EMIT_TILE - 1) / EMIT_TILE;
+    if (tile == ntiles - 1 && excl + btotal > cap) header->overflow = 1u;
+  }
+  __syncthreads();
+  uint32_t off = s_prefix + woff + inc - tsum;
+
+#pragma unroll
+  for (int i = 0; i < EMIT_IPT; ++i) {
+    const uint32_t c = cnt[i];
+    const uint32_t w = rc[i].z - rc[i].x;
+    if (c != 0 && c <= COOP_THRESHOLD) {
+      uint32_t o = off;
+      for (uint32_t y = rc[i].y; y < rc[i].w; ++y)
+        for (uint32_t x = rc[i].x; x < rc[i].z; ++x) {
+          if (o < cap) { keys[o] = y * grid_w + x; vals[o] = gid[i]; }
+          ++o;
+        }
+    }
+    // large rectangles: the whole warp writes them with lane-strided, coalesced stores
+    uint32_t big = __ballot_sync(0xffffffffu, c > COOP_THRESHOLD);
+    while (big) {
+      const int src = __ffs(big) - 1;
+      big &= big - 1;
+      const uint32_t bc = __shfl_sync(0xffffffffu, c, src);
+      const uint32_t bw = __shfl_sync(0xffffffffu, w, src);
+      const uint32_t bx = __shfl_sync(0xffffffffu, (uint32_t)rc[i].x, src);
+      const uint32_t by = __shfl_sync(0xffffffffu, (uint32_t)rc[i].y, src);
+      const uint32_t bo = __shfl_sync(0xffffffffu, off, src);
+      const uint32_t bg = __shfl_sync(0xffffffffu, gid[i], src);
+      for (uint32_t k = lane; k < bc; k += 32) {
+        const uint32_t o = bo + k;
+        if (o < cap) { keys[o] = (by + k / bw) * grid_w + (bx + k % bw); vals[o] = bg; }
+      }
+    }
+    off += c;
+  }
+}
+
+int launch_emit(const tgr_params& p, const GeomView& g, const BinView& b, uint64_t cap, cudaStream_t s) {
+  const int ntiles = (p.P + EMIT_TILE - 1) / EMIT_TILE;
+  if (ntiles == 0) return 0;
+  cudaMemsetAsync(g.scan_state, 0, (size_t)(ntiles + 1) * 4, s);
+  const uint32_t gw = (p.W + TILE - 1) / TILE;
+  emit_kernel<<<ntiles, EMIT_THREADS, 0, s>>>(p.P, g.order, g.rect, gw, b.key_a, b.val_a,
+                                              (uint32_t)std::min<uint64_t>(cap, 0xffffffffull), g.header, g.scan_state);
+  return check_launch("emit", p.debug != 0, s);
+}
+
+// per-tile [start,end) in the tile-sorted instance list; ranges must be zero-initialised
+__global__ void __launch_bounds__(256) ranges_kernel(const uint32_t* __restrict__ keys, uint32_t cap,
+                                                     const GeomHeader* __restrict__ header, uint2* __restrict__ ranges) {
+  const uint32_t L = min(header->num_rendered, cap);
+  if (header->overflow) return;
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= L) return;
+  const uint32_t cur = keys[idx];
+  if (idx == 0) {
+    ranges[cur].x = 0;
+  } else {
+    const uint32_t prev = keys[idx - 1];
+    if (cur != prev) {
+      ranges[prev].y = idx;
+      ranges[cur].x = idx;
+    }
+  }
+  if (idx == L - 1) ranges[cur].y = L;
+}
+
+int launch_ranges(const tgr_params& p, const GeomView& g, const uint32_t* sorted_keys, const ImageView& im,
+                  uint64_t cap, cudaStream_t s) {
+  const uint32_t T = ((p.W + TILE - 1) / TILE) * ((p.H + TILE - 1) / TILE);
+  cudaMemsetAsync(im.ranges, 0, (size_t)T * sizeof(uint2), s);
+  if (cap == 0) return 0;
+  const unsigned blocks = (unsigned)((cap + 255) / 256);
+  ranges_kernel<<<blocks, 256, 0, s>>>(sorted_keys, (uint32_t)cap, g.header, im.ranges);
+  return check_launch("ranges", p.debug != 0, s);
+}
+
+}  // namespace tgr

@@ -1,0 +1,233 @@
+// c_abi.cu — extern "C" boundary (include/tetgs_rast.h) and stage orchestration.  No torch types.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "common.cuh"
+
+namespace tgr {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what, bool debug, cudaStream_t s) {
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && debug) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return 2;
+  }
+  return 0;
+}
+
+static cudaEvent_t count_event() {
+  static thread_local cudaEvent_t ev[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 15;
+  if (!ev[dev]) cudaEventCreateWithFlags(&ev[dev], cudaEventDisableTiming);
+  return ev[dev];
+}
+
+static int validate(const tgr_params* p, bool need_bin, uint64_t cap) {
+  if (!p) { set_error("null params"); return 1; }
+  if (p->P < 0 || p->W <= 0 || p->H <= 0) { set_error("bad sizes P=%d W=%d H=%d", p->P, p->W, p->H); return 1; }
+  if (p->D < 0 || p->D > 3) { set_error("SH degree %d not in 0..3", p->D); return 1; }
+  if (!p->geom_buffer || p->geom_bytes < tgr_geom_bytes(p->P)) { set_error("geom buffer too small"); return 1; }
+  if (!p->image_buffer || p->image_bytes < tgr_image_bytes(p->W, p->H)) { set_error("image buffer too small"); return 1; }
+  if (need_bin && (!p->binning_buffer || p->binning_bytes < tgr_binning_bytes(p->P, cap))) {
+    set_error("binning buffer too small for capacity %llu", (unsigned long long)cap);
+    return 1;
+  }
+  if ((p->W + TILE - 1) / TILE > 65535 || (p->H + TILE - 1) / TILE > 65535) { set_error("image too large"); return 1; }
+  return 0;
+}
+
+}  // namespace tgr
+
+using namespace tgr;
+
+extern "C" {
+
+int tgr_abi_version(void) { return TGR_ABI_VERSION; }
+const char* tgr_last_error(void) { return g_err; }
+
+uint64_t tgr_geom_bytes(int32_t P) { return carve_geom(nullptr, P).bytes; }
+uint64_t tgr_image_bytes(int32_t W, int32_t H) { return carve_image(nullptr, W, H).bytes; }
+uint64_t tgr_binning_bytes(int32_t P, uint64_t cap) { return carve_bin(nullptr, P, cap).bytes; }
+uint64_t tgr_sort_temp_bytes(uint64_t n) { return sort_temp_bytes(n); }
+
+int tgr_forward_preprocess(const tgr_params* p, const tgr_binding* bind, void* stream) {
+  if (int rc = validate(p, false, 0)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p->P == 0) {
+    if (p->host_num_rendered) *p->host_num_rendered = 0;
+    return 0;
+  }
+  if (!bind) {
+    if (!p->means3D || !p->opacities) { set_error("means3D/opacities missing"); return 1; }
+    if (!p->cov3D_precomp && (!p->scales || !p->rotations)) { set_error("need scales+rotations or cov3D_precomp"); return 1; }
+  }
+  if (!p->colors_precomp && (!p->shs || p->M < (p->D + 1) * (p->D + 1))) { set_error("need colors_precomp or shs with M >= (D+1)^2"); return 1; }
+  GeomView g = carve_geom(p->geom_buffer, p->P);
+  cudaMemsetAsync(g.header, 0, sizeof(GeomHeader), s);
+  if (int rc = launch_preprocess(*p, bind, g, s)) return rc;
+  if (p->host_num_rendered) {
+    cudaMemcpyAsync(p->host_num_rendered, &g.header->num_rendered, sizeof(uint32_t), cudaMemcpyDeviceToHost, s);
+    cudaEventRecord(count_event(), s);
+  }
+  // (depth bits, id) order of the Gaussians: positive floats compare like their bit patterns; bit 31 is 0
+  bool in_b = false;
+  if (int rc = launch_sort_pairs((uint64_t)p->P, nullptr, g.depth_key, g.order, g.key_alt, g.val_alt, true, 0, 32,
+                                 g.sort_temp, s, &in_b)) return rc;
+  if (in_b) { set_error("internal: depth sort must end in buffer A"); return 3; }
+  return check_launch("forward_preprocess", p->debug != 0, s);
+}
+
+int tgr_wait_num_rendered(void) {
+  cudaError_t e = cudaEventSynchronize(count_event());
+  if (e != cudaSuccess) { set_error("wait_num_rendered: %s", cudaGetErrorString(e)); return 2; }
+  return 0;
+}
+
+static const uint32_t* sorted_vals(const tgr_params* p, const BinView& b, bool* in_b_out = nullptr) {
+  const uint32_t T = (uint32_t)((p->W + TILE - 1) / TILE) * ((p->H + TILE - 1) / TILE);
+  SortPlan plan = make_sort_plan(0, tile_bits(T));
+  bool in_b = (plan.npasses & 1) != 0;
+  if (in_b_out) *in_b_out = in_b;
+  return in_b ? b.val_b : b.val_a;
+}
+
+int tgr_forward_render(const tgr_params* p, uint64_t cap, void* stream) {
+  if (int rc = validate(p, true, cap)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GeomView g = carve_geom(p->geom_buffer, p->P);
+  BinView b = carve_bin(p->binning_buffer, p->P, cap);
+  ImageView im = carve_image(p->image_buffer, p->W, p->H);
+  const uint32_t T = (uint32_t)((p->W + TILE - 1) / TILE) * ((p->H + TILE - 1) / TILE);
+  if (p->P > 0 && cap > 0) {
+    if (int rc = launch_emit(*p, g, b, cap, s)) return rc;
+    bool in_b = false;
+    if (int rc = launch_sort_pairs(cap, &g.header->num_rendered, b.key_a, b.val_a, b.key_b, b.val_b, false, 0,
+                                   tile_bits(T), b.sort_temp, s, &in_b)) return rc;
+    if (int rc = launch_ranges(*p, g, in_b ? b.key_b : b.key_a, im, cap, s)) return rc;
+  } else {
+    cudaMemsetAsync(im.ranges, 0, (size_t)T * sizeof(uint2), s);
+  }
+  const uint32_t* plist = sorted_vals(p, b);
+  if (int rc = launch_blend_fwd(*p, g, plist, im, s)) return rc;
+  return check_launch("forward_render", p->debug != 0, s);
+}
+
+int tgr_backward(const tgr_params* p, const tgr_binding* bind, uint64_t cap, void* stream) {
+  if (int rc = validate(p, true, cap)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p->P == 0) return 0;
+  if (!p->dL_dout_color) { set_error("dL_dout_color missing"); return 1; }
+  GeomView g = carve_geom(p->geom_buffer, p->P);
+  BinView b = carve_bin(p->binning_buffer, p->P, cap);
+  ImageView im = carve_image(p->image_buffer, p->W, p->H);
+  cudaMemsetAsync(b.grad_acc, 0, (size_t)p->P * GRAD_ACC * sizeof(float), s);
+  if (int rc = launch_blend_bwd(*p, g, sorted_vals(p, b), im, b.grad_acc, s)) return rc;
+  if (int rc = launch_preprocess_bwd(*p, bind, g, b.grad_acc, s)) return rc;
+  return check_launch("backward", p->debug != 0, s);
+}
+
+int tgr_read_header(const void* geom_buffer, uint32_t out[4], void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GeomView g = carve_geom(const_cast<void*>(geom_buffer), 0);
+  cudaError_t e = cudaMemcpyAsync(out, g.header, 16, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) { set_error("read_header: %s", cudaGetErrorString(e)); return 2; }
+  return 0;
+}
+
+int tgr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, void* stream) {
+  return launch_mark_visible(P, means3D, viewmatrix, projmatrix, present, static_cast<cudaStream_t>(stream));
+}
+
+int tgr_sort_pairs_u32(uint64_t n, uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
+                       int begin_bit, int end_bit, void* temp, uint64_t temp_bytes, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (temp_bytes < sort_temp_bytes(n)) { set_error("sort temp too small"); return 1; }
+  bool in_b = false;
+  if (int rc = launch_sort_pairs(n, nullptr, keys_in, vals_in, keys_out, vals_out, false, begin_bit, end_bit,
+                                 static_cast<uint32_t*>(temp), s, &in_b)) return rc;
+  if (!in_b && n > 0) {  // even number of passes: result sits in the input buffers
+    cudaMemcpyAsync(keys_out, keys_in, n * 4, cudaMemcpyDeviceToDevice, s);
+    cudaMemcpyAsync(vals_out, vals_in, n * 4, cudaMemcpyDeviceToDevice, s);
+  }
+  return check_launch("sort_pairs_u32", false, s);
+}
+
+// ---- parity helpers -------------------------------------------------------------------------------
+__global__ void export_keys_kernel(uint32_t R, const uint32_t* __restrict__ tile_keys, const uint32_t* __restrict__ ids,
+                                   const float4* __restrict__ rgb_depth, uint64_t* __restrict__ keys_out,
+                                   uint32_t* __restrict__ ids_out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R) return;
+  uint32_t id = ids[i];
+  if (keys_out) keys_out[i] = ((uint64_t)tile_keys[i] << 32) | (uint64_t)__float_as_uint(rgb_depth[id].w);
+  if (ids_out) ids_out[i] = id;
+}
+
+int tgr_export_binning(const tgr_params* p, uint64_t R, uint64_t* keys, uint32_t* ids, uint32_t* ranges, void* stream) {
+  if (int rc = validate(p, true, R)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GeomView g = carve_geom(p->geom_buffer, p->P);
+  BinView b = carve_bin(p->binning_buffer, p->P, R);
+  ImageView im = carve_image(p->image_buffer, p->W, p->H);
+  bool in_b = false;
+  const uint32_t* vals = sorted_vals(p, b, &in_b);
+  const uint32_t* tk = in_b ? b.key_b : b.key_a;
+  if (R > 0 && (keys || ids))
+    export_keys_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>((uint32_t)R, tk, vals, g.rgb_depth, keys, ids);
+  if (ranges) {
+    const uint32_t T = (uint32_t)((p->W + TILE - 1) / TILE) * ((p->H + TILE - 1) / TILE);
+    cudaMemcpyAsync(ranges, im.ranges, (size_t)T * 8, cudaMemcpyDeviceToDevice, s);
+  }
+  return check_launch("export_binning", true, s);
+}
+
+__global__ void export_geom_kernel(int P, GeomView g, float* depth, float* xy, float* co, float* rgb, uint32_t* tiles) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const ushort4 rc = g.rect[i];
+  const bool vis = (rc.z - rc.x) * (rc.w - rc.y) != 0;
+  const float4 cd = g.rgb_depth[i];
+  const float4 c = g.conic_opacity[i];
+  const float2 m = g.xy[i];
+  if (depth) depth[i] = vis ? cd.w : 0.f;
+  if (xy) { xy[2 * i] = vis ? m.x : 0.f; xy[2 * i + 1] = vis ? m.y : 0.f; }
+  if (co) { co[4 * i] = vis ? c.x : 0.f; co[4 * i + 1] = vis ? c.y : 0.f; co[4 * i + 2] = vis ? c.z : 0.f; co[4 * i + 3] = vis ? c.w : 0.f; }
+  if (rgb) { rgb[3 * i] = vis ? cd.x : 0.f; rgb[3 * i + 1] = vis ? cd.y : 0.f; rgb[3 * i + 2] = vis ? cd.z : 0.f; }
+  if (tiles) tiles[i] = (uint32_t)(rc.z - rc.x) * (uint32_t)(rc.w - rc.y);
+}
+
+int tgr_export_geom(const tgr_params* p, float* depth, float* xy, float* conic_opacity, float* rgb,
+                    uint32_t* tiles_touched, void* stream) {
+  if (int rc = validate(p, false, 0)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p->P == 0) return 0;
+  GeomView g = carve_geom(p->geom_buffer, p->P);
+  export_geom_kernel<<<(p->P + 255) / 256, 256, 0, s>>>(p->P, g, depth, xy, conic_opacity, rgb, tiles_touched);
+  return check_launch("export_geom", true, s);
+}
+
+int tgr_export_image_state(const tgr_params* p, float* final_T, uint32_t* n_contrib, void* stream) {
+  if (int rc = validate(p, false, 0)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ImageView im = carve_image(p->image_buffer, p->W, p->H);
+  const size_t N = (size_t)p->W * p->H;
+  if (final_T) cudaMemcpyAsync(final_T, im.final_T, N * 4, cudaMemcpyDeviceToDevice, s);
+  if (n_contrib) cudaMemcpyAsync(n_contrib, im.n_contrib, N * 4, cudaMemcpyDeviceToDevice, s);
+  return check_launch("export_image_state", true, s);
+}
+
+}  // extern "C"

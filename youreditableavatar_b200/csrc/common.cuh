@@ -1,0 +1,267 @@
+// common.cuh — shared declarations for the sm_100a TetGS rasterizer kernels.
+// Workspace layouts, small fp32 3x3 algebra and launch helpers.  No torch, no glm, no CUB.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/tetgs_rast.h"
+
+namespace tgr {
+
+constexpr int TILE = TGR_TILE;          // 16x16 pixel tiles (reference config.h:16-17)
+constexpr int TILE_PIX = TILE * TILE;   // 256
+constexpr int NUM_SM = 148;             // B200
+
+__host__ __device__ inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------
+// Radix sort plan / temp layout (sort.cu)
+// ---------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_IPT = 16;
+constexpr int RS_TILE = RS_THREADS * RS_IPT;  // 4096 pairs per CTA
+constexpr int RS_BINS = 256;
+constexpr int RS_MAX_PASSES = 4;
+
+struct SortPlan {
+  int npasses;
+  int begin[RS_MAX_PASSES];
+  int bits[RS_MAX_PASSES];
+};
+
+__host__ __device__ inline SortPlan make_sort_plan(int begin_bit, int end_bit) {
+  SortPlan pl{};
+  int nb = end_bit - begin_bit;
+  if (nb <= 0) { pl.npasses = 0; return pl; }
+  int np = (nb + 7) / 8;
+  int per = (nb + np - 1) / np;
+  pl.npasses = np;
+  int b = begin_bit;
+  for (int i = 0; i < np; ++i) {
+    int w = (end_bit - b) < per ? (end_bit - b) : per;
+    pl.begin[i] = b;
+    pl.bits[i] = w;
+    b += w;
+  }
+  return pl;
+}
+
+// temp: [ghist: RS_MAX_PASSES*256 u32][tickets: 32 u32][lookback: RS_MAX_PASSES * ntiles * 256 u32]
+__host__ __device__ inline uint64_t sort_ntiles(uint64_t n) { return (n + RS_TILE - 1) / RS_TILE; }
+__host__ __device__ inline uint64_t sort_temp_bytes(uint64_t n) {
+  uint64_t words = (uint64_t)RS_MAX_PASSES * RS_BINS + 32 + (uint64_t)RS_MAX_PASSES * sort_ntiles(n) * RS_BINS;
+  return align_up(words * 4, 128);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Workspace layouts.  All sections 128-byte aligned.  The same carve is replayed in the backward,
+// so sizes are pure functions of (P), (W,H), (P,R) — as in rasterizer_impl.cu:155-194.
+// ---------------------------------------------------------------------------------------------
+struct GeomHeader {        // 128 bytes
+  uint32_t num_rendered;   // total (Gaussian,tile) instances = sum of tiles touched
+  uint32_t overflow;       // set when num_rendered > capacity of the binning buffer
+  uint32_t num_visible;    // Gaussians with radius > 0
+  uint32_t emit_ticket;    // dynamic block id for the emit kernel's chained scan
+  uint32_t pad[28];
+};
+
+struct GeomView {
+  GeomHeader* header;
+  uint32_t* depth_key;     // [P] fp32 bits of view-space depth (0x7fffffff when culled); sort buffer A keys
+  uint32_t* order;         // [P] Gaussian ids in (depth, id) order; sort buffer A values
+  uint32_t* key_alt;       // [P] sort buffer B keys
+  uint32_t* val_alt;       // [P] sort buffer B values
+  ushort4* rect;           // [P] tile rectangle (x0,y0,x1,y1); all zero when culled
+  float2* xy;              // [P] pixel-space mean
+  float4* conic_opacity;   // [P] inverse 2D covariance (xx,xy,yy) + opacity
+  float4* rgb_depth;       // [P] colour + view-space depth
+  uint8_t* clamped;        // [P] bit c set when colour channel c was clamped at 0
+  uint32_t* scan_state;    // [ceil(P/EMIT_TILE)+1] chained-scan state of the emit kernel
+  uint32_t* sort_temp;     // sort_temp_bytes(P)
+  uint64_t bytes;
+};
+
+constexpr int EMIT_THREADS = 256;
+constexpr int EMIT_IPT = 4;
+constexpr int EMIT_TILE = EMIT_THREADS * EMIT_IPT;
+
+template <typename T>
+__host__ __device__ inline T* carve(char*& p, uint64_t count) {
+  uint64_t a = align_up((uint64_t)(uintptr_t)p, 128);
+  T* r = reinterpret_cast<T*>(a);
+  p = reinterpret_cast<char*>(a) + count * sizeof(T);
+  return r;
+}
+
+__host__ __device__ inline GeomView carve_geom(void* base, int32_t P) {
+  GeomView g;
+  char* p = static_cast<char*>(base);
+  uint64_t n = (uint64_t)(P > 0 ? P : 0);
+  g.header = carve<GeomHeader>(p, 1);
+  g.depth_key = carve<uint32_t>(p, n);
+  g.order = carve<uint32_t>(p, n);
+  g.key_alt = carve<uint32_t>(p, n);
+  g.val_alt = carve<uint32_t>(p, n);
+  g.rect = carve<ushort4>(p, n);
+  g.xy = carve<float2>(p, n);
+  g.conic_opacity = carve<float4>(p, n);
+  g.rgb_depth = carve<float4>(p, n);
+  g.clamped = carve<uint8_t>(p, n);
+  g.scan_state = carve<uint32_t>(p, (n + EMIT_TILE - 1) / EMIT_TILE + 1);
+  g.sort_temp = carve<uint32_t>(p, sort_temp_bytes(n) / 4);
+  g.bytes = (uint64_t)(p - static_cast<char*>(base)) + 128;
+  return g;
+}
+
+struct ImageView {
+  float* final_T;        // [N] transmittance left after blending
+  uint32_t* n_contrib;   // [N] 1-based index in the tile list of the last blended Gaussian
+  uint2* ranges;         // [T] [start,end) of each tile in the sorted instance list
+  uint32_t* tile_last;   // [T] max n_contrib over the pixels of the tile (lets the backward skip the tail)
+  uint64_t bytes;
+};
+
+__host__ __device__ inline ImageView carve_image(void* base, int32_t W, int32_t H) {
+  ImageView v;
+  char* p = static_cast<char*>(base);
+  uint64_t N = (uint64_t)W * H;
+  uint64_t T = (uint64_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+  v.final_T = carve<float>(p, N);
+  v.n_contrib = carve<uint32_t>(p, N);
+  v.ranges = carve<uint2>(p, T);
+  v.tile_last = carve<uint32_t>(p, T);
+  v.bytes = (uint64_t)(p - static_cast<char*>(base)) + 128;
+  return v;
+}
+
+struct BinView {
+  uint32_t* key_a;   // [R] tile id per instance (sort buffer A)
+  uint32_t* val_a;   // [R] Gaussian id per instance
+  uint32_t* key_b;   // [R] sort buffer B
+  uint32_t* val_b;
+  uint32_t* sort_temp;
+  float* grad_acc;   // [P*GRAD_ACC] backward accumulators (see blend_bwd.cu); lives here so it is
+                     // allocated with the call that needs it and freed with the autograd node
+  uint64_t bytes;
+};
+
+constexpr int GRAD_ACC = 12;  // mean2D.xy, conic.xyz, opacity, rgb, depth, 2 pad
+
+__host__ __device__ inline BinView carve_bin(void* base, int32_t P, uint64_t R) {
+  BinView b;
+  char* p = static_cast<char*>(base);
+  b.key_a = carve<uint32_t>(p, R);
+  b.val_a = carve<uint32_t>(p, R);
+  b.key_b = carve<uint32_t>(p, R);
+  b.val_b = carve<uint32_t>(p, R);
+  b.sort_temp = carve<uint32_t>(p, sort_temp_bytes(R) / 4);
+  b.grad_acc = carve<float>(p, (uint64_t)(P > 0 ? P : 0) * GRAD_ACC);
+  b.bytes = (uint64_t)(p - static_cast<char*>(base)) + 128;
+  return b;
+}
+
+// number of bits needed to represent tile ids 0..T-1
+__host__ __device__ inline int tile_bits(uint32_t T) {
+  int b = 0;
+  while ((1u << b) < T && b < 31) ++b;
+  return b < 1 ? 1 : b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3x3 column-major algebra with exactly the scalar expression shapes glm::mat3 expands to
+// (third_party/glm/glm/detail/type_mat3x3.inl:486-519), so that nvcc's FMA contraction — and therefore
+// every fp32 rounding — matches the reference build.  m[c][r]: column c, row r.
+// ---------------------------------------------------------------------------------------------
+struct M3 {
+  float m[3][3];
+};
+
+__device__ __forceinline__ M3 m3(float a0, float a1, float a2, float b0, float b1, float b2, float c0, float c1,
+                                 float c2) {
+  M3 r;
+  r.m[0][0] = a0; r.m[0][1] = a1; r.m[0][2] = a2;
+  r.m[1][0] = b0; r.m[1][1] = b1; r.m[1][2] = b2;
+  r.m[2][0] = c0; r.m[2][1] = c1; r.m[2][2] = c2;
+  return r;
+}
+
+__device__ __forceinline__ M3 m3_mul(const M3& A, const M3& B) {
+  M3 R;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      R.m[c][r] = A.m[0][r] * B.m[c][0] + A.m[1][r] * B.m[c][1] + A.m[2][r] * B.m[c][2];
+  return R;
+}
+
+__device__ __forceinline__ M3 m3_T(const M3& A) {
+  M3 R;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) R.m[c][r] = A.m[r][c];
+  return R;
+}
+
+// p' = M p (+ translation) for the column-major 4x4 camera matrices (auxiliary.h:58-77)
+__device__ __forceinline__ float3 xform4x3(const float3& p, const float* __restrict__ m) {
+  float3 t = {
+      m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12],
+      m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+      m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14],
+  };
+  return t;
+}
+__device__ __forceinline__ float4 xform4x4(const float3& p, const float* __restrict__ m) {
+  float4 t = {
+      m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12],
+      m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+      m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14],
+      m[3] * p.x + m[7] * p.y + m[11] * p.z + m[15],
+  };
+  return t;
+}
+
+// NDC -> pixel; evaluated in double exactly like auxiliary.h:41-44 (its literals are doubles)
+__device__ __forceinline__ float ndc2pix(float v, int S) { return ((v + 1.0) * S - 1.0) * 0.5; }
+
+// Tile rectangle touched by a splat of integer radius r centred at p (auxiliary.h:46-56)
+__device__ __forceinline__ void tile_rect(const float2 p, int r, uint32_t gx, uint32_t gy, uint2& rmin, uint2& rmax) {
+  rmin = {min(gx, (uint32_t)max((int)0, (int)((p.x - r) / TILE))), min(gy, (uint32_t)max((int)0, (int)((p.y - r) / TILE)))};
+  rmax = {min(gx, (uint32_t)max((int)0, (int)((p.x + r + TILE - 1) / TILE))),
+          min(gy, (uint32_t)max((int)0, (int)((p.y + r + TILE - 1) / TILE)))};
+}
+
+// SH basis constants (auxiliary.h:22-39)
+__device__ constexpr float SH_C0 = 0.28209479177387814f;
+__device__ constexpr float SH_C1 = 0.4886025119029199f;
+__device__ constexpr float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                       -1.0925484305920792f, 0.5462742152960396f};
+__device__ constexpr float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                       0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
+                                       -0.5900435899266435f};
+
+// ---------------------------------------------------------------------------------------------
+// host-side plumbing
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int check_launch(const char* what, bool debug, cudaStream_t s);
+
+// stage launchers (each in its own .cu)
+int launch_preprocess(const tgr_params& p, const tgr_binding* bind, const GeomView& g, cudaStream_t s);
+int launch_sort_pairs(uint64_t n_host, const uint32_t* n_dev, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b,
+                      uint32_t* vals_b, bool iota_vals, int begin_bit, int end_bit, uint32_t* temp, cudaStream_t s,
+                      bool* result_in_b);
+int launch_emit(const tgr_params& p, const GeomView& g, const BinView& b, uint64_t cap, cudaStream_t s);
+int launch_ranges(const tgr_params& p, const GeomView& g, const uint32_t* sorted_keys, const ImageView& im,
+                  uint64_t cap, cudaStream_t s);
+int launch_blend_fwd(const tgr_params& p, const GeomView& g, const uint32_t* point_list, const ImageView& im,
+                     cudaStream_t s);
+int launch_blend_bwd(const tgr_params& p, const GeomView& g, const uint32_t* point_list, const ImageView& im,
+                     float* grad_acc, cudaStream_t s);
+int launch_preprocess_bwd(const tgr_params& p, const tgr_binding* bind, const GeomView& g, const float* grad_acc,
+                          cudaStream_t s);
+int launch_mark_visible(int32_t P, const float* means3D, const float* view, const float* proj, uint8_t* present,
+                        cudaStream_t s);
+
+}  // namespace tgr

@@ -1,0 +1,245 @@
+// sort.cu — hand-written onesweep LSD radix sort for (u32 key, u32 value) pairs on sm_100a.
+//
+// Replaces cub::DeviceRadixSort::SortPairs at rasterizer_impl.cu:303-308 and simple_knn.cu:207-213.
+// The reference sorts 64-bit (tile<<32 | depth) keys in six 8-bit passes over all R instances.  Here
+// the same total order (tile, depth bits, Gaussian id) is produced by two *stable* 32-bit sorts:
+// P Gaussians by depth bits, then R instances by tile id (ceil(log2 T) bits) — see DESIGN.md.
+//
+// One kernel per digit pass ("onesweep"): a CTA takes a 4096-pair tile via an atomic ticket, ranks
+// its keys with warp-level match.any multi-split (stable in (warp, item, lane) order), obtains its
+// per-digit global offset with a decoupled look-back over the preceding tiles, reorders the tile in
+// shared memory and writes digit-contiguous runs with coalesced stores.  An upfront histogram kernel
+// produces the per-pass digit totals for all passes in one read of the keys.
+#include <algorithm>
+#include "common.cuh"
+
+namespace tgr {
+
+constexpr uint32_t LB_FLAG_AGG = 1u << 30;   // tile aggregate available
+constexpr uint32_t LB_FLAG_INC = 2u << 30;   // inclusive prefix available
+constexpr uint32_t LB_VALUE = (1u << 30) - 1;
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- upfront digit histograms for every pass -------------------------------------------------
+__global__ void __launch_bounds__(256) radix_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n_host,
+                                                         const uint32_t* __restrict__ n_dev, SortPlan plan,
+                                                         uint32_t* __restrict__ ghist) {
+  __shared__ uint32_t sh[RS_MAX_PASSES * RS_BINS];
+  for (int i = threadIdx.x; i < RS_MAX_PASSES * RS_BINS; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  uint32_t n = n_dev ? min(*n_dev, n_host) : n_host;
+  const uint32_t stride = gridDim.x * blockDim.x * 4;
+  for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) * 4; base < n; base += stride) {
+    uint32_t k[4];
+    int cnt;
+    if (base + 4 <= n) {
+      uint4 v = *reinterpret_cast<const uint4*>(keys + base);
+      k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w;
+      cnt = 4;
+    } else {
+      cnt = n - base;
+      for (int j = 0; j < cnt; ++j) k[j] = keys[base + j];
+    }
+    for (int j = 0; j < cnt; ++j) {
+#pragma unroll
+      for (int ps = 0; ps < RS_MAX_PASSES; ++ps)
+        if (ps < plan.npasses) atomicAdd(&sh[ps * RS_BINS + ((k[j] >> plan.begin[ps]) & ((1u << plan.bits[ps]) - 1))], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < plan.npasses * RS_BINS; i += blockDim.x)
+    if (sh[i]) atomicAdd(&ghist[i], sh[i]);
+}
+
+// ---- one digit pass ------------------------------------------------------------------------------
+template <bool IOTA>
+__global__ void __launch_bounds__(RS_THREADS) radix_pass_kernel(
+    const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
+    uint32_t* __restrict__ vals_out, uint32_t n_host, const uint32_t* __restrict__ n_dev, int begin_bit, int nbits,
+    const uint32_t* __restrict__ ghist, uint32_t* __restrict__ ticket, uint32_t* __restrict__ lookback) {
+  extern __shared__ uint32_t smem[];
+  uint32_t* s_keys = smem;                          // [RS_TILE]
+  uint32_t* s_vals = s_keys + RS_TILE;              // [RS_TILE]
+  uint32_t* s_whist = s_vals + RS_TILE;             // [8][256]
+  uint32_t* s_goff = s_whist + (RS_THREADS / 32) * RS_BINS;  // [256]
+  uint32_t* s_lstart = s_goff + RS_BINS;            // [256]
+  uint32_t* s_scan = s_lstart + RS_BINS;            // [16]
+  __shared__ uint32_t s_tile;
+
+  const uint32_t n = n_dev ? min(*n_dev, n_host) : n_host;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = RS_THREADS / 32;
+
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  for (int i = tid; i < NW * RS_BINS; i += RS_THREADS) s_whist[i] = 0;
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint64_t base64 = (uint64_t)tile * RS_TILE;
+  if (base64 >= n) return;
+  const uint32_t base = (uint32_t)base64;
+  const uint32_t count = min((uint32_t)RS_TILE, n - base);
+  const uint32_t mask = (1u << nbits) - 1u;
+
+  // ---- load keys, warp-striped: item i of lane l is element wbase + 32*i + l -----------------
+  const uint32_t wbase = base + warp * (32 * RS_IPT);
+  uint32_t key[RS_IPT];
+#pragma unroll
+  for (int i = 0; i < RS_IPT; ++i) {
+    const uint32_t idx = wbase + i * 32 + lane;
+    key[i] = idx < n ? keys_in[idx] : 0xffffffffu;
+  }
+
+  // ---- stable rank within the warp ---------------------------------------------------------------
+  uint16_t rnk[RS_IPT];
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  uint32_t* whist = s_whist + warp * RS_BINS;
+#pragma unroll
+  for (int i = 0; i < RS_IPT; ++i) {
+    const uint32_t idx = wbase + i * 32 + lane;
+    const uint32_t d = (key[i] >> begin_bit) & mask;
+    const uint32_t vm = __ballot_sync(0xffffffffu, idx < n);
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const uint32_t old = whist[d];
+    __syncwarp();
+    rnk[i] = (uint16_t)(old + __popc(peers & lt_mask));
+    if (lane == (__ffs(peers) - 1)) whist[d] = old + __popc(peers & vm);
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // ---- per digit (thread == digit): exclusive scan over the warps, tile total -------------------
+  uint32_t total = 0;
+  {
+    const int d = tid;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const uint32_t t = s_whist[w * RS_BINS + d];
+      s_whist[w * RS_BINS + d] = total;
+      total += t;
+    }
+  }
+
+  // ---- decoupled look-back: exclusive prefix of this digit over preceding tiles ------------------
+  uint32_t excl = 0;
+  {
+    uint32_t* lb = lookback + (uint64_t)tile * RS_BINS + tid;
+    if (tile == 0) {
+      st_volatile_u32(lb, LB_FLAG_INC | total);
+    } else {
+      st_volatile_u32(lb, LB_FLAG_AGG | total);
+      const uint32_t* q = lb - RS_BINS;
+      while (true) {
+        uint32_t v = ld_volatile_u32(q);
+        if ((v & ~LB_VALUE) == 0) continue;  // predecessor not published yet
+        excl += v & LB_VALUE;
+        if (v & LB_FLAG_INC) break;
+        q -= RS_BINS;
+      }
+      st_volatile_u32(lb, LB_FLAG_INC | (excl + total));
+    }
+  }
+
+  // ---- block exclusive scans over the 256 digits: tile-local start, global digit base ------------
+  {
+    const uint32_t gh = ghist[tid];
+    uint32_t a = total, b = gh;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t ta = __shfl_up_sync(0xffffffffu, a, o);
+      uint32_t tb = __shfl_up_sync(0xffffffffu, b, o);
+      if (lane >= o) { a += ta; b += tb; }
+    }
+    if (lane == 31) { s_scan[warp] = a; s_scan[8 + warp] = b; }
+    __syncthreads();
+    uint32_t offa = 0, offb = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+      if (w < warp) { offa += s_scan[w]; offb += s_scan[8 + w]; }
+    const uint32_t lstart = offa + a - total;   // exclusive
+    const uint32_t gbase = offb + b - gh;       // exclusive
+    s_lstart[tid] = lstart;
+    s_goff[tid] = gbase + excl - lstart;
+  }
+  __syncthreads();
+
+  // ---- scatter keys into tile-sorted order in shared memory --------------------------------------
+  uint16_t pos[RS_IPT];
+#pragma unroll
+  for (int i = 0; i < RS_IPT; ++i) {
+    const uint32_t idx = wbase + i * 32 + lane;
+    const uint32_t d = (key[i] >> begin_bit) & mask;
+    const uint32_t ps = s_lstart[d] + s_whist[warp * RS_BINS + d] + rnk[i];
+    pos[i] = (uint16_t)ps;
+    if (idx < n) s_keys[ps] = key[i];
+  }
+  // values ride along
+#pragma unroll
+  for (int i = 0; i < RS_IPT; ++i) {
+    const uint32_t idx = wbase + i * 32 + lane;
+    if (idx < n) s_vals[pos[i]] = IOTA ? idx : vals_in[idx];
+  }
+  __syncthreads();
+
+  // ---- coalesced write-out: position p of the tile goes to s_goff[digit] + p --------------------
+#pragma unroll
+  for (int j = 0; j < RS_IPT; ++j) {
+    const uint32_t ps = j * RS_THREADS + tid;
+    if (ps < count) {
+      const uint32_t k = s_keys[ps];
+      const uint32_t d = (k >> begin_bit) & mask;
+      const uint32_t o = s_goff[d] + ps;
+      keys_out[o] = k;
+      vals_out[o] = s_vals[ps];
+    }
+  }
+}
+
+constexpr size_t RS_SMEM = (size_t)(2 * RS_TILE + (RS_THREADS / 32) * RS_BINS + 2 * RS_BINS + 16) * 4;
+
+int launch_sort_pairs(uint64_t n_host, const uint32_t* n_dev, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b,
+                      uint32_t* vals_b, bool iota_vals, int begin_bit, int end_bit, uint32_t* temp, cudaStream_t s,
+                      bool* result_in_b) {
+  SortPlan plan = make_sort_plan(begin_bit, end_bit);
+  if (result_in_b) *result_in_b = (plan.npasses & 1) != 0;
+  if (n_host == 0 || plan.npasses == 0) return 0;
+  if (n_host >= (1ull << 30)) { set_error("sort: n=%llu exceeds 2^30", (unsigned long long)n_host); return 1; }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(radix_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM);
+    cudaFuncSetAttribute(radix_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM);
+    attr_set = true;
+  }
+  const uint64_t ntiles = sort_ntiles(n_host);
+  uint32_t* ghist = temp;
+  uint32_t* tickets = temp + RS_MAX_PASSES * RS_BINS;
+  uint32_t* lookback = tickets + 32;
+  const size_t zero_bytes = ((size_t)RS_MAX_PASSES * RS_BINS + 32 + (size_t)plan.npasses * ntiles * RS_BINS) * 4;
+  cudaMemsetAsync(temp, 0, zero_bytes, s);
+  int hist_blocks = (int)std::min<uint64_t>((n_host + 256 * 16 - 1) / (256 * 16), (uint64_t)NUM_SM * 8);
+  radix_hist_kernel<<<hist_blocks, 256, 0, s>>>(keys_a, (uint32_t)n_host, n_dev, plan, ghist);
+  const uint32_t* kin = keys_a; const uint32_t* vin = vals_a;
+  uint32_t* kout = keys_b; uint32_t* vout = vals_b;
+  for (int ps = 0; ps < plan.npasses; ++ps) {
+    uint32_t* lb = lookback + (uint64_t)ps * ntiles * RS_BINS;
+    if (ps == 0 && iota_vals)
+      radix_pass_kernel<true><<<(unsigned)ntiles, RS_THREADS, RS_SMEM, s>>>(
+          kin, vin, kout, vout, (uint32_t)n_host, n_dev, plan.begin[ps], plan.bits[ps], ghist + ps * RS_BINS, tickets + ps, lb);
+    else
+      radix_pass_kernel<false><<<(unsigned)ntiles, RS_THREADS, RS_SMEM, s>>>(
+          kin, vin, kout, vout, (uint32_t)n_host, n_dev, plan.begin[ps], plan.bits[ps], ghist + ps * RS_BINS, tickets + ps, lb);
+    const uint32_t* tk = kin; const uint32_t* tv = vin;
+    kin = kout; vin = vout;
+    kout = const_cast<uint32_t*>(tk); vout = const_cast<uint32_t*>(tv);
+  }
+  return check_launch("radix_sort", false, s);
+}
+
+}  // namespace tgr
