@@ -4,8 +4,12 @@
 // Differences in *how* (results agree to fp32 rounding / atomics order):
 //   * the replay starts at the tile's last contributing list entry (tile_last, written by the forward)
 //     instead of the end of the tile list, so the never-blended tail is not even staged;
-//   * per-Gaussian partial gradients are reduced across the warp with shuffles and committed with one
-//     lane's atomics per warp (the reference issues 9 global float atomics per (pixel, Gaussian) pair);
+//   * same warp-block footprint culling as the forward (blend_fwd.cu): a warp only replays the Gaussians
+//     that can reach alpha >= 1/255 inside its 8x4 pixel block, and only those at or before the block's own
+//     last contributor;
+//   * per-Gaussian partial gradients are reduced across the warp with a recursive-halving butterfly
+//     (16 shuffles for up to 16 quantities instead of 5 per quantity) and committed with ONE red.global
+//     instruction per (warp, Gaussian) — the reference issues 9 global float atomics per (pixel, Gaussian);
 //   * all per-Gaussian 2D gradients land in one packed accumulator row grad_acc[g][12]
 //     {dmean2D.x, dmean2D.y, dconic.xx, dconic.xy, dconic.yy, dopacity, dr, dg, db, dz, -, -};
 //   * extras: gradients of the depth / alpha images flow through the same recurrence.
@@ -15,10 +19,59 @@ namespace tgr {
 
 constexpr int BB = 256;
 
+__device__ __forceinline__ uint32_t block_mask_b(float x, float y, float hx, float hy, float tile_x0, float tile_y0) {
+  if (!(hx >= 0.f)) return 0u;
+  const float fx0 = ceilf(x - hx) - tile_x0, fx1 = floorf(x + hx) - tile_x0;
+  const float fy0 = ceilf(y - hy) - tile_y0, fy1 = floorf(y + hy) - tile_y0;
+  if (fx1 < 0.f || fy1 < 0.f || fx0 > 15.f || fy0 > 15.f || fx0 > fx1 || fy0 > fy1) return 0u;
+  const int x0 = (int)fmaxf(fx0, 0.f), x1 = (int)fminf(fx1, 15.f);
+  const int y0 = (int)fmaxf(fy0, 0.f), y1 = (int)fminf(fy1, 15.f);
+  const uint32_t colm = ((x0 < 8) ? 1u : 0u) | ((x1 >= 8) ? 2u : 0u);
+  const int r0 = y0 >> 2, r1 = y1 >> 2;
+  uint32_t m = 0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+    if (r >= r0 && r <= r1) m |= colm << (2 * r);
+  return m;
+}
+
+// Sums 16 per-lane quantities over the warp; afterwards lane l holds the total of quantity l>>1.
+__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool hi = lane & 16;
+    const float send = hi ? v[i] : v[i + 8];
+    const float keep = hi ? v[i + 8] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool hi = lane & 8;
+    const float send = hi ? v[i] : v[i + 4];
+    const float keep = hi ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool hi = lane & 4;
+    const float send = hi ? v[i] : v[i + 2];
+    const float keep = hi ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    const bool hi = lane & 2;
+    const float send = hi ? v[0] : v[1];
+    const float keep = hi ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  return v[0];
+}
+
 template <bool EXTRAS>
 __global__ void __launch_bounds__(BB) blend_bwd_kernel(const uint2* __restrict__ ranges,
                                                        const uint32_t* __restrict__ point_list, int W, int H,
-                                                       const float* __restrict__ bg, const float2* __restrict__ xy,
+                                                       const float* __restrict__ bg, const float4* __restrict__ xy_ext,
                                                        const float4* __restrict__ conic_opacity,
                                                        const float4* __restrict__ rgb_depth,
                                                        const float* __restrict__ final_T,
@@ -29,9 +82,10 @@ __global__ void __launch_bounds__(BB) blend_bwd_kernel(const uint2* __restrict__
                                                        const float* __restrict__ dL_dalpha_img,
                                                        float* __restrict__ grad_acc) {
   __shared__ uint32_t s_id[BB];
-  __shared__ float2 s_xy[BB];
-  __shared__ float4 s_co[BB];
-  __shared__ float4 s_cd[BB];
+  __shared__ __align__(16) float4 s_xy[BB];
+  __shared__ __align__(16) float4 s_co[BB];
+  __shared__ __align__(16) float4 s_cd[BB];
+  __shared__ uint32_t s_ball[8][BB / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t tiles_x = (W + TILE - 1) / TILE;
@@ -41,6 +95,7 @@ __global__ void __launch_bounds__(BB) blend_bwd_kernel(const uint2* __restrict__
   const bool inside = px < (uint32_t)W && py < (uint32_t)H;
   const uint32_t pix_id = (uint32_t)W * py + px;
   const float2 pixf = {(float)px, (float)py};
+  const float tile_x0 = (float)(blockIdx.x * TILE), tile_y0 = (float)(blockIdx.y * TILE);
 
   const uint2 range = ranges[tile_id];
   const int total = (int)min(tile_last[tile_id], range.y - range.x);  // entries [0,total) can contribute
@@ -50,6 +105,7 @@ __global__ void __launch_bounds__(BB) blend_bwd_kernel(const uint2* __restrict__
   const float T_final = inside ? final_T[pix_id] : 0.f;
   float T = T_final;
   const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
+  const int warp_last = __reduce_max_sync(0xffffffffu, last_contributor);
 
   const size_t HW = (size_t)H * W;
   float dpix[3] = {0.f, 0.f, 0.f};
@@ -63,8 +119,9 @@ __global__ void __launch_bounds__(BB) blend_bwd_kernel(const uint2* __restrict__
       if (dL_dalpha_img) dalp = dL_dalpha_img[pix_id];
     }
   }
-  // d(out)/dalpha_i through the final transmittance: colour gets +T_final*bg, alpha image gets -T_final
-  const float bg_dot_dpixel = bg[0] * dpix[0] + bg[1] * dpix[1] + bg[2] * dpix[2];
+  // d(out)/dalpha_i through the final transmittance: colour gets +T_final*bg, the alpha image -T_final
+  float tail = bg[0] * dpix[0] + bg[1] * dpix[1] + bg[2] * dpix[2];
+  if (EXTRAS) tail -= dalp;
 
   float accum_rec[3] = {0.f, 0.f, 0.f}, last_color[3] = {0.f, 0.f, 0.f};
   float accum_z = 0.f, last_z = 0.f;
@@ -72,102 +129,99 @@ __global__ void __launch_bounds__(BB) blend_bwd_kernel(const uint2* __restrict__
   const float ddelx_dx = 0.5f * W;
   const float ddely_dy = 0.5f * H;
 
-  int idx = total;  // list position (0-based) of the entry about to be visited is idx-1
   for (int r = 0; r < rounds; ++r) {
-    __syncthreads();
-    const int progress = r * BB + tid;
+    __syncthreads();  // previous batch fully consumed
+    const int progress = r * BB + tid;     // batch entry `tid` is list position total-1-progress
+    uint32_t mymask = 0;
     if (progress < total) {
       const uint32_t id = point_list[range.x + (total - 1 - progress)];
+      const float4 g = xy_ext[id];
       s_id[tid] = id;
-      s_xy[tid] = xy[id];
+      s_xy[tid] = g;
       s_co[tid] = conic_opacity[id];
       s_cd[tid] = rgb_depth[id];
+      mymask = block_mask_b(g.x, g.y, g.z, g.w, tile_x0, tile_y0);
+    }
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const uint32_t bal = __ballot_sync(0xffffffffu, (mymask >> b) & 1u);
+      if (lane == 0) s_ball[b][warp] = bal;
     }
     __syncthreads();
-    const int nb = min(BB, total - r * BB);
-    for (int j = 0; j < nb; ++j) {
-      --idx;
-      bool valid = inside && idx < last_contributor;
-      float G = 0.f, alpha = 0.f;
-      float2 d = {0.f, 0.f};
-      float4 con_o = s_co[j];
-      if (valid) {
-        const float2 m = s_xy[j];
-        d = {m.x - pixf.x, m.y - pixf.y};
-        const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
-        if (power > 0.0f) valid = false;
-        else {
-          G = expf(power);
-          alpha = min(0.99f, con_o.w * G);
-          if (alpha < 1.0f / 255.0f) valid = false;
-        }
-      }
-      if (!__any_sync(0xffffffffu, valid)) continue;
 
-      float g_mx = 0.f, g_my = 0.f, g_cx = 0.f, g_cy = 0.f, g_cw = 0.f, g_op = 0.f;
-      float g_c0 = 0.f, g_c1 = 0.f, g_c2 = 0.f, g_z = 0.f;
-      if (valid) {
-        T = T / (1.f - alpha);
-        const float dchannel_dcolor = alpha * T;
-        const float4 cd = s_cd[j];
-        const float c[3] = {cd.x, cd.y, cd.z};
-        float dL_dalpha = 0.0f;
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-          accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
-          last_color[ch] = c[ch];
-          dL_dalpha += (c[ch] - accum_rec[ch]) * dpix[ch];
+    const int batch_first_pos = total - 1 - r * BB;  // list position of batch entry 0
+    if (batch_first_pos - (BB - 1) >= warp_last) continue;  // whole batch lies behind this block's last contributor
+#pragma unroll 1
+    for (int w8 = 0; w8 < BB / 32; ++w8) {
+      uint32_t m = s_ball[warp][w8];
+      while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1;
+        const int j = w8 * 32 + bit;
+        const int pos = batch_first_pos - j;  // 0-based list position
+        if (pos >= warp_last) continue;
+        bool valid = pos < last_contributor;
+        float G = 0.f, alpha = 0.f;
+        float2 d = {0.f, 0.f};
+        const float4 con_o = s_co[j];
+        if (valid) {
+          const float4 g = s_xy[j];
+          d = {g.x - pixf.x, g.y - pixf.y};
+          const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
+          if (power > 0.0f) valid = false;
+          else {
+            G = expf(power);
+            alpha = min(0.99f, con_o.w * G);
+            if (alpha < 1.0f / 255.0f) valid = false;
+          }
         }
-        g_c0 = dchannel_dcolor * dpix[0];
-        g_c1 = dchannel_dcolor * dpix[1];
-        g_c2 = dchannel_dcolor * dpix[2];
-        if (EXTRAS) {
-          accum_z = last_alpha * last_z + (1.f - last_alpha) * accum_z;
-          last_z = cd.w;
-          dL_dalpha += (cd.w - accum_z) * ddep;
-          g_z = dchannel_dcolor * ddep;
-        }
-        dL_dalpha *= T;
-        last_alpha = alpha;
-        float tail = bg_dot_dpixel;
-        if (EXTRAS) tail -= dalp;
-        dL_dalpha += (-T_final / (1.f - alpha)) * tail;
+        if (!__any_sync(0xffffffffu, valid)) continue;
 
-        const float dL_dG = con_o.w * dL_dalpha;
-        const float gdx = G * d.x;
-        const float gdy = G * d.y;
-        const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
-        const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
-        g_mx = dL_dG * dG_ddelx * ddelx_dx;
-        g_my = dL_dG * dG_ddely * ddely_dy;
-        g_cx = -0.5f * gdx * d.x * dL_dG;
-        g_cy = -0.5f * gdx * d.y * dL_dG;
-        g_cw = -0.5f * gdy * d.y * dL_dG;
-        g_op = G * dL_dalpha;
-      }
-      // warp reduction, then one lane commits
+        float v[16];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        g_mx += __shfl_xor_sync(0xffffffffu, g_mx, o);
-        g_my += __shfl_xor_sync(0xffffffffu, g_my, o);
-        g_cx += __shfl_xor_sync(0xffffffffu, g_cx, o);
-        g_cy += __shfl_xor_sync(0xffffffffu, g_cy, o);
-        g_cw += __shfl_xor_sync(0xffffffffu, g_cw, o);
-        g_op += __shfl_xor_sync(0xffffffffu, g_op, o);
-        g_c0 += __shfl_xor_sync(0xffffffffu, g_c0, o);
-        g_c1 += __shfl_xor_sync(0xffffffffu, g_c1, o);
-        g_c2 += __shfl_xor_sync(0xffffffffu, g_c2, o);
-        if (EXTRAS) g_z += __shfl_xor_sync(0xffffffffu, g_z, o);
+        for (int k = 0; k < 16; ++k) v[k] = 0.f;
+        if (valid) {
+          T = T / (1.f - alpha);
+          const float dchannel_dcolor = alpha * T;
+          const float4 cd = s_cd[j];
+          const float c[3] = {cd.x, cd.y, cd.z};
+          float dL_dalpha = 0.0f;
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
+            last_color[ch] = c[ch];
+            dL_dalpha += (c[ch] - accum_rec[ch]) * dpix[ch];
+          }
+          v[6] = dchannel_dcolor * dpix[0];
+          v[7] = dchannel_dcolor * dpix[1];
+          v[8] = dchannel_dcolor * dpix[2];
+          if (EXTRAS) {
+            accum_z = last_alpha * last_z + (1.f - last_alpha) * accum_z;
+            last_z = cd.w;
+            dL_dalpha += (cd.w - accum_z) * ddep;
+            v[9] = dchannel_dcolor * ddep;
+          }
+          dL_dalpha *= T;
+          last_alpha = alpha;
+          dL_dalpha += (-T_final / (1.f - alpha)) * tail;
+
+          const float dL_dG = con_o.w * dL_dalpha;
+          const float gdx = G * d.x;
+          const float gdy = G * d.y;
+          const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
+          const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
+          v[0] = dL_dG * dG_ddelx * ddelx_dx;
+          v[1] = dL_dG * dG_ddely * ddely_dy;
+          v[2] = -0.5f * gdx * d.x * dL_dG;
+          v[3] = -0.5f * gdx * d.y * dL_dG;
+          v[4] = -0.5f * gdy * d.y * dL_dG;
+          v[5] = G * dL_dalpha;
+        }
+        const float sum = warp_reduce16(v, lane);
+        // lane 2q holds quantity q: one predicated RED, 9-10 consecutive floats of the accumulator row
+        const int q = lane >> 1;
+        if (!(lane & 1) && q < (EXTRAS ? 10 : 9)) atomicAdd(grad_acc + (size_t)s_id[j] * GRAD_ACC + q, sum);
       }
-      float* acc = grad_acc + (size_t)s_id[j] * GRAD_ACC;
-      // spread the 9-10 atomics over lanes so they issue in one instruction
-      float v = 0.f;
-      switch (lane) {
-        case 0: v = g_mx; break; case 1: v = g_my; break; case 2: v = g_cx; break; case 3: v = g_cy; break;
-        case 4: v = g_cw; break; case 5: v = g_op; break; case 6: v = g_c0; break; case 7: v = g_c1; break;
-        case 8: v = g_c2; break; case 9: v = g_z; break; default: break;
-      }
-      if (lane < (EXTRAS ? 10 : 9)) atomicAdd(acc + lane, v);
     }
   }
 }
@@ -177,11 +231,11 @@ int launch_blend_bwd(const tgr_params& p, const GeomView& g, const uint32_t* poi
   dim3 grid((p.W + TILE - 1) / TILE, (p.H + TILE - 1) / TILE, 1);
   const bool ex = p.extras && (p.dL_dout_depth || p.dL_dout_alpha);
   if (ex)
-    blend_bwd_kernel<true><<<grid, BB, 0, s>>>(im.ranges, point_list, p.W, p.H, p.background, g.xy, g.conic_opacity,
+    blend_bwd_kernel<true><<<grid, BB, 0, s>>>(im.ranges, point_list, p.W, p.H, p.background, g.xy_ext, g.conic_opacity,
                                                g.rgb_depth, im.final_T, im.n_contrib, im.tile_last, p.dL_dout_color,
                                                p.dL_dout_depth, p.dL_dout_alpha, grad_acc);
   else
-    blend_bwd_kernel<false><<<grid, BB, 0, s>>>(im.ranges, point_list, p.W, p.H, p.background, g.xy, g.conic_opacity,
+    blend_bwd_kernel<false><<<grid, BB, 0, s>>>(im.ranges, point_list, p.W, p.H, p.background, g.xy_ext, g.conic_opacity,
                                                 g.rgb_depth, im.final_T, im.n_contrib, im.tile_last, p.dL_dout_color,
                                                 nullptr, nullptr, grad_acc);
   return check_launch("blend_bwd", p.debug != 0, s);

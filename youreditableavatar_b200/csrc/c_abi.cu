@@ -202,7 +202,7 @@ __global__ void export_geom_kernel(int P, GeomView g, float* depth, float* xy, f
   const bool vis = (rc.z - rc.x) * (rc.w - rc.y) != 0;
   const float4 cd = g.rgb_depth[i];
   const float4 c = g.conic_opacity[i];
-  const float2 m = g.xy[i];
+  const float4 m = g.xy_ext[i];
   if (depth) depth[i] = vis ? cd.w : 0.f;
   if (xy) { xy[2 * i] = vis ? m.x : 0.f; xy[2 * i + 1] = vis ? m.y : 0.f; }
   if (co) { co[4 * i] = vis ? c.x : 0.f; co[4 * i + 1] = vis ? c.y : 0.f; co[4 * i + 2] = vis ? c.z : 0.f; co[4 * i + 3] = vis ? c.w : 0.f; }

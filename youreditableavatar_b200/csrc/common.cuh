@@ -71,7 +71,7 @@ struct GeomView {
   uint32_t* key_alt;       // [P] sort buffer B keys
   uint32_t* val_alt;       // [P] sort buffer B values
   ushort4* rect;           // [P] tile rectangle (x0,y0,x1,y1); all zero when culled
-  float2* xy;              // [P] pixel-space mean
+  float4* xy_ext;          // [P] pixel-space mean (x,y) + conservative half-extents (hx,hy) of alpha >= 1/255
   float4* conic_opacity;   // [P] inverse 2D covariance (xx,xy,yy) + opacity
   float4* rgb_depth;       // [P] colour + view-space depth
   uint8_t* clamped;        // [P] bit c set when colour channel c was clamped at 0
@@ -102,7 +102,7 @@ __host__ __device__ inline GeomView carve_geom(void* base, int32_t P) {
   g.key_alt = carve<uint32_t>(p, n);
   g.val_alt = carve<uint32_t>(p, n);
   g.rect = carve<ushort4>(p, n);
-  g.xy = carve<float2>(p, n);
+  g.xy_ext = carve<float4>(p, n);
   g.conic_opacity = carve<float4>(p, n);
   g.rgb_depth = carve<float4>(p, n);
   g.clamped = carve<uint8_t>(p, n);

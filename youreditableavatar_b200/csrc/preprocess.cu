@@ -209,7 +209,23 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const tgr_params p, con
             const float3 cam = {p.campos[0], p.campos[1], p.campos[2]};
             rgb = sh_to_rgb(p.D, sh, p_orig, cam, clamped);
           }
-          g.xy[idx] = point_image;
+          // Conservative footprint of {alpha >= 1/255}: |dx| <= sqrt(2 tau Sxx), |dy| <= sqrt(2 tau Syy) with
+          // tau = ln(255 o) and S the inverse of the conic actually used by the blend kernels.  Margins cover
+          // fp32 rounding of power/exp; ill-conditioned conics disable culling (huge extents).  Pairs outside
+          // this box fail the reference's alpha < 1/255 test (forward.cu:343-345), so skipping them is exact.
+          float hx = -1.f, hy = -1.f;
+          if (!(opacity < 1.0f / 255.0f)) {
+            const float tau = logf(255.0f * opacity) * 1.01f + 0.01f;
+            const float ac = conic.x * conic.z, bb = conic.y * conic.y;
+            const float det_lo = (ac - bb) - 1e-6f * (fabsf(ac) + bb);
+            if (det_lo > 0.f && ac <= 1000.f * det_lo && tau < 1e30f) {
+              hx = sqrtf(2.f * tau * conic.z / det_lo) * 1.001f + 0.01f;
+              hy = sqrtf(2.f * tau * conic.x / det_lo) * 1.001f + 0.01f;
+            } else {
+              hx = hy = 1e30f;
+            }
+          }
+          g.xy_ext[idx] = make_float4(point_image.x, point_image.y, hx, hy);
           g.conic_opacity[idx] = {conic.x, conic.y, conic.z, opacity};
           g.rgb_depth[idx] = {rgb.x, rgb.y, rgb.z, p_view.z};
           g.clamped[idx] = clamped;
