@@ -14,26 +14,9 @@
 //     {dmean2D.x, dmean2D.y, dconic.xx, dconic.xy, dconic.yy, dopacity, dr, dg, db, dz, -, -};
 //   * extras: gradients of the depth / alpha images flow through the same recurrence.
 #include "common.cuh"
+#include "pipeline.cuh"
 
 namespace tgr {
-
-constexpr int BB = 256;
-
-__device__ __forceinline__ uint32_t block_mask_b(float x, float y, float hx, float hy, float tile_x0, float tile_y0) {
-  if (!(hx >= 0.f)) return 0u;
-  const float fx0 = ceilf(x - hx) - tile_x0, fx1 = floorf(x + hx) - tile_x0;
-  const float fy0 = ceilf(y - hy) - tile_y0, fy1 = floorf(y + hy) - tile_y0;
-  if (fx1 < 0.f || fy1 < 0.f || fx0 > 15.f || fy0 > 15.f || fx0 > fx1 || fy0 > fy1) return 0u;
-  const int x0 = (int)fmaxf(fx0, 0.f), x1 = (int)fminf(fx1, 15.f);
-  const int y0 = (int)fmaxf(fy0, 0.f), y1 = (int)fminf(fy1, 15.f);
-  const uint32_t colm = ((x0 < 8) ? 1u : 0u) | ((x1 >= 8) ? 2u : 0u);
-  const int r0 = y0 >> 2, r1 = y1 >> 2;
-  uint32_t m = 0;
-#pragma unroll
-  for (int r = 0; r < 4; ++r)
-    if (r >= r0 && r <= r1) m |= colm << (2 * r);
-  return m;
-}
 
 // Sums 16 per-lane quantities over the warp; afterwards lane l holds the total of quantity l>>1.
 __device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
@@ -69,38 +52,61 @@ __device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
 }
 
 template <bool EXTRAS>
-__global__ void __launch_bounds__(BB) blend_bwd_kernel(const uint2* __restrict__ ranges,
-                                                       const uint32_t* __restrict__ point_list, int W, int H,
-                                                       const float* __restrict__ bg, const float4* __restrict__ xy_ext,
-                                                       const float4* __restrict__ conic_opacity,
-                                                       const float4* __restrict__ rgb_depth,
-                                                       const float* __restrict__ final_T,
-                                                       const uint32_t* __restrict__ n_contrib,
-                                                       const uint32_t* __restrict__ tile_last,
-                                                       const float* __restrict__ dL_dpix,
-                                                       const float* __restrict__ dL_ddepth,
-                                                       const float* __restrict__ dL_dalpha_img,
-                                                       float* __restrict__ grad_acc) {
-  __shared__ uint32_t s_id[BB];
-  __shared__ __align__(16) float4 s_xy[BB];
-  __shared__ __align__(16) float4 s_co[BB];
-  __shared__ __align__(16) float4 s_cd[BB];
-  __shared__ uint32_t s_ball[8][BB / 32];
+__global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint2* __restrict__ ranges,
+                                                               const uint32_t* __restrict__ point_list, int W, int H,
+                                                               const float* __restrict__ bg,
+                                                               const float4* __restrict__ xy_ext,
+                                                               const float4* __restrict__ conic_opacity,
+                                                               const float4* __restrict__ rgb_depth,
+                                                               const float* __restrict__ final_T,
+                                                               const uint32_t* __restrict__ n_contrib,
+                                                               const uint32_t* __restrict__ tile_last,
+                                                               const float* __restrict__ dL_dpix,
+                                                               const float* __restrict__ dL_ddepth,
+                                                               const float* __restrict__ dL_dalpha_img,
+                                                               float* __restrict__ grad_acc) {
+  __shared__ uint32_t s_id[BL_STAGES][BL_BATCH];
+  __shared__ __align__(16) float4 s_xy[BL_STAGES][BL_BATCH];
+  __shared__ __align__(16) float4 s_co[BL_STAGES][BL_BATCH];
+  __shared__ __align__(16) float4 s_cd[BL_STAGES][BL_BATCH];
+  __shared__ uint32_t s_ball[BL_STAGES][8][BL_CHUNKS];
+  __shared__ __align__(8) uint64_t s_full[BL_STAGES], s_empty[BL_STAGES];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t tiles_x = (W + TILE - 1) / TILE;
   const uint32_t tile_id = blockIdx.y * tiles_x + blockIdx.x;
+  const uint2 range = ranges[tile_id];
+  const int total = (int)min(tile_last[tile_id], range.y - range.x);  // entries [0,total) can contribute
+  if (total == 0) return;
+  const int rounds = (total + BL_BATCH - 1) / BL_BATCH;
+
+  if (tid == 0) {
+    for (int s = 0; s < BL_STAGES; ++s) {
+      mbar_init(&s_full[s], 32);
+      mbar_init(&s_empty[s], 8);
+    }
+  }
+  __syncthreads();
+
+  if (warp == 8) {
+    // ======================= PRODUCER: back-to-front gather =======================
+    const float tile_x0 = (float)(blockIdx.x * TILE), tile_y0 = (float)(blockIdx.y * TILE);
+    for (int b = 0; b < rounds; ++b) {
+      const int stage = b % BL_STAGES;
+      if (b >= BL_STAGES) mbar_wait(&s_empty[stage], ((b / BL_STAGES) - 1) & 1);
+      produce_batch(point_list + range.x, total, b * BL_BATCH, /*reverse=*/true, xy_ext, conic_opacity, rgb_depth,
+                    s_xy[stage], s_co[stage], s_cd[stage], s_id[stage], s_ball[stage], tile_x0, tile_y0, lane);
+      mbar_arrive(&s_full[stage]);
+    }
+    return;
+  }
+
+  // ========================= CONSUMERS =========================
   const uint32_t px = blockIdx.x * TILE + (warp & 1) * 8 + (lane & 7);
   const uint32_t py = blockIdx.y * TILE + (warp >> 1) * 4 + (lane >> 3);
   const bool inside = px < (uint32_t)W && py < (uint32_t)H;
   const uint32_t pix_id = (uint32_t)W * py + px;
   const float2 pixf = {(float)px, (float)py};
-  const float tile_x0 = (float)(blockIdx.x * TILE), tile_y0 = (float)(blockIdx.y * TILE);
-
-  const uint2 range = ranges[tile_id];
-  const int total = (int)min(tile_last[tile_id], range.y - range.x);  // entries [0,total) can contribute
-  if (total == 0) return;
-  const int rounds = (total + BB - 1) / BB;
 
   const float T_final = inside ? final_T[pix_id] : 0.f;
   float T = T_final;
@@ -129,100 +135,87 @@ __global__ void __launch_bounds__(BB) blend_bwd_kernel(const uint2* __restrict__
   const float ddelx_dx = 0.5f * W;
   const float ddely_dy = 0.5f * H;
 
-  for (int r = 0; r < rounds; ++r) {
-    __syncthreads();  // previous batch fully consumed
-    const int progress = r * BB + tid;     // batch entry `tid` is list position total-1-progress
-    uint32_t mymask = 0;
-    if (progress < total) {
-      const uint32_t id = point_list[range.x + (total - 1 - progress)];
-      const float4 g = xy_ext[id];
-      s_id[tid] = id;
-      s_xy[tid] = g;
-      s_co[tid] = conic_opacity[id];
-      s_cd[tid] = rgb_depth[id];
-      mymask = block_mask_b(g.x, g.y, g.z, g.w, tile_x0, tile_y0);
-    }
-#pragma unroll
-    for (int b = 0; b < 8; ++b) {
-      const uint32_t bal = __ballot_sync(0xffffffffu, (mymask >> b) & 1u);
-      if (lane == 0) s_ball[b][warp] = bal;
-    }
-    __syncthreads();
-
-    const int batch_first_pos = total - 1 - r * BB;  // list position of batch entry 0
-    if (batch_first_pos - (BB - 1) >= warp_last) continue;  // whole batch lies behind this block's last contributor
+  for (int b = 0; b < rounds; ++b) {
+    const int stage = b % BL_STAGES;
+    const int batch_first_pos = total - 1 - b * BL_BATCH;  // list position of batch entry 0 (descending)
+    mbar_wait(&s_full[stage], (b / BL_STAGES) & 1);
+    if (batch_first_pos - (BL_BATCH - 1) < warp_last) {  // else: whole batch lies behind this block's last contributor
 #pragma unroll 1
-    for (int w8 = 0; w8 < BB / 32; ++w8) {
-      uint32_t m = s_ball[warp][w8];
-      while (m) {
-        const int bit = __ffs(m) - 1;
-        m &= m - 1;
-        const int j = w8 * 32 + bit;
-        const int pos = batch_first_pos - j;  // 0-based list position
-        if (pos >= warp_last) continue;
-        bool valid = pos < last_contributor;
-        float G = 0.f, alpha = 0.f;
-        float2 d = {0.f, 0.f};
-        const float4 con_o = s_co[j];
-        if (valid) {
-          const float4 g = s_xy[j];
-          d = {g.x - pixf.x, g.y - pixf.y};
-          const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
-          if (power > 0.0f) valid = false;
-          else {
-            G = expf(power);
-            alpha = min(0.99f, con_o.w * G);
-            if (alpha < 1.0f / 255.0f) valid = false;
+      for (int c = 0; c < BL_CHUNKS; ++c) {
+        uint32_t m = s_ball[stage][warp][c];
+        while (m) {
+          const int bit = __ffs(m) - 1;
+          m &= m - 1;
+          const int j = c * 32 + bit;
+          const int pos = batch_first_pos - j;  // 0-based list position
+          if (pos >= warp_last) continue;
+          bool valid = pos < last_contributor;
+          float G = 0.f, alpha = 0.f;
+          float2 d = {0.f, 0.f};
+          const float4 con_o = s_co[stage][j];
+          if (valid) {
+            const float4 g = s_xy[stage][j];
+            d = {g.x - pixf.x, g.y - pixf.y};
+            const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
+            if (power > 0.0f) valid = false;
+            else {
+              G = expf(power);
+              alpha = min(0.99f, con_o.w * G);
+              if (alpha < 1.0f / 255.0f) valid = false;
+            }
           }
-        }
-        if (!__any_sync(0xffffffffu, valid)) continue;
+          if (!__any_sync(0xffffffffu, valid)) continue;
 
-        float v[16];
+          float v[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = 0.f;
-        if (valid) {
-          T = T / (1.f - alpha);
-          const float dchannel_dcolor = alpha * T;
-          const float4 cd = s_cd[j];
-          const float c[3] = {cd.x, cd.y, cd.z};
-          float dL_dalpha = 0.0f;
+          for (int k = 0; k < 16; ++k) v[k] = 0.f;
+          if (valid) {
+            T = T / (1.f - alpha);
+            const float dchannel_dcolor = alpha * T;
+            const float4 cd = s_cd[stage][j];
+            const float c3[3] = {cd.x, cd.y, cd.z};
+            float dL_dalpha = 0.0f;
 #pragma unroll
-          for (int ch = 0; ch < 3; ++ch) {
-            accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
-            last_color[ch] = c[ch];
-            dL_dalpha += (c[ch] - accum_rec[ch]) * dpix[ch];
-          }
-          v[6] = dchannel_dcolor * dpix[0];
-          v[7] = dchannel_dcolor * dpix[1];
-          v[8] = dchannel_dcolor * dpix[2];
-          if (EXTRAS) {
-            accum_z = last_alpha * last_z + (1.f - last_alpha) * accum_z;
-            last_z = cd.w;
-            dL_dalpha += (cd.w - accum_z) * ddep;
-            v[9] = dchannel_dcolor * ddep;
-          }
-          dL_dalpha *= T;
-          last_alpha = alpha;
-          dL_dalpha += (-T_final / (1.f - alpha)) * tail;
+            for (int ch = 0; ch < 3; ++ch) {
+              accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
+              last_color[ch] = c3[ch];
+              dL_dalpha += (c3[ch] - accum_rec[ch]) * dpix[ch];
+            }
+            v[6] = dchannel_dcolor * dpix[0];
+            v[7] = dchannel_dcolor * dpix[1];
+            v[8] = dchannel_dcolor * dpix[2];
+            if (EXTRAS) {
+              accum_z = last_alpha * last_z + (1.f - last_alpha) * accum_z;
+              last_z = cd.w;
+              dL_dalpha += (cd.w - accum_z) * ddep;
+              v[9] = dchannel_dcolor * ddep;
+            }
+            dL_dalpha *= T;
+            last_alpha = alpha;
+            dL_dalpha += (-T_final / (1.f - alpha)) * tail;
 
-          const float dL_dG = con_o.w * dL_dalpha;
-          const float gdx = G * d.x;
-          const float gdy = G * d.y;
-          const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
-          const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
-          v[0] = dL_dG * dG_ddelx * ddelx_dx;
-          v[1] = dL_dG * dG_ddely * ddely_dy;
-          v[2] = -0.5f * gdx * d.x * dL_dG;
-          v[3] = -0.5f * gdx * d.y * dL_dG;
-          v[4] = -0.5f * gdy * d.y * dL_dG;
-          v[5] = G * dL_dalpha;
+            const float dL_dG = con_o.w * dL_dalpha;
+            const float gdx = G * d.x;
+            const float gdy = G * d.y;
+            const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
+            const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
+            v[0] = dL_dG * dG_ddelx * ddelx_dx;
+            v[1] = dL_dG * dG_ddely * ddely_dy;
+            v[2] = -0.5f * gdx * d.x * dL_dG;
+            v[3] = -0.5f * gdx * d.y * dL_dG;
+            v[4] = -0.5f * gdy * d.y * dL_dG;
+            v[5] = G * dL_dalpha;
+          }
+          const float sum = warp_reduce16(v, lane);
+          // lane 2q holds quantity q: one predicated RED, 9-10 consecutive floats of the accumulator row
+          const int q = lane >> 1;
+          if (!(lane & 1) && q < (EXTRAS ? 10 : 9))
+            atomicAdd(grad_acc + (size_t)s_id[stage][j] * GRAD_ACC + q, sum);
         }
-        const float sum = warp_reduce16(v, lane);
-        // lane 2q holds quantity q: one predicated RED, 9-10 consecutive floats of the accumulator row
-        const int q = lane >> 1;
-        if (!(lane & 1) && q < (EXTRAS ? 10 : 9)) atomicAdd(grad_acc + (size_t)s_id[j] * GRAD_ACC + q, sum);
       }
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[stage]);
   }
 }
 
@@ -231,11 +224,11 @@ int launch_blend_bwd(const tgr_params& p, const GeomView& g, const uint32_t* poi
   dim3 grid((p.W + TILE - 1) / TILE, (p.H + TILE - 1) / TILE, 1);
   const bool ex = p.extras && (p.dL_dout_depth || p.dL_dout_alpha);
   if (ex)
-    blend_bwd_kernel<true><<<grid, BB, 0, s>>>(im.ranges, point_list, p.W, p.H, p.background, g.xy_ext, g.conic_opacity,
+    blend_bwd_kernel<true><<<grid, BL_THREADS, 0, s>>>(im.ranges, point_list, p.W, p.H, p.background, g.xy_ext, g.conic_opacity,
                                                g.rgb_depth, im.final_T, im.n_contrib, im.tile_last, p.dL_dout_color,
                                                p.dL_dout_depth, p.dL_dout_alpha, grad_acc);
   else
-    blend_bwd_kernel<false><<<grid, BB, 0, s>>>(im.ranges, point_list, p.W, p.H, p.background, g.xy_ext, g.conic_opacity,
+    blend_bwd_kernel<false><<<grid, BL_THREADS, 0, s>>>(im.ranges, point_list, p.W, p.H, p.background, g.xy_ext, g.conic_opacity,
                                                 g.rgb_depth, im.final_T, im.n_contrib, im.tile_last, p.dL_dout_color,
                                                 nullptr, nullptr, grad_acc);
   return check_launch("blend_bwd", p.debug != 0, s);

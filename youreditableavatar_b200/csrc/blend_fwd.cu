@@ -5,128 +5,116 @@
 // accumulation order) is evaluated with the same fp32 expressions so the image is bit-identical.
 // Extras (new): depth = sum z_i alpha_i T_i, alpha = 1 - T_final.
 //
-// How it differs from the reference kernel:
-//   * 256 threads; warp w owns the 8x4 pixel block at (8*(w&1), 4*(w>>1)) of the tile.  While a batch of
-//     256 list entries is staged, every staging thread also tests its Gaussian's conservative footprint
-//     (half-extents of the alpha >= 1/255 ellipse, computed once per Gaussian by the preprocess kernel)
-//     against the eight warp blocks; eight __ballot_sync per warp turn that into a 256-bit "overlaps my
-//     block" mask per consumer warp.  A warp then only evaluates the Gaussians whose footprint reaches its
-//     block — pairs it skips would have failed the reference's alpha < 1/255 test, so results are unchanged.
-//   * staging is a gather (point_list -> per-Gaussian records); it uses 16-byte cp.async copies into a
-//     double-buffered shared-memory batch so the gather of batch b+1 overlaps the blending of batch b.
+// How it differs from the reference kernel (which stages 256 entries, __syncthreads, all 256 pixels
+// evaluate all 256 entries, __syncthreads, repeat):
+//   * warp specialisation + mbarrier ring.  9 warps: warp 8 is the PRODUCER — it gathers the tile's list in
+//     batches of 128 entries (point_list -> per-Gaussian 16-byte records) into a 4-stage shared-memory ring
+//     and signals full[stage]; warps 0..7 are CONSUMERS, each owning the 8x4 pixel block at
+//     (8*(w&1), 4*(w>>1)) and signalling empty[stage] when done with a stage.  There is no __syncthreads in
+//     the loop, so a consumer whose block is cheap runs ahead by up to 4 batches instead of waiting for the
+//     slowest warp after every batch (ncu on the barrier version: >50% of issue slots stalled on barrier).
+//   * footprint culling.  The producer tests every Gaussian's conservative footprint (half-extents of the
+//     alpha >= 1/255 ellipse, computed once per Gaussian by the preprocess kernel) against the eight warp
+//     blocks; __ballot_sync turns that into one 32-bit mask per (consumer, chunk of 32 entries).  A consumer
+//     only evaluates entries whose footprint reaches its block; everything it skips would have failed the
+//     reference's alpha < 1/255 test, so results are unchanged.
 //   * the tile's maximum contributing list position is written out for the backward (tile_last).
 #include "common.cuh"
+#include "pipeline.cuh"
 
 namespace tgr {
 
-constexpr int FB = 256;  // batch size == threads per CTA
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// 8-bit mask of the warp blocks (bit = 2*row4 + col8) a footprint [x-hx,x+hx]x[y-hy,y+hy] can reach.
-__device__ __forceinline__ uint32_t block_mask(float x, float y, float hx, float hy, float tile_x0, float tile_y0) {
-  if (!(hx >= 0.f)) return 0u;  // never reaches alpha >= 1/255 (or NaN extents)
-  // pixel centres are integers: pixels p with x-hx <= p <= x+hx
-  const float fx0 = ceilf(x - hx) - tile_x0, fx1 = floorf(x + hx) - tile_x0;
-  const float fy0 = ceilf(y - hy) - tile_y0, fy1 = floorf(y + hy) - tile_y0;
-  if (fx1 < 0.f || fy1 < 0.f || fx0 > 15.f || fy0 > 15.f || fx0 > fx1 || fy0 > fy1) return 0u;
-  const int x0 = (int)fmaxf(fx0, 0.f), x1 = (int)fminf(fx1, 15.f);
-  const int y0 = (int)fmaxf(fy0, 0.f), y1 = (int)fminf(fy1, 15.f);
-  const uint32_t colm = ((x0 < 8) ? 1u : 0u) | ((x1 >= 8) ? 2u : 0u);      // which 8-wide columns
-  const int r0 = y0 >> 2, r1 = y1 >> 2;                                       // which 4-high rows
-  uint32_t m = 0;
-#pragma unroll
-  for (int r = 0; r < 4; ++r)
-    if (r >= r0 && r <= r1) m |= colm << (2 * r);
-  return m;
-}
-
 template <bool EXTRAS>
-__global__ void __launch_bounds__(FB) blend_fwd_kernel(const uint2* __restrict__ ranges,
-                                                       const uint32_t* __restrict__ point_list, int W, int H,
-                                                       const float4* __restrict__ xy_ext,
-                                                       const float4* __restrict__ conic_opacity,
-                                                       const float4* __restrict__ rgb_depth,
-                                                       const float* __restrict__ bg, float* __restrict__ final_T,
-                                                       uint32_t* __restrict__ n_contrib, uint32_t* __restrict__ tile_last,
-                                                       float* __restrict__ out_color, float* __restrict__ out_depth,
-                                                       float* __restrict__ out_alpha) {
-  __shared__ __align__(16) float4 s_xy[2][FB];   // x, y, hx, hy
-  __shared__ __align__(16) float4 s_co[2][FB];   // conic xx, xy, yy, opacity
-  __shared__ __align__(16) float4 s_cd[2][FB];   // r, g, b, depth
-  __shared__ uint32_t s_ball[2][8][FB / 32];     // [buf][consumer block][producer warp]
-  __shared__ uint32_t s_last[FB / 32];
+__global__ void __launch_bounds__(BL_THREADS) blend_fwd_kernel(const uint2* __restrict__ ranges,
+                                                               const uint32_t* __restrict__ point_list, int W, int H,
+                                                               const float4* __restrict__ xy_ext,
+                                                               const float4* __restrict__ conic_opacity,
+                                                               const float4* __restrict__ rgb_depth,
+                                                               const float* __restrict__ bg, float* __restrict__ final_T,
+                                                               uint32_t* __restrict__ n_contrib,
+                                                               uint32_t* __restrict__ tile_last,
+                                                               float* __restrict__ out_color, float* __restrict__ out_depth,
+                                                               float* __restrict__ out_alpha) {
+  __shared__ __align__(16) float4 s_xy[BL_STAGES][BL_BATCH];   // x, y, hx, hy
+  __shared__ __align__(16) float4 s_co[BL_STAGES][BL_BATCH];   // conic xx, xy, yy, opacity
+  __shared__ __align__(16) float4 s_cd[BL_STAGES][BL_BATCH];   // r, g, b, depth
+  __shared__ uint32_t s_ball[BL_STAGES][8][BL_CHUNKS];         // [stage][consumer block][chunk of 32]
+  __shared__ __align__(8) uint64_t s_full[BL_STAGES], s_empty[BL_STAGES];
+  __shared__ uint32_t s_stop[BL_STAGES];
+  __shared__ uint32_t s_done_warps;
+  __shared__ uint32_t s_last[8];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t tiles_x = (W + TILE - 1) / TILE;
   const uint32_t tile_id = blockIdx.y * tiles_x + blockIdx.x;
+  const uint2 range = ranges[tile_id];
+  const int total = (int)(range.y - range.x);
+  const int rounds = (total + BL_BATCH - 1) / BL_BATCH;
+
+  if (tid == 0) {
+    for (int s = 0; s < BL_STAGES; ++s) {
+      mbar_init(&s_full[s], 32);   // every producer lane arrives after its stores
+      mbar_init(&s_empty[s], 8);   // one arrival per consumer warp
+      s_stop[s] = 0;
+    }
+    s_done_warps = 0;
+  }
+  __syncthreads();
+
+  if (warp == 8) {
+    // ======================= PRODUCER =======================
+    const float tile_x0 = (float)(blockIdx.x * TILE), tile_y0 = (float)(blockIdx.y * TILE);
+    for (int b = 0; b < rounds; ++b) {
+      const int stage = b % BL_STAGES;
+      if (b >= BL_STAGES) mbar_wait(&s_empty[stage], ((b / BL_STAGES) - 1) & 1);
+      if (*(volatile uint32_t*)&s_done_warps == 8u) {  // every pixel of the tile has terminated
+        if (lane == 0) s_stop[stage] = 1;
+        __syncwarp();
+        mbar_arrive(&s_full[stage]);
+        break;
+      }
+      produce_batch(point_list + range.x, total, b * BL_BATCH, /*reverse=*/false, xy_ext, conic_opacity, rgb_depth,
+                    s_xy[stage], s_co[stage], s_cd[stage], nullptr, s_ball[stage], tile_x0, tile_y0, lane);
+      mbar_arrive(&s_full[stage]);
+    }
+    return;
+  }
+
+  // ========================= CONSUMERS =========================
   const uint32_t px = blockIdx.x * TILE + (warp & 1) * 8 + (lane & 7);
   const uint32_t py = blockIdx.y * TILE + (warp >> 1) * 4 + (lane >> 3);
   const bool inside = px < (uint32_t)W && py < (uint32_t)H;
   const uint32_t pix_id = (uint32_t)W * py + px;
   const float2 pixf = {(float)px, (float)py};
-  const float tile_x0 = (float)(blockIdx.x * TILE), tile_y0 = (float)(blockIdx.y * TILE);
-
-  const uint2 range = ranges[tile_id];
-  const int total = (int)(range.y - range.x);
-  const int rounds = (total + FB - 1) / FB;
 
   bool done = !inside;
+  bool warp_done = false;
   float T = 1.0f;
   uint32_t last_contributor = 0;
   float C[3] = {0.f, 0.f, 0.f};
   float Dz = 0.f;
 
-  auto issue = [&](int round, int buf) {  // gather batch `round` into buffer `buf` (asynchronously)
-    const int progress = round * FB + tid;
-    if (progress < total) {
-      const uint32_t id = point_list[range.x + progress];
-      cp_async16(&s_xy[buf][tid], &xy_ext[id]);
-      cp_async16(&s_co[buf][tid], &conic_opacity[id]);
-      cp_async16(&s_cd[buf][tid], &rgb_depth[id]);
+  for (int b = 0; b < rounds; ++b) {
+    const int stage = b % BL_STAGES;
+    if (!warp_done && __all_sync(0xffffffffu, done)) {
+      warp_done = true;
+      if (lane == 0) atomicAdd(&s_done_warps, 1u);
     }
-    cp_async_commit();
-  };
-  if (rounds > 0) issue(0, 0);
-
-  for (int i = 0; i < rounds; ++i) {
-    const int buf = i & 1;
-    cp_async_wait<0>();
-    // own record has landed: classify it against the eight warp blocks
-    uint32_t mymask = 0;
-    if (i * FB + tid < total) {
-      const float4 g = s_xy[buf][tid];
-      mymask = block_mask(g.x, g.y, g.z, g.w, tile_x0, tile_y0);
-    }
-#pragma unroll
-    for (int b = 0; b < 8; ++b) {
-      const uint32_t bal = __ballot_sync(0xffffffffu, (mymask >> b) & 1u);
-      if (lane == 0) s_ball[buf][b][warp] = bal;
-    }
-    // all records + masks of batch i visible; nobody still reads buffer buf^1 (batch i-1)
-    const int num_done = __syncthreads_count(done);
-    if (num_done == FB) break;
-    if (i + 1 < rounds) issue(i + 1, buf ^ 1);
-
-    if (!__all_sync(0xffffffffu, done)) {
-      const uint32_t base_pos = (uint32_t)(i * FB);
+    mbar_wait(&s_full[stage], (b / BL_STAGES) & 1);
+    if (*(volatile uint32_t*)&s_stop[stage]) break;
+    if (!warp_done) {
+      const uint32_t base_pos = (uint32_t)(b * BL_BATCH);
 #pragma unroll 1
-      for (int w8 = 0; w8 < FB / 32; ++w8) {
-        uint32_t m = s_ball[buf][warp][w8];
+      for (int c = 0; c < BL_CHUNKS; ++c) {
+        uint32_t m = s_ball[stage][warp][c];
         while (m) {
           const int bit = __ffs(m) - 1;
           m &= m - 1;
-          const int j = w8 * 32 + bit;
+          const int j = c * 32 + bit;
           if (!done) {
-            const float4 g = s_xy[buf][j];
+            const float4 g = s_xy[stage][j];
             const float2 d = {g.x - pixf.x, g.y - pixf.y};
-            const float4 con_o = s_co[buf][j];
+            const float4 con_o = s_co[stage][j];
             const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
             if (power <= 0.0f) {
               const float alpha = min(0.99f, con_o.w * expf(power));
@@ -135,7 +123,7 @@ __global__ void __launch_bounds__(FB) blend_fwd_kernel(const uint2* __restrict__
                 if (test_T < 0.0001f) {
                   done = true;
                 } else {
-                  const float4 cd = s_cd[buf][j];
+                  const float4 cd = s_cd[stage][j];
                   C[0] += cd.x * alpha * T;
                   C[1] += cd.y * alpha * T;
                   C[2] += cd.z * alpha * T;
@@ -150,8 +138,9 @@ __global__ void __launch_bounds__(FB) blend_fwd_kernel(const uint2* __restrict__
         if (__all_sync(0xffffffffu, done)) break;
       }
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[stage]);
   }
-  cp_async_wait<0>();
 
   if (inside) {
     final_T[pix_id] = T;
@@ -166,13 +155,13 @@ __global__ void __launch_bounds__(FB) blend_fwd_kernel(const uint2* __restrict__
     }
   }
   // tile-wide maximum of last_contributor: lets the backward start at the last useful list entry
-  uint32_t wl = __reduce_max_sync(0xffffffffu, inside ? last_contributor : 0u);
+  const uint32_t wl = __reduce_max_sync(0xffffffffu, inside ? last_contributor : 0u);
   if (lane == 0) s_last[warp] = wl;
-  __syncthreads();
+  bar_sync_named(1, 256);  // the eight consumer warps only (the producer has left)
   if (tid == 0) {
     uint32_t m = 0;
 #pragma unroll
-    for (int w = 0; w < FB / 32; ++w) m = max(m, s_last[w]);
+    for (int w = 0; w < 8; ++w) m = max(m, s_last[w]);
     tile_last[tile_id] = m;
   }
 }
@@ -181,13 +170,13 @@ int launch_blend_fwd(const tgr_params& p, const GeomView& g, const uint32_t* poi
                      cudaStream_t s) {
   dim3 grid((p.W + TILE - 1) / TILE, (p.H + TILE - 1) / TILE, 1);
   if (p.extras && p.out_depth && p.out_alpha)
-    blend_fwd_kernel<true><<<grid, FB, 0, s>>>(im.ranges, point_list, p.W, p.H, g.xy_ext, g.conic_opacity, g.rgb_depth,
-                                               p.background, im.final_T, im.n_contrib, im.tile_last, p.out_color,
-                                               p.out_depth, p.out_alpha);
+    blend_fwd_kernel<true><<<grid, BL_THREADS, 0, s>>>(im.ranges, point_list, p.W, p.H, g.xy_ext, g.conic_opacity,
+                                                       g.rgb_depth, p.background, im.final_T, im.n_contrib,
+                                                       im.tile_last, p.out_color, p.out_depth, p.out_alpha);
   else
-    blend_fwd_kernel<false><<<grid, FB, 0, s>>>(im.ranges, point_list, p.W, p.H, g.xy_ext, g.conic_opacity, g.rgb_depth,
-                                                p.background, im.final_T, im.n_contrib, im.tile_last, p.out_color,
-                                                nullptr, nullptr);
+    blend_fwd_kernel<false><<<grid, BL_THREADS, 0, s>>>(im.ranges, point_list, p.W, p.H, g.xy_ext, g.conic_opacity,
+                                                        g.rgb_depth, p.background, im.final_T, im.n_contrib,
+                                                        im.tile_last, p.out_color, nullptr, nullptr);
   return check_launch("blend_fwd", p.debug != 0, s);
 }
 
