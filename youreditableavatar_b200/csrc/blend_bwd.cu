@@ -52,7 +52,9 @@ __device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
 }
 
 template <bool EXTRAS>
-__global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint2* __restrict__ ranges,
+__global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint32_t* __restrict__ order, uint32_t* __restrict__ queue_counters,
+                                                               uint32_t num_tiles, uint32_t num_queues,
+                                                               const uint2* __restrict__ ranges,
                                                                const uint32_t* __restrict__ point_list, int W, int H,
                                                                const float* __restrict__ bg,
                                                                const float4* __restrict__ xy_ext,
@@ -74,7 +76,15 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint2* __re
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t tiles_x = (W + TILE - 1) / TILE;
-  const uint32_t tile_id = blockIdx.y * tiles_x + blockIdx.x;
+  __shared__ uint32_t s_rank;
+  if (warp == 0) {
+    const uint32_t r = fetch_tile_rank(queue_counters, num_tiles, num_queues, lane);
+    if (lane == 0) s_rank = r;
+  }
+  __syncthreads();
+  if (s_rank == NO_TILE) return;
+  const uint32_t tile_id = order[s_rank];
+  const uint32_t tile_bx = tile_id % tiles_x, tile_by = tile_id / tiles_x;
   const uint2 range = ranges[tile_id];
   const int total = (int)min(tile_last[tile_id], range.y - range.x);  // entries [0,total) can contribute
   if (total == 0) return;
@@ -90,20 +100,32 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint2* __re
 
   if (warp == 8) {
     // ======================= PRODUCER: back-to-front gather =======================
-    const float tile_x0 = (float)(blockIdx.x * TILE), tile_y0 = (float)(blockIdx.y * TILE);
+    const float tile_x0 = (float)(tile_bx * TILE), tile_y0 = (float)(tile_by * TILE);
+    const uint32_t* list = point_list + range.x;
+    uint32_t ids[BL_CHUNKS];
+    prod_load_ids(list, total, 0, true, lane, ids);
+    prod_issue(ids, xy_ext, conic_opacity, rgb_depth, s_xy[0], s_co[0], s_cd[0], s_id[0], lane);
+    prod_load_ids(list, total, BL_BATCH, true, lane, ids);
     for (int b = 0; b < rounds; ++b) {
       const int stage = b % BL_STAGES;
-      if (b >= BL_STAGES) mbar_wait(&s_empty[stage], ((b / BL_STAGES) - 1) & 1);
-      produce_batch(point_list + range.x, total, b * BL_BATCH, /*reverse=*/true, xy_ext, conic_opacity, rgb_depth,
-                    s_xy[stage], s_co[stage], s_cd[stage], s_id[stage], s_ball[stage], tile_x0, tile_y0, lane);
+      if (b + 1 < rounds) {  // put the gathers of batch b+1 in flight, prefetch the ids of batch b+2
+        const int nstage = (b + 1) % BL_STAGES;
+        if (b + 1 >= BL_STAGES) mbar_wait(&s_empty[nstage], (((b + 1) / BL_STAGES) - 1) & 1);
+        prod_issue(ids, xy_ext, conic_opacity, rgb_depth, s_xy[nstage], s_co[nstage], s_cd[nstage], s_id[nstage], lane);
+        prod_load_ids(list, total, (b + 2) * BL_BATCH, true, lane, ids);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      prod_classify(total, b * BL_BATCH, s_xy[stage], s_ball[stage], tile_x0, tile_y0, lane);
       mbar_arrive(&s_full[stage]);
     }
     return;
   }
 
   // ========================= CONSUMERS =========================
-  const uint32_t px = blockIdx.x * TILE + (warp & 1) * 8 + (lane & 7);
-  const uint32_t py = blockIdx.y * TILE + (warp >> 1) * 4 + (lane >> 3);
+  const uint32_t px = tile_bx * TILE + (warp & 1) * 8 + (lane & 7);
+  const uint32_t py = tile_by * TILE + (warp >> 1) * 4 + (lane >> 3);
   const bool inside = px < (uint32_t)W && py < (uint32_t)H;
   const uint32_t pix_id = (uint32_t)W * py + px;
   const float2 pixf = {(float)px, (float)py};
@@ -221,14 +243,16 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint2* __re
 
 int launch_blend_bwd(const tgr_params& p, const GeomView& g, const uint32_t* point_list, const ImageView& im,
                      float* grad_acc, cudaStream_t s) {
-  dim3 grid((p.W + TILE - 1) / TILE, (p.H + TILE - 1) / TILE, 1);
+  const uint32_t T = (uint32_t)((p.W + TILE - 1) / TILE) * ((p.H + TILE - 1) / TILE);
+  if (int rc = launch_tile_order(im.ranges, im.tile_last, T, im.order_bwd, im.queue_counters, s)) return rc;
+  const dim3 grid(T, 1, 1);
   const bool ex = p.extras && (p.dL_dout_depth || p.dL_dout_alpha);
   if (ex)
-    blend_bwd_kernel<true><<<grid, BL_THREADS, 0, s>>>(im.ranges, point_list, p.W, p.H, p.background, g.xy_ext, g.conic_opacity,
+    blend_bwd_kernel<true><<<grid, BL_THREADS, 0, s>>>(im.order_bwd, im.queue_counters, T, num_queues(), im.ranges, point_list, p.W, p.H, p.background, g.xy_ext, g.conic_opacity,
                                                g.rgb_depth, im.final_T, im.n_contrib, im.tile_last, p.dL_dout_color,
                                                p.dL_dout_depth, p.dL_dout_alpha, grad_acc);
   else
-    blend_bwd_kernel<false><<<grid, BL_THREADS, 0, s>>>(im.ranges, point_list, p.W, p.H, p.background, g.xy_ext, g.conic_opacity,
+    blend_bwd_kernel<false><<<grid, BL_THREADS, 0, s>>>(im.order_bwd, im.queue_counters, T, num_queues(), im.ranges, point_list, p.W, p.H, p.background, g.xy_ext, g.conic_opacity,
                                                 g.rgb_depth, im.final_T, im.n_contrib, im.tile_last, p.dL_dout_color,
                                                 nullptr, nullptr, grad_acc);
   return check_launch("blend_bwd", p.debug != 0, s);

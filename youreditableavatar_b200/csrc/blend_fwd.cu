@@ -24,8 +24,12 @@
 
 namespace tgr {
 
+constexpr int FG = 4;  // candidates evaluated together by a consumer warp
+
 template <bool EXTRAS>
-__global__ void __launch_bounds__(BL_THREADS) blend_fwd_kernel(const uint2* __restrict__ ranges,
+__global__ void __launch_bounds__(BL_THREADS) blend_fwd_kernel(const uint32_t* __restrict__ order, uint32_t* __restrict__ queue_counters,
+                                                               uint32_t num_tiles, uint32_t num_queues,
+                                                               const uint2* __restrict__ ranges,
                                                                const uint32_t* __restrict__ point_list, int W, int H,
                                                                const float4* __restrict__ xy_ext,
                                                                const float4* __restrict__ conic_opacity,
@@ -46,7 +50,15 @@ __global__ void __launch_bounds__(BL_THREADS) blend_fwd_kernel(const uint2* __re
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t tiles_x = (W + TILE - 1) / TILE;
-  const uint32_t tile_id = blockIdx.y * tiles_x + blockIdx.x;
+  __shared__ uint32_t s_rank;
+  if (warp == 0) {
+    const uint32_t r = fetch_tile_rank(queue_counters, num_tiles, num_queues, lane);
+    if (lane == 0) s_rank = r;
+  }
+  __syncthreads();
+  if (s_rank == NO_TILE) return;
+  const uint32_t tile_id = order[s_rank];
+  const uint32_t tile_bx = tile_id % tiles_x, tile_by = tile_id / tiles_x;
   const uint2 range = ranges[tile_id];
   const int total = (int)(range.y - range.x);
   const int rounds = (total + BL_BATCH - 1) / BL_BATCH;
@@ -63,26 +75,41 @@ __global__ void __launch_bounds__(BL_THREADS) blend_fwd_kernel(const uint2* __re
 
   if (warp == 8) {
     // ======================= PRODUCER =======================
-    const float tile_x0 = (float)(blockIdx.x * TILE), tile_y0 = (float)(blockIdx.y * TILE);
+    const float tile_x0 = (float)(tile_bx * TILE), tile_y0 = (float)(tile_by * TILE);
+    const uint32_t* list = point_list + range.x;
+    uint32_t ids[BL_CHUNKS];
+    if (rounds > 0) {
+      prod_load_ids(list, total, 0, false, lane, ids);
+      prod_issue(ids, xy_ext, conic_opacity, rgb_depth, s_xy[0], s_co[0], s_cd[0], nullptr, lane);
+      prod_load_ids(list, total, BL_BATCH, false, lane, ids);
+    }
     for (int b = 0; b < rounds; ++b) {
       const int stage = b % BL_STAGES;
-      if (b >= BL_STAGES) mbar_wait(&s_empty[stage], ((b / BL_STAGES) - 1) & 1);
       if (*(volatile uint32_t*)&s_done_warps == 8u) {  // every pixel of the tile has terminated
+        cp_async_wait<0>();
         if (lane == 0) s_stop[stage] = 1;
         __syncwarp();
         mbar_arrive(&s_full[stage]);
         break;
       }
-      produce_batch(point_list + range.x, total, b * BL_BATCH, /*reverse=*/false, xy_ext, conic_opacity, rgb_depth,
-                    s_xy[stage], s_co[stage], s_cd[stage], nullptr, s_ball[stage], tile_x0, tile_y0, lane);
+      if (b + 1 < rounds) {  // put the gathers of batch b+1 in flight, prefetch the ids of batch b+2
+        const int nstage = (b + 1) % BL_STAGES;
+        if (b + 1 >= BL_STAGES) mbar_wait(&s_empty[nstage], (((b + 1) / BL_STAGES) - 1) & 1);
+        prod_issue(ids, xy_ext, conic_opacity, rgb_depth, s_xy[nstage], s_co[nstage], s_cd[nstage], nullptr, lane);
+        prod_load_ids(list, total, (b + 2) * BL_BATCH, false, lane, ids);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      prod_classify(total, b * BL_BATCH, s_xy[stage], s_ball[stage], tile_x0, tile_y0, lane);
       mbar_arrive(&s_full[stage]);
     }
     return;
   }
 
   // ========================= CONSUMERS =========================
-  const uint32_t px = blockIdx.x * TILE + (warp & 1) * 8 + (lane & 7);
-  const uint32_t py = blockIdx.y * TILE + (warp >> 1) * 4 + (lane >> 3);
+  const uint32_t px = tile_bx * TILE + (warp & 1) * 8 + (lane & 7);
+  const uint32_t py = tile_by * TILE + (warp >> 1) * 4 + (lane >> 3);
   const bool inside = px < (uint32_t)W && py < (uint32_t)H;
   const uint32_t pix_id = (uint32_t)W * py + px;
   const float2 pixf = {(float)px, (float)py};
@@ -107,33 +134,46 @@ __global__ void __launch_bounds__(BL_THREADS) blend_fwd_kernel(const uint2* __re
 #pragma unroll 1
       for (int c = 0; c < BL_CHUNKS; ++c) {
         uint32_t m = s_ball[stage][warp][c];
+        // Candidates are taken FG at a time: their loads, power and exp are independent (ILP), only the
+        // transmittance update is a serial chain.  Profiling showed the kernel bound by the single-warp
+        // latency of the heaviest tile, not by SM throughput.
         while (m) {
-          const int bit = __ffs(m) - 1;
-          m &= m - 1;
-          const int j = c * 32 + bit;
-          if (!done) {
-            const float4 g = s_xy[stage][j];
+          int j[FG];
+          bool ok[FG];
+#pragma unroll
+          for (int k = 0; k < FG; ++k) {
+            ok[k] = m != 0;
+            j[k] = ok[k] ? (c * 32 + __ffs(m) - 1) : j[0];
+            m &= m - 1;
+          }
+          float alpha[FG];
+          float4 cd[FG];
+#pragma unroll
+          for (int k = 0; k < FG; ++k) {
+            const float4 g = s_xy[stage][j[k]];
+            const float4 con_o = s_co[stage][j[k]];
+            cd[k] = s_cd[stage][j[k]];
             const float2 d = {g.x - pixf.x, g.y - pixf.y};
-            const float4 con_o = s_co[stage][j];
             const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
-            if (power <= 0.0f) {
-              const float alpha = min(0.99f, con_o.w * expf(power));
-              if (alpha >= 1.0f / 255.0f) {
-                const float test_T = T * (1 - alpha);
-                if (test_T < 0.0001f) {
-                  done = true;
-                } else {
-                  const float4 cd = s_cd[stage][j];
-                  C[0] += cd.x * alpha * T;
-                  C[1] += cd.y * alpha * T;
-                  C[2] += cd.z * alpha * T;
-                  if (EXTRAS) Dz += cd.w * alpha * T;
-                  T = test_T;
-                  last_contributor = base_pos + j + 1;
-                }
-              }
+            alpha[k] = min(0.99f, con_o.w * expf(power));
+            ok[k] = ok[k] && (power <= 0.0f) && (alpha[k] >= 1.0f / 255.0f);
+          }
+#pragma unroll
+          for (int k = 0; k < FG; ++k) {
+            const float test_T = T * (1 - alpha[k]);
+            const bool act = ok[k] && !done;
+            const bool term = act && (test_T < 0.0001f);
+            done = done || term;
+            if (act && !term) {
+              C[0] += cd[k].x * alpha[k] * T;
+              C[1] += cd[k].y * alpha[k] * T;
+              C[2] += cd[k].z * alpha[k] * T;
+              if (EXTRAS) Dz += cd[k].w * alpha[k] * T;
+              T = test_T;
+              last_contributor = base_pos + j[k] + 1;
             }
           }
+          if (__all_sync(0xffffffffu, done)) break;
         }
         if (__all_sync(0xffffffffu, done)) break;
       }
@@ -168,13 +208,15 @@ __global__ void __launch_bounds__(BL_THREADS) blend_fwd_kernel(const uint2* __re
 
 int launch_blend_fwd(const tgr_params& p, const GeomView& g, const uint32_t* point_list, const ImageView& im,
                      cudaStream_t s) {
-  dim3 grid((p.W + TILE - 1) / TILE, (p.H + TILE - 1) / TILE, 1);
+  const uint32_t T = (uint32_t)((p.W + TILE - 1) / TILE) * ((p.H + TILE - 1) / TILE);
+  if (int rc = launch_tile_order(im.ranges, nullptr, T, im.order_fwd, im.queue_counters, s)) return rc;
+  const dim3 grid(T, 1, 1);
   if (p.extras && p.out_depth && p.out_alpha)
-    blend_fwd_kernel<true><<<grid, BL_THREADS, 0, s>>>(im.ranges, point_list, p.W, p.H, g.xy_ext, g.conic_opacity,
+    blend_fwd_kernel<true><<<grid, BL_THREADS, 0, s>>>(im.order_fwd, im.queue_counters, T, num_queues(), im.ranges, point_list, p.W, p.H, g.xy_ext, g.conic_opacity,
                                                        g.rgb_depth, p.background, im.final_T, im.n_contrib,
                                                        im.tile_last, p.out_color, p.out_depth, p.out_alpha);
   else
-    blend_fwd_kernel<false><<<grid, BL_THREADS, 0, s>>>(im.ranges, point_list, p.W, p.H, g.xy_ext, g.conic_opacity,
+    blend_fwd_kernel<false><<<grid, BL_THREADS, 0, s>>>(im.order_fwd, im.queue_counters, T, num_queues(), im.ranges, point_list, p.W, p.H, g.xy_ext, g.conic_opacity,
                                                         g.rgb_depth, p.background, im.final_T, im.n_contrib,
                                                         im.tile_last, p.out_color, nullptr, nullptr);
   return check_launch("blend_fwd", p.debug != 0, s);

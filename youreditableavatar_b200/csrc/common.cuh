@@ -112,11 +112,16 @@ __host__ __device__ inline GeomView carve_geom(void* base, int32_t P) {
   return g;
 }
 
+constexpr int MAX_QUEUES = 1024;
+
 struct ImageView {
   float* final_T;        // [N] transmittance left after blending
   uint32_t* n_contrib;   // [N] 1-based index in the tile list of the last blended Gaussian
   uint2* ranges;         // [T] [start,end) of each tile in the sorted instance list
   uint32_t* tile_last;   // [T] max n_contrib over the pixels of the tile (lets the backward skip the tail)
+  uint32_t* order_fwd;   // [T] tile ids, heaviest (longest list) first: CTA i of blend_fwd renders tile order_fwd[i]
+  uint32_t* order_bwd;   // [T] same for the backward, by tile_last
+  uint32_t* queue_counters;  // [MAX_QUEUES] per-SM work-queue cursors of the blend kernels (zeroed by tile_order)
   uint64_t bytes;
 };
 
@@ -129,6 +134,9 @@ __host__ __device__ inline ImageView carve_image(void* base, int32_t W, int32_t 
   v.n_contrib = carve<uint32_t>(p, N);
   v.ranges = carve<uint2>(p, T);
   v.tile_last = carve<uint32_t>(p, T);
+  v.order_fwd = carve<uint32_t>(p, T);
+  v.order_bwd = carve<uint32_t>(p, T);
+  v.queue_counters = carve<uint32_t>(p, MAX_QUEUES);
   v.bytes = (uint64_t)(p - static_cast<char*>(base)) + 128;
   return v;
 }
@@ -253,6 +261,9 @@ int launch_sort_pairs(uint64_t n_host, const uint32_t* n_dev, uint32_t* keys_a, 
                       uint32_t* vals_b, bool iota_vals, int begin_bit, int end_bit, uint32_t* temp, cudaStream_t s,
                       bool* result_in_b);
 int launch_emit(const tgr_params& p, const GeomView& g, const BinView& b, uint64_t cap, cudaStream_t s);
+int launch_tile_order(const uint2* ranges, const uint32_t* tile_last, uint32_t T, uint32_t* order,
+                      uint32_t* queue_counters, cudaStream_t s);
+uint32_t num_queues();  // number of SMs of the current device (one work queue per SM)
 int launch_ranges(const tgr_params& p, const GeomView& g, const uint32_t* sorted_keys, const ImageView& im,
                   uint64_t cap, cudaStream_t s);
 int launch_blend_fwd(const tgr_params& p, const GeomView& g, const uint32_t* point_list, const ImageView& im,

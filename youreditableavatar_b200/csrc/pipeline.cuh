@@ -11,6 +11,55 @@ constexpr int BL_STAGES = 4;                 // ring depth: consumers may drift 
 constexpr int BL_THREADS = 9 * 32;           // 8 consumer warps + 1 producer warp
 static_assert(8 * BL_CHUNKS == 32, "produce_batch maps one (block, chunk) ballot word to each producer lane");
 
+// ---- SM-affine work queues ------------------------------------------------------------------------------
+// Tiles are sorted heaviest-first (tile_order_kernel).  All non-empty tiles of an avatar view fit in the first
+// wave of CTAs, so WHICH SM a tile lands on decides the balance, and the hardware's CTA->SM placement is not
+// a simple modulo (measured on B200: tools/cuda/smid_map.cu).  Instead of trusting blockIdx, every CTA reads
+// %smid and pops the next rank of that SM's own queue; queue q holds the ranks dealt to it boustrophedon-wise
+// (q, 2n-1-q, 2n+q, 4n-1-q, ...) so per-SM sums of a sorted list are even.  A CTA whose queue is drained
+// steals from the others (warp-parallel scan of the counters), which also absorbs dynamic imbalance.
+constexpr uint32_t NO_TILE = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t queue_rank(uint32_t q, uint32_t k, uint32_t nq) {
+  return k * nq + ((k & 1u) ? (nq - 1u - q) : q);
+}
+
+// Called by warp 0 (all 32 lanes).  counters[nq] must be zero at kernel start.  Returns a rank < T or NO_TILE.
+__device__ __forceinline__ uint32_t fetch_tile_rank(uint32_t* __restrict__ counters, uint32_t T, uint32_t nq, int lane) {
+  uint32_t smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  const uint32_t q = smid % nq;
+  uint32_t r = NO_TILE;
+  if (lane == 0) {
+    const uint32_t k = atomicAdd(&counters[q], 1u);
+    r = queue_rank(q, k, nq);
+    if (r >= T) r = NO_TILE;
+  }
+  r = __shfl_sync(0xffffffffu, r, 0);
+  if (r != NO_TILE) return r;
+  // own queue drained: steal.  Each lane inspects queues q+1+lane, q+1+lane+32, ...
+  // (#CTAs == #ranks, so a CTA may only give up once every queue is observed drained)
+  while (true) {
+    uint32_t found = NO_TILE;
+    for (uint32_t i = lane; i < nq && found == NO_TILE; i += 32) {
+      const uint32_t qq = (q + 1u + i) % nq;
+      const uint32_t k = *(volatile uint32_t*)&counters[qq];
+      if (queue_rank(qq, k, nq) < T) found = qq;
+    }
+    const uint32_t have = __ballot_sync(0xffffffffu, found != NO_TILE);
+    if (!have) return NO_TILE;  // every queue is drained
+    const int src = __ffs(have) - 1;
+    const uint32_t qq = __shfl_sync(0xffffffffu, found, src);
+    if (lane == 0) {
+      const uint32_t k = atomicAdd(&counters[qq], 1u);
+      r = queue_rank(qq, k, nq);
+      if (r >= T) r = NO_TILE;
+    }
+    r = __shfl_sync(0xffffffffu, r, 0);
+    if (r != NO_TILE) return r;
+  }
+}
+
 // ---- mbarrier (shared::cta) ------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count)
@@ -65,23 +114,25 @@ __device__ __forceinline__ uint32_t block_mask(float x, float y, float hx, float
   return m;
 }
 
-// Producer warp: gathers BL_BATCH list entries starting at batch entry `first` into one ring stage.
+// ---- producer warp ------------------------------------------------------------------------------------
 // Batch entry e maps to list position e (forward) or total-1-e (reverse, for the back-to-front replay).
-// Records go global -> shared with 16-byte cp.async (no register staging); the footprint of each landed
-// record is then classified against the eight warp blocks and balloted into s_ball[block][chunk].
-__device__ __forceinline__ void produce_batch(const uint32_t* __restrict__ list, int total, int first, bool reverse,
-                                              const float4* __restrict__ xy_ext,
-                                              const float4* __restrict__ conic_opacity,
-                                              const float4* __restrict__ rgb_depth, float4* s_xy, float4* s_co,
-                                              float4* s_cd, uint32_t* s_id, uint32_t (*s_ball)[BL_CHUNKS],
-                                              float tile_x0, float tile_y0, int lane) {
-  uint32_t ids[BL_CHUNKS];
+// The producer is software-pipelined: ids of batch b+2 are prefetched into registers and the 16-byte
+// cp.async gathers of batch b+1 are in flight while the footprints of batch b are classified.
+__device__ __forceinline__ void prod_load_ids(const uint32_t* __restrict__ list, int total, int first, bool reverse,
+                                              int lane, uint32_t (&ids)[BL_CHUNKS]) {
 #pragma unroll
   for (int c = 0; c < BL_CHUNKS; ++c) {
     const int e = first + c * 32 + lane;
     ids[c] = 0xffffffffu;
-    if (e < total) ids[c] = list[reverse ? (total - 1 - e) : e];
+    if (e < total) ids[c] = __ldg(list + (reverse ? (total - 1 - e) : e));
   }
+}
+
+// Records go global -> shared with cp.async (no register staging); one commit group per batch.
+__device__ __forceinline__ void prod_issue(const uint32_t (&ids)[BL_CHUNKS], const float4* __restrict__ xy_ext,
+                                           const float4* __restrict__ conic_opacity,
+                                           const float4* __restrict__ rgb_depth, float4* s_xy, float4* s_co,
+                                           float4* s_cd, uint32_t* s_id, int lane) {
 #pragma unroll
   for (int c = 0; c < BL_CHUNKS; ++c) {
     if (ids[c] != 0xffffffffu) {
@@ -93,12 +144,16 @@ __device__ __forceinline__ void produce_batch(const uint32_t* __restrict__ list,
     }
   }
   cp_async_commit();
-  cp_async_wait<0>();
+}
+
+// Classifies the landed footprints of one batch against the eight warp blocks: s_ball[block][chunk].
+__device__ __forceinline__ void prod_classify(int total, int first, const float4* s_xy, uint32_t (*s_ball)[BL_CHUNKS],
+                                              float tile_x0, float tile_y0, int lane) {
   uint32_t keep = 0;
 #pragma unroll
   for (int c = 0; c < BL_CHUNKS; ++c) {
     uint32_t mm = 0;
-    if (ids[c] != 0xffffffffu) {
+    if (first + c * 32 + lane < total) {
       const float4 g = s_xy[c * 32 + lane];
       mm = block_mask(g.x, g.y, g.z, g.w, tile_x0, tile_y0);
     }
