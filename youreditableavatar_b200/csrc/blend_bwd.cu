@@ -18,6 +18,8 @@
 
 namespace tgr {
 
+constexpr int BG = 2;  // candidates evaluated together by a consumer warp
+
 // Sums 16 per-lane quantities over the warp; afterwards lane l holds the total of quantity l>>1.
 __device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
 #pragma unroll
@@ -165,74 +167,85 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint32_t* _
 #pragma unroll 1
       for (int c = 0; c < BL_CHUNKS; ++c) {
         uint32_t m = s_ball[stage][warp][c];
+        // Candidates are taken BG at a time so the loads / power / exp of one overlap the serial
+        // transmittance + colour recurrences and the butterfly reduction of the other.
         while (m) {
-          const int bit = __ffs(m) - 1;
-          m &= m - 1;
-          const int j = c * 32 + bit;
-          const int pos = batch_first_pos - j;  // 0-based list position
-          if (pos >= warp_last) continue;
-          bool valid = pos < last_contributor;
-          float G = 0.f, alpha = 0.f;
-          float2 d = {0.f, 0.f};
-          const float4 con_o = s_co[stage][j];
-          if (valid) {
-            const float4 g = s_xy[stage][j];
-            d = {g.x - pixf.x, g.y - pixf.y};
-            const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
-            if (power > 0.0f) valid = false;
-            else {
-              G = expf(power);
-              alpha = min(0.99f, con_o.w * G);
-              if (alpha < 1.0f / 255.0f) valid = false;
-            }
-          }
-          if (!__any_sync(0xffffffffu, valid)) continue;
-
-          float v[16];
+          int j[BG];
+          bool valid[BG];
+          float G[BG], alpha[BG];
+          float2 d[BG];
+          float4 con_o[BG], cd[BG];
+          bool has[BG];
+          int jmax = 0;
 #pragma unroll
-          for (int k = 0; k < 16; ++k) v[k] = 0.f;
-          if (valid) {
-            T = T / (1.f - alpha);
-            const float dchannel_dcolor = alpha * T;
-            const float4 cd = s_cd[stage][j];
-            const float c3[3] = {cd.x, cd.y, cd.z};
-            float dL_dalpha = 0.0f;
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-              accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
-              last_color[ch] = c3[ch];
-              dL_dalpha += (c3[ch] - accum_rec[ch]) * dpix[ch];
-            }
-            v[6] = dchannel_dcolor * dpix[0];
-            v[7] = dchannel_dcolor * dpix[1];
-            v[8] = dchannel_dcolor * dpix[2];
-            if (EXTRAS) {
-              accum_z = last_alpha * last_z + (1.f - last_alpha) * accum_z;
-              last_z = cd.w;
-              dL_dalpha += (cd.w - accum_z) * ddep;
-              v[9] = dchannel_dcolor * ddep;
-            }
-            dL_dalpha *= T;
-            last_alpha = alpha;
-            dL_dalpha += (-T_final / (1.f - alpha)) * tail;
-
-            const float dL_dG = con_o.w * dL_dalpha;
-            const float gdx = G * d.x;
-            const float gdy = G * d.y;
-            const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
-            const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
-            v[0] = dL_dG * dG_ddelx * ddelx_dx;
-            v[1] = dL_dG * dG_ddely * ddely_dy;
-            v[2] = -0.5f * gdx * d.x * dL_dG;
-            v[3] = -0.5f * gdx * d.y * dL_dG;
-            v[4] = -0.5f * gdy * d.y * dL_dG;
-            v[5] = G * dL_dalpha;
+          for (int k = 0; k < BG; ++k) {
+            has[k] = m != 0;
+            j[k] = has[k] ? (c * 32 + __ffs(m) - 1) : j[0];
+            m &= m - 1;
+            jmax = max(jmax, j[k]);
           }
-          const float sum = warp_reduce16(v, lane);
-          // lane 2q holds quantity q: one predicated RED, 9-10 consecutive floats of the accumulator row
-          const int q = lane >> 1;
-          if (!(lane & 1) && q < (EXTRAS ? 10 : 9))
-            atomicAdd(grad_acc + (size_t)s_id[stage][j] * GRAD_ACC + q, sum);
+          if (batch_first_pos - jmax >= warp_last) continue;  // all of them lie behind this block's last contributor
+#pragma unroll
+          for (int k = 0; k < BG; ++k) {
+            const int pos = batch_first_pos - j[k];  // 0-based list position
+            const float4 g = s_xy[stage][j[k]];
+            con_o[k] = s_co[stage][j[k]];
+            cd[k] = s_cd[stage][j[k]];
+            d[k] = {g.x - pixf.x, g.y - pixf.y};
+            const float power =
+                -0.5f * (con_o[k].x * d[k].x * d[k].x + con_o[k].z * d[k].y * d[k].y) - con_o[k].y * d[k].x * d[k].y;
+            G[k] = expf(power);
+            alpha[k] = min(0.99f, con_o[k].w * G[k]);
+            valid[k] = has[k] && (pos < last_contributor) && (power <= 0.0f) && (alpha[k] >= 1.0f / 255.0f);
+          }
+#pragma unroll
+          for (int k = 0; k < BG; ++k) {
+            if (!__any_sync(0xffffffffu, valid[k])) continue;
+            float v[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = 0.f;
+            if (valid[k]) {
+              T = __fdividef(T, 1.f - alpha[k]);
+              const float dchannel_dcolor = alpha[k] * T;
+              const float c3[3] = {cd[k].x, cd[k].y, cd[k].z};
+              float dL_dalpha = 0.0f;
+#pragma unroll
+              for (int ch = 0; ch < 3; ++ch) {
+                accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
+                last_color[ch] = c3[ch];
+                dL_dalpha += (c3[ch] - accum_rec[ch]) * dpix[ch];
+              }
+              v[6] = dchannel_dcolor * dpix[0];
+              v[7] = dchannel_dcolor * dpix[1];
+              v[8] = dchannel_dcolor * dpix[2];
+              if (EXTRAS) {
+                accum_z = last_alpha * last_z + (1.f - last_alpha) * accum_z;
+                last_z = cd[k].w;
+                dL_dalpha += (cd[k].w - accum_z) * ddep;
+                v[9] = dchannel_dcolor * ddep;
+              }
+              dL_dalpha *= T;
+              last_alpha = alpha[k];
+              dL_dalpha += __fdividef(-T_final, 1.f - alpha[k]) * tail;
+
+              const float dL_dG = con_o[k].w * dL_dalpha;
+              const float gdx = G[k] * d[k].x;
+              const float gdy = G[k] * d[k].y;
+              const float dG_ddelx = -gdx * con_o[k].x - gdy * con_o[k].y;
+              const float dG_ddely = -gdy * con_o[k].z - gdx * con_o[k].y;
+              v[0] = dL_dG * dG_ddelx * ddelx_dx;
+              v[1] = dL_dG * dG_ddely * ddely_dy;
+              v[2] = -0.5f * gdx * d[k].x * dL_dG;
+              v[3] = -0.5f * gdx * d[k].y * dL_dG;
+              v[4] = -0.5f * gdy * d[k].y * dL_dG;
+              v[5] = G[k] * dL_dalpha;
+            }
+            const float sum = warp_reduce16(v, lane);
+            // lane 2q holds quantity q: one predicated RED, 9-10 consecutive floats of the accumulator row
+            const int q = lane >> 1;
+            if (!(lane & 1) && q < (EXTRAS ? 10 : 9))
+              atomicAdd(grad_acc + (size_t)s_id[stage][j[k]] * GRAD_ACC + q, sum);
+          }
         }
       }
     }
