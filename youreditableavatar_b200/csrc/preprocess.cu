@@ -119,11 +119,29 @@ __device__ __forceinline__ void load_sh(const float* __restrict__ shs, size_t id
   }
 }
 
-template <bool BOUND>
+constexpr int SH_ROW = 48;        // floats per SH row at M = 16
+constexpr int SH_ROW_PAD = 49;    // padded shared-memory row stride (bank-conflict-free per-thread rows)
+
+// STAGED: the block's 256 SH rows (48 KB, contiguous in HBM) are moved global -> shared with fully coalesced
+// 16-byte loads; each thread then reads its own padded row.  Used when M == 16 and degree >= 2.
+template <bool BOUND, bool STAGED>
 __global__ void __launch_bounds__(256) preprocess_kernel(const tgr_params p, const tgr_binding bind, GeomView g) {
+  extern __shared__ float s_rows[];
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int P = p.P;
   uint32_t my_tiles = 0, my_vis = 0;
+  if (STAGED) {
+    const int block_first = blockIdx.x * blockDim.x;
+    const int nrows = min((int)blockDim.x, P - block_first);
+    const float4* src = reinterpret_cast<const float4*>(p.shs + (size_t)block_first * SH_ROW);
+    for (int v = threadIdx.x; v < nrows * (SH_ROW / 4); v += blockDim.x) {
+      const float4 q = __ldg(src + v);
+      const int e = v * 4;
+      float* d = s_rows + (e / SH_ROW) * SH_ROW_PAD + (e % SH_ROW);
+      d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
+    }
+    __syncthreads();
+  }
 
   if (idx < P) {
     int radius_out = 0;
@@ -203,11 +221,15 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const tgr_params p, con
           if (p.colors_precomp != nullptr) {
             rgb = {p.colors_precomp[3 * idx], p.colors_precomp[3 * idx + 1], p.colors_precomp[3 * idx + 2]};
           } else {
-            float sh[48];
-            const int ncoef = (p.D + 1) * (p.D + 1);
-            load_sh(p.shs, (size_t)idx, p.M, ncoef, sh);
             const float3 cam = {p.campos[0], p.campos[1], p.campos[2]};
-            rgb = sh_to_rgb(p.D, sh, p_orig, cam, clamped);
+            if (STAGED) {
+              rgb = sh_to_rgb(p.D, s_rows + threadIdx.x * SH_ROW_PAD, p_orig, cam, clamped);
+            } else {
+              float sh[48];
+              const int ncoef = (p.D + 1) * (p.D + 1);
+              load_sh(p.shs, (size_t)idx, p.M, ncoef, sh);
+              rgb = sh_to_rgb(p.D, sh, p_orig, cam, clamped);
+            }
           }
           // Conservative footprint of {alpha >= 1/255}: |dx| <= sqrt(2 tau Sxx), |dy| <= sqrt(2 tau Syy) with
           // tau = ln(255 o) and S the inverse of the conic actually used by the blend kernels.  Margins cover
@@ -262,11 +284,23 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const tgr_params p, con
 int launch_preprocess(const tgr_params& p, const tgr_binding* bind, const GeomView& g, cudaStream_t s) {
   const int blocks = (p.P + 255) / 256;
   if (blocks == 0) return 0;
+  const bool staged = p.colors_precomp == nullptr && p.shs != nullptr && p.M == 16 && p.D >= 2 &&
+                      (reinterpret_cast<uintptr_t>(p.shs) & 15) == 0;
+  const size_t smem = staged ? (size_t)256 * SH_ROW_PAD * sizeof(float) : 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(preprocess_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * SH_ROW_PAD * 4);
+    cudaFuncSetAttribute(preprocess_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * SH_ROW_PAD * 4);
+    attr_set = true;
+  }
+  tgr_binding none{};
+  const tgr_binding& b = bind ? *bind : none;
   if (bind) {
-    preprocess_kernel<true><<<blocks, 256, 0, s>>>(p, *bind, g);
+    if (staged) preprocess_kernel<true, true><<<blocks, 256, smem, s>>>(p, b, g);
+    else preprocess_kernel<true, false><<<blocks, 256, 0, s>>>(p, b, g);
   } else {
-    tgr_binding none{};
-    preprocess_kernel<false><<<blocks, 256, 0, s>>>(p, none, g);
+    if (staged) preprocess_kernel<false, true><<<blocks, 256, smem, s>>>(p, b, g);
+    else preprocess_kernel<false, false><<<blocks, 256, 0, s>>>(p, b, g);
   }
   return check_launch("preprocess", p.debug != 0, s);
 }

@@ -12,11 +12,32 @@ __device__ __forceinline__ void store3(float* p, size_t i, float a, float b, flo
   p[3 * i + 0] = a; p[3 * i + 1] = b; p[3 * i + 2] = c;
 }
 
-template <bool BOUND>
+constexpr int SH_ROW = 48;        // floats per SH row at M = 16
+constexpr int SH_ROW_PAD = 49;    // padded shared-memory row stride: 49*t mod 32 is a bijection over a warp
+
+// STAGED: the block's 256 SH rows (48 KB, contiguous in HBM) are moved global -> shared with fully coalesced
+// 16-byte loads, each thread then walks its own padded row bank-conflict-free; dL/dsh goes back the same way.
+// (One thread per Gaussian reading 48 floats at a 192-byte stride straight from global costs 32 sectors per
+// request — ncu showed the unstaged kernel at ~30% of HBM bandwidth.)
+template <bool BOUND, bool STAGED>
 __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p, const tgr_binding bind, GeomView g,
                                                              const float* __restrict__ grad_acc) {
+  extern __shared__ float s_rows[];
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= p.P) return;
+  const int block_first = blockIdx.x * blockDim.x;
+  const int nrows = min((int)blockDim.x, p.P - block_first);
+  if (STAGED) {
+    const float4* src = reinterpret_cast<const float4*>(p.shs + (size_t)block_first * SH_ROW);
+    for (int v = threadIdx.x; v < nrows * (SH_ROW / 4); v += blockDim.x) {
+      const float4 q = __ldg(src + v);
+      const int e = v * 4;
+      float* d = s_rows + (e / SH_ROW) * SH_ROW_PAD + (e % SH_ROW);
+      d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
+    }
+    __syncthreads();
+  }
+  float* const row = s_rows + threadIdx.x * SH_ROW_PAD;
+  if (idx < p.P) {
   const size_t i = (size_t)idx;
   const int M = p.M;
   const bool has_sh = (p.shs != nullptr && p.colors_precomp == nullptr && M > 0);
@@ -145,13 +166,14 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
     if (has_sh) {
       const int D = p.D;
       const int ncoef = (D + 1) * (D + 1);
-      float sh[48];
-      {
+      float sh_local[STAGED ? 1 : 48];
+      if (!STAGED) {
         const float* base = p.shs + i * (size_t)M * 3;
 #pragma unroll
         for (int k = 0; k < 48; ++k)
-          if (k < ncoef * 3) sh[k] = __ldg(base + k);
+          if (k < ncoef * 3) sh_local[k] = __ldg(base + k);
       }
+      const float* sh = STAGED ? row : sh_local;
       const float3 cam = {p.campos[0], p.campos[1], p.campos[2]};
       const float3 dir_orig = {mean.x - cam.x, mean.y - cam.y, mean.z - cam.z};
       const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
@@ -204,30 +226,25 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
           }
         }
       }
+      // view-direction term first (it still needs the SH values that the staged row is about to lose)
+      const float ddir[3] = {dRGBdx[0] * dRGB[0] + dRGBdx[1] * dRGB[1] + dRGBdx[2] * dRGB[2],
+                             dRGBdy[0] * dRGB[0] + dRGBdy[1] * dRGB[1] + dRGBdy[2] * dRGB[2],
+                             dRGBdz[0] * dRGB[0] + dRGBdz[1] * dRGB[1] + dRGBdz[2] * dRGB[2]};
       // dL/dsh rows; rows beyond the active degree are zero
-      float* out = p.dL_dsh + i * (size_t)M * 3;
-      if (((M * 3) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dL_dsh) & 15) == 0 && M <= 16) {
-        float tmp[48];
+      if (STAGED) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
           const float wk = (k < ncoef) ? w[k] : 0.f;
-          tmp[3 * k + 0] = wk * dRGB[0]; tmp[3 * k + 1] = wk * dRGB[1]; tmp[3 * k + 2] = wk * dRGB[2];
+          row[3 * k + 0] = wk * dRGB[0]; row[3 * k + 1] = wk * dRGB[1]; row[3 * k + 2] = wk * dRGB[2];
         }
-        float4* o4 = reinterpret_cast<float4*>(out);
-        const int nv = (M * 3) >> 2;
-#pragma unroll
-        for (int k = 0; k < 12; ++k)
-          if (k < nv) o4[k] = make_float4(tmp[4 * k], tmp[4 * k + 1], tmp[4 * k + 2], tmp[4 * k + 3]);
       } else {
+        float* out = p.dL_dsh + i * (size_t)M * 3;
         for (int k = 0; k < M; ++k) {
           const float wk = (k < ncoef && k < 16) ? w[k] : 0.f;
           out[3 * k + 0] = wk * dRGB[0]; out[3 * k + 1] = wk * dRGB[1]; out[3 * k + 2] = wk * dRGB[2];
         }
       }
-      // view-direction term into dL/dmean (normalisation Jacobian, auxiliary.h:107-117)
-      const float ddir[3] = {dRGBdx[0] * dRGB[0] + dRGBdx[1] * dRGB[1] + dRGBdx[2] * dRGB[2],
-                             dRGBdy[0] * dRGB[0] + dRGBdy[1] * dRGB[1] + dRGBdy[2] * dRGB[2],
-                             dRGBdz[0] * dRGB[0] + dRGBdz[1] * dRGB[1] + dRGBdz[2] * dRGB[2]};
+      // ... into dL/dmean through the normalisation Jacobian (auxiliary.h:107-117)
       const float3 v = dir_orig;
       const float sum2 = v.x * v.x + v.y * v.y + v.z * v.z;
       const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
@@ -261,11 +278,11 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
     }
   } else if (has_sh) {
     // culled Gaussian: its SH gradient rows are zero
-    float* out = p.dL_dsh + i * (size_t)M * 3;
-    if (((M * 3) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dL_dsh) & 15) == 0) {
-      float4* o4 = reinterpret_cast<float4*>(out);
-      for (int k = 0; k < (M * 3) >> 2; ++k) o4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (STAGED) {
+#pragma unroll
+      for (int k = 0; k < SH_ROW; ++k) row[k] = 0.f;
     } else {
+      float* out = p.dL_dsh + i * (size_t)M * 3;
       for (int k = 0; k < M * 3; ++k) out[k] = 0.f;
     }
   }
@@ -314,17 +331,40 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
         for (int c = 0; c < 3; ++c) atomicAdd(&bind.dL_dverts[3 * vi[k] + c], wv[k] * dmean[c]);
     }
   }
+  }  // idx < P
+  if (STAGED) {
+    __syncthreads();
+    float4* dst = reinterpret_cast<float4*>(p.dL_dsh + (size_t)block_first * SH_ROW);
+    for (int v = threadIdx.x; v < nrows * (SH_ROW / 4); v += blockDim.x) {
+      const int e = v * 4;
+      const float* d = s_rows + (e / SH_ROW) * SH_ROW_PAD + (e % SH_ROW);
+      dst[v] = make_float4(d[0], d[1], d[2], d[3]);
+    }
+  }
 }
 
 int launch_preprocess_bwd(const tgr_params& p, const tgr_binding* bind, const GeomView& g, const float* grad_acc,
                           cudaStream_t s) {
   const int blocks = (p.P + 255) / 256;
   if (blocks == 0) return 0;
+  const bool has_sh = (p.shs != nullptr && p.colors_precomp == nullptr && p.M > 0);
+  const bool staged = has_sh && p.M == 16 && p.D >= 2 && p.dL_dsh != nullptr &&
+                      (reinterpret_cast<uintptr_t>(p.shs) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.dL_dsh) & 15) == 0;
+  const size_t smem = staged ? (size_t)256 * SH_ROW_PAD * sizeof(float) : 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(preprocess_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * SH_ROW_PAD * 4);
+    cudaFuncSetAttribute(preprocess_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * SH_ROW_PAD * 4);
+    attr_set = true;
+  }
+  tgr_binding none{};
+  const tgr_binding& b = bind ? *bind : none;
   if (bind) {
-    preprocess_bwd_kernel<true><<<blocks, 256, 0, s>>>(p, *bind, g, grad_acc);
+    if (staged) preprocess_bwd_kernel<true, true><<<blocks, 256, smem, s>>>(p, b, g, grad_acc);
+    else preprocess_bwd_kernel<true, false><<<blocks, 256, 0, s>>>(p, b, g, grad_acc);
   } else {
-    tgr_binding none{};
-    preprocess_bwd_kernel<false><<<blocks, 256, 0, s>>>(p, none, g, grad_acc);
+    if (staged) preprocess_bwd_kernel<false, true><<<blocks, 256, smem, s>>>(p, b, g, grad_acc);
+    else preprocess_bwd_kernel<false, false><<<blocks, 256, 0, s>>>(p, b, g, grad_acc);
   }
   return check_launch("preprocess_bwd", p.debug != 0, s);
 }
