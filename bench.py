@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py — fwd+bwd rasterize views/s on the BASELINE.json workload.
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference]
+  (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...)
+
+A *step* = every rank renders V (default 8) different orbit views of the C3 scene — 1 M mesh-bound Gaussians,
+1024x1024, SH degree 3, forward + backward with the depth/alpha extras — accumulating the per-Gaussian
+gradients in one flat buffer, then (N > 1) all-reduces that buffer once.  Prints ONE JSON line on rank 0.
+
+  value   views/s over all ranks, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e     same metric through the public operator API with HOST buffers: every view's camera + upstream
+          gradients are copied from pinned host memory and the rendered image + a gradient checksum are read
+          back inside the timed region (Gaussian parameters are model state and stay resident, as in the
+          reference's training loops)
+  roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md.
+`--impl reference` times the UNMODIFIED reference CUDA rasterizer (oracle/_ref, built by oracle/build_ref.py)
+on the same scene through its own `_C` entry points; if that build is absent it falls back to the CPU oracle.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fwd+bwd rasterize views/s (1M Gaussians, 1024^2)"
+UNIT = "views/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C3")
+    ap.add_argument("--views-per-step", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc = gpu_index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return world, rank, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x, world):
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(x, world):
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+# ----------------------------------------------------------------------------------------------------
+def build_workload(cfg, V, rank, world):
+    from youreditableavatar_b200 import scene
+    P, res, _, g = scene.CONFIGS[cfg]
+    gs = scene.make_scene(cfg, device="cuda")
+    act = scene.activate(gs)
+    n_views = V * world
+    cams = [scene.orbit_camera(v, n_views, res, res, device="cuda") for v in range(rank, n_views, world)]
+    gen = torch.Generator().manual_seed(1 + rank)
+    N = res * res
+    up_host = []
+    for _ in range(V):
+        dc = (torch.randn(3, res, res, generator=gen) / (3 * N)).pin_memory()
+        dd = (torch.randn(1, res, res, generator=gen) / N).pin_memory()
+        da = (torch.randn(1, res, res, generator=gen) / N).pin_memory()
+        up_host.append((dc, dd, da))
+    up_dev = [tuple(t.cuda() for t in u) for u in up_host]
+    return P, res, act, cams, up_host, up_dev
+
+
+def cam_to_host(cam):
+    return {k: (v.cpu().pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in cam.items()}
+
+
+def cam_to_dev(cam):
+    return {k: (v.cuda(non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in cam.items()}
+
+
+class OursRunner:
+    name = "ours"
+
+    def __init__(self, P, res, act, extras=True):
+        from youreditableavatar_b200.parallel import GradBucket
+        self.act, self.extras = act, extras
+        self.bucket = GradBucket(P, 16, "cuda")
+
+    def step(self, cams, ups, world, host_io=None):
+        from youreditableavatar_b200.parallel import render_batch_fwd_bwd
+        if host_io is None:
+            render_batch_fwd_bwd(self.act, cams, 3, lambda i, c, d, a: ups[i], self.bucket, extras=self.extras)
+        else:
+            host_cams, host_ups, out_pinned = host_io
+            dev_cams = [cam_to_dev(c) for c in host_cams]
+
+            def upstream(i, color, depth, alpha):
+                out_pinned[i].copy_(color, non_blocking=True)          # D2H of the rendered image
+                return tuple(t.cuda(non_blocking=True) for t in host_ups[i])  # H2D of this view's upstream grads
+            render_batch_fwd_bwd(self.act, dev_cams, 3, upstream, self.bucket, extras=self.extras)
+        self.bucket.all_reduce()
+        if host_io is not None:
+            return float(self.bucket.flat[:1024].sum().item())           # D2H read of a gradient checksum
+        return None
+
+
+class RefRunner:
+    """The reference's own CUDA rasterizer (unmodified sources compiled into oracle/_ref)."""
+    name = "reference"
+
+    def __init__(self, P, res, act):
+        from oracle import ref_cuda
+        self.ref, self.act = ref_cuda, act
+        self.acc = None
+
+    def step(self, cams, ups, world, host_io=None):
+        if host_io is not None:
+            host_cams, host_ups, out_pinned = host_io
+            cams = [cam_to_dev(c) for c in host_cams]
+        for i, cam in enumerate(cams):
+            fwd = self.ref.forward(self.act, cam, 3)
+            if host_io is not None:
+                out_pinned[i].copy_(fwd[1], non_blocking=True)
+                dLc = host_ups[i][0].cuda(non_blocking=True)
+            else:
+                dLc = ups[i][0]
+            grads = self.ref.backward(self.act, cam, 3, fwd, dLc)
+            if i == 0:
+                self.acc = list(grads)            # first view: adopt the freshly zero-filled tensors
+            else:
+                for a, g in zip(self.acc, grads):  # later views: what a user of the reference has to do
+                    a.add_(g)
+        if world > 1:
+            import torch.distributed as dist
+            for a in self.acc:
+                dist.all_reduce(a)
+        if host_io is not None:
+            return float(self.acc[0].flatten()[:1024].sum().item())
+        return None
+
+
+def timed(runner, cams, ups, world, steps, warmup, host_io=None):
+    for _ in range(warmup):
+        runner.step(cams, ups, world, host_io)
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        runner.step(cams, ups, world, host_io)
+    e1.record()
+    barrier(world)
+    return max_over_ranks(e0.elapsed_time(e1), world)  # ms
+
+
+# ----------------------------------------------------------------------------------------------------
+def cpu_oracle_baseline(cfg, budget_tiles=24):
+    """float64 oracle (oracle/oracle.py) on a bounded sample of the same workload: the full per-Gaussian
+    preprocess + fwd+bwd blending of `budget_tiles` non-empty tiles, extrapolated by list entries."""
+    import numpy as np
+    from oracle import oracle
+    from youreditableavatar_b200 import scene
+    P, res, _, g = scene.CONFIGS[cfg]
+    torch.set_num_threads(os.cpu_count() or 1)
+    gs = {k: (v.cpu() if isinstance(v, torch.Tensor) else v) for k, v in scene.make_scene(cfg, device="cuda").items()}
+    act = {k: v.cpu() for k, v in scene.activate(gs).items()}
+    cam = scene.orbit_camera(0, 8, res, res, device="cpu")
+    t0 = time.time()
+    inp = {k: v.double().requires_grad_(True) for k, v in act.items()}
+    rec = oracle.preprocess(inp["means3D"], inp["opacities"], cam["viewmatrix"], cam["projmatrix"], cam["campos"], res, res,
+                            cam["tanfovx"], cam["tanfovy"], scales=inp["scales"], rotations=inp["rotations"],
+                            shs=inp["shs"], degree=3)
+    xy32 = rec["xy"].detach().numpy().astype(np.float32)
+    radii = torch.where(rec["valid"], rec["radius"].detach(), torch.zeros_like(rec["radius"])).numpy().astype(np.int32)
+    keys, ids, ranges, cnt = oracle.build_keys(xy32, radii, rec["depth"].detach().numpy().astype(np.float32), res, res)
+    t_pre = time.time() - t0
+    lens = (ranges[:, 1].astype(np.int64) - ranges[:, 0].astype(np.int64))
+    nonempty = np.flatnonzero(lens > 0)
+    rng = np.random.RandomState(0)
+    pick = rng.choice(nonempty, size=min(budget_tiles, len(nonempty)), replace=False)
+    sub = np.zeros_like(ranges)
+    sub[pick] = ranges[pick]
+    t1 = time.time()
+    color, depth, alpha, fT, nc = oracle.blend(rec, ids, sub, res, res, cam["bg"])
+    (color.sum() + depth.sum() + alpha.sum()).backward()
+    t_blend = time.time() - t1
+    frac = lens[pick].sum() / max(lens.sum(), 1)
+    per_view = t_pre + t_blend / max(frac, 1e-9)
+    return {"value": 1.0 / per_view, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "oracle/oracle.py float64: full preprocess+keys+sort of %d Gaussians (%.1f s) + fwd+bwd blend of "
+                      "%d of %d non-empty tiles (%.1f s, %.3f of the list entries), extrapolated to one view"
+                      % (P, t_pre, len(pick), len(nonempty), t_blend, frac)}
+
+
+def main():
+    args = parse()
+    world, rank, local = dist_setup(args)
+    if args.gpus != world and rank == 0 and world > 1:
+        print("warning: --gpus %d but WORLD_SIZE %d" % (args.gpus, world), file=sys.stderr)
+    V = args.views_per_step
+    cfg = args.config
+
+    if args.impl == "reference":
+        from oracle import ref_cuda
+        if not ref_cuda.available():
+            if rank == 0:
+                cb = cpu_oracle_baseline(cfg)
+                print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
+                                  "n_gpus": world, "steps": 1, "warmup": 0, "ms_per_step": 1000.0 / cb["value"],
+                                  "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                                  "data": "synthetic", "config": {"workload": cfg}, "cpu_baseline": cb,
+                                  "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                                          "d2h_bytes_per_step": 0},
+                                  "note": "reference CUDA build (oracle/_ref) absent: CPU oracle port timed instead"}))
+            return
+
+    P, res, act, cams, up_host, up_dev = build_workload(cfg, V, rank, world)
+    runner = OursRunner(P, res, act) if args.impl == "ours" else RefRunner(P, res, act)
+    from youreditableavatar_b200 import _lib
+    L = _lib.lib()
+
+    # ---- device-resident throughput (value) with per-stage events + clock sampling -------------------
+    for _ in range(max(args.warmup, 3)):
+        runner.step(cams, up_dev, world)
+    sampler = ClockSampler(local)
+    launches0 = L.tgr_kernel_launches()
+    if args.impl == "ours":
+        L.tgr_profile_enable(1)
+    sampler.start()
+    ms = timed(runner, cams, up_dev, world, args.steps, 0)
+    clocks = sampler.stop()
+    launches = L.tgr_kernel_launches() - launches0
+    stage = {}
+    if args.impl == "ours":
+        sums = (C.c_float * _lib.NUM_STAGES)()
+        cnts = (C.c_int32 * _lib.NUM_STAGES)()
+        L.tgr_profile_collect(sums, cnts)
+        L.tgr_profile_enable(0)
+        stage = {n: {"ms_avg": (sums[i] / cnts[i]) if cnts[i] else None, "launches": int(cnts[i])}
+                 for i, n in enumerate(_lib.STAGE_NAMES)}
+    views = V * world * args.steps
+    value = views / (ms / 1000.0)
+
+    # ---- end to end through the operator API with host buffers ------------------------------------------
+    host_cams = [cam_to_host(c) for c in cams]
+    out_pinned = [torch.empty(3, res, res).pin_memory() for _ in range(V)]
+    host_io = (host_cams, up_host, out_pinned)
+    ms_e2e = timed(runner, cams, up_dev, world, args.steps, max(1, args.warmup // 2), host_io)
+    e2e_value = views / (ms_e2e / 1000.0)
+    cam_bytes = sum(v.numel() * 4 for v in host_cams[0].values() if isinstance(v, torch.Tensor))
+    n_up = 3 if args.impl == "ours" else 1  # the reference has no depth/alpha outputs to back-propagate
+    h2d = V * (cam_bytes + sum(t.numel() * 4 for t in up_host[0][:n_up]))
+    d2h = V * (3 * res * res * 4) + 4
+
+    if rank != 0:
+        return
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: 1M mesh/tet-bound Gaussians (synthetic avatar shell, marching tets on a 376^3 Kuhn grid), "
+                               "1024x1024, SH degree 3, fwd+bwd with depth/alpha outputs" % cfg,
+                   "views_per_step_per_gpu": V, "global_views_per_step": V * world,
+                   "parallelism": "dp%d over views, 1 all-reduce of the flat gradient buffer per step" % world,
+                   "cache": "inputs (236 MB of parameters + 8 different cameras) exceed the 126 MB L2; no flush"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if args.impl == "ours":
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        # dominant kernel: blend_bwd.  Algorithmic bytes per launch: N*20 + R*40 + P*48
+        fo_R = []
+        from youreditableavatar_b200 import rasterizer as rz
+        e = torch.Tensor([])
+        cam = cams[0]
+        R0 = rz.c_rasterize_gaussians(cam["bg"], act["means3D"], e, act["opacities"], act["scales"], act["rotations"], 1.0,
+                                      e, cam["viewmatrix"], cam["projmatrix"], cam["tanfovx"], cam["tanfovy"], res, res,
+                                      act["shs"], 3, cam["campos"], False, False)[0]
+        alg = res * res * 20 + R0 * 40 + P * 48
+        dom = stage.get("blend_bwd", {}).get("ms_avg") or float("nan")
+        ach = alg / (dom * 1e-3) / 1e9
+        out["roofline"] = {"bound": "hbm", "kernel": "blend_bwd_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+                           "frac": ach / peak, "traffic": None, "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback",
+                           "algorithmic_bytes_per_launch": alg, "ms_per_launch": dom,
+                           "note": "blend_bwd is issue/latency bound (FP32 + shuffle), not HBM bound: see profiles/"}
+        out["stages"] = stage
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_oracle_baseline(cfg)
+    else:
+        out["impl"] = "reference"
+        out["reference_kind"] = "reference CUDA rasterizer, unmodified sources compiled for sm_100a into oracle/_ref"
+        out["gpu_launches"] = None
+        out["cpu_baseline"] = {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
+                               "sample": "not a CPU run: the reference ships no CPU rasterizer; this arm is its CUDA "
+                                         "rasterizer on the same B200 (see ours-arm cpu_baseline for the CPU oracle)"}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

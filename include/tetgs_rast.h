@@ -41,7 +41,8 @@ typedef struct tgr_params {
   int32_t prefiltered;  /* accepted for API parity; a culled point is simply skipped */
   int32_t debug;        /* 1: synchronise + report CUDA errors after every stage (auxiliary.h:166-173) */
   int32_t extras;       /* 1: also produce depth/alpha images (new) */
-  int32_t reserved0;
+  int32_t accumulate;   /* backward: 1 = add into the output gradient tensors instead of overwriting them
+                           (multi-view gradient accumulation without an extra pass; new) */
   /* camera (device pointers) */
   const float* background; /* [3] */
   const float* viewmatrix; /* [16] */
@@ -150,6 +151,24 @@ int tgr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, c
 uint64_t tgr_knn_bytes(int32_t P);
 int tgr_dist2(int32_t P, const float* points, float* mean_dist2, void* workspace, uint64_t workspace_bytes,
               void* stream);
+
+/* ---- per-stage device timing (CUDA events recorded on the launching stream) ----
+ * tgr_profile_enable(1) makes every subsequent stage launch bracket itself with events;
+ * tgr_profile_collect synchronises the recorded events and returns, per stage id (TGR_STAGE_*), the summed
+ * milliseconds and the number of launches since the last collect.  Arrays must hold TGR_NUM_STAGES entries. */
+#define TGR_STAGE_PREPROCESS 0
+#define TGR_STAGE_DEPTH_SORT 1
+#define TGR_STAGE_EMIT 2
+#define TGR_STAGE_TILE_SORT 3
+#define TGR_STAGE_RANGES 4
+#define TGR_STAGE_BLEND_FWD 5
+#define TGR_STAGE_BLEND_BWD 6
+#define TGR_STAGE_PREPROCESS_BWD 7
+#define TGR_NUM_STAGES 8
+/* Running count of CUDA kernels this library has launched in the calling process (memsets excluded). */
+uint64_t tgr_kernel_launches(void);
+int tgr_profile_enable(int on);
+int tgr_profile_collect(float* sum_ms, int32_t* launches);
 
 /* ---- parity / debugging helpers (used by tests; not on the hot path) ----
  * Reconstructs the reference's sorted 64-bit keys (tile << 32 | depth bits, rasterizer_impl.cu:102-104),

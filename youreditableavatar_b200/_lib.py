@@ -19,7 +19,7 @@ class TgrParams(C.Structure):
     _fields_ = [
         ("P", C.c_int32), ("D", C.c_int32), ("M", C.c_int32), ("W", C.c_int32), ("H", C.c_int32),
         ("tan_fovx", C.c_float), ("tan_fovy", C.c_float), ("scale_modifier", C.c_float),
-        ("prefiltered", C.c_int32), ("debug", C.c_int32), ("extras", C.c_int32), ("reserved0", C.c_int32),
+        ("prefiltered", C.c_int32), ("debug", C.c_int32), ("extras", C.c_int32), ("accumulate", C.c_int32),
         ("background", C.c_void_p), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p),
         ("means3D", C.c_void_p), ("shs", C.c_void_p), ("colors_precomp", C.c_void_p), ("opacities", C.c_void_p),
         ("scales", C.c_void_p), ("rotations", C.c_void_p), ("cov3D_precomp", C.c_void_p),
@@ -67,10 +67,16 @@ SYMBOLS = {
     "tgr_export_binning": (C.c_int, [C.POINTER(TgrParams), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tgr_export_geom": (C.c_int, [C.POINTER(TgrParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tgr_export_image_state": (C.c_int, [C.POINTER(TgrParams), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tgr_kernel_launches": (C.c_uint64, []),
+    "tgr_profile_enable": (C.c_int, [C.c_int]),
+    "tgr_profile_collect": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "tgr_sort_temp_bytes": (C.c_uint64, [C.c_uint64]),
     "tgr_sort_pairs_u32": (C.c_int, [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                      C.c_void_p, C.c_uint64, C.c_void_p]),
 }
+
+NUM_STAGES = 8
+STAGE_NAMES = ["preprocess", "depth_sort", "emit", "tile_sort", "ranges", "blend_fwd", "blend_bwd", "preprocess_bwd"]
 
 _lib = None
 

@@ -132,6 +132,7 @@ int launch_emit(const tgr_params& p, const GeomView& g, const BinView& b, uint64
   const uint32_t gw = (p.W + TILE - 1) / TILE;
   emit_kernel<<<ntiles, EMIT_THREADS, 0, s>>>(p.P, g.order, g.rect, gw, b.key_a, b.val_a,
                                               (uint32_t)std::min<uint64_t>(cap, 0xffffffffull), g.header, g.scan_state);
+  count_launch();
   return check_launch("emit", p.debug != 0, s);
 }
 
@@ -162,6 +163,7 @@ int launch_ranges(const tgr_params& p, const GeomView& g, const uint32_t* sorted
   if (cap == 0) return 0;
   const unsigned blocks = (unsigned)((cap + 255) / 256);
   ranges_kernel<<<blocks, 256, 0, s>>>(sorted_keys, (uint32_t)cap, g.header, im.ranges);
+  count_launch();
   return check_launch("ranges", p.debug != 0, s);
 }
 
@@ -235,6 +237,7 @@ uint32_t num_queues() {
 int launch_tile_order(const uint2* ranges, const uint32_t* tile_last, uint32_t T, uint32_t* order,
                       uint32_t* queue_counters, cudaStream_t s) {
   tile_order_kernel<<<1, 1024, 0, s>>>(ranges, tile_last, T, order, queue_counters);
+  count_launch();
   return check_launch("tile_order", false, s);
 }
 

@@ -268,6 +268,7 @@ int launch_blend_bwd(const tgr_params& p, const GeomView& g, const uint32_t* poi
     blend_bwd_kernel<false><<<grid, BL_THREADS, 0, s>>>(im.order_bwd, im.queue_counters, T, num_queues(), im.ranges, point_list, p.W, p.H, p.background, g.xy_ext, g.conic_opacity,
                                                 g.rgb_depth, im.final_T, im.n_contrib, im.tile_last, p.dL_dout_color,
                                                 nullptr, nullptr, grad_acc);
+  count_launch();
   return check_launch("blend_bwd", p.debug != 0, s);
 }
 

@@ -219,6 +219,7 @@ int launch_blend_fwd(const tgr_params& p, const GeomView& g, const uint32_t* poi
     blend_fwd_kernel<false><<<grid, BL_THREADS, 0, s>>>(im.order_fwd, im.queue_counters, T, num_queues(), im.ranges, point_list, p.W, p.H, g.xy_ext, g.conic_opacity,
                                                         g.rgb_depth, p.background, im.final_T, im.n_contrib,
                                                         im.tile_last, p.out_color, nullptr, nullptr);
+  count_launch();
   return check_launch("blend_fwd", p.debug != 0, s);
 }
 

@@ -2,11 +2,15 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include "common.cuh"
 
 namespace tgr {
 
 static thread_local char g_err[512] = "";
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -23,6 +27,35 @@ int check_launch(const char* what, bool debug, cudaStream_t s) {
     return 2;
   }
   return 0;
+}
+
+// ---- per-stage profiling ---------------------------------------------------------------------------
+constexpr int PROF_MAX = 4096;  // launches per stage between two collects
+struct ProfState {
+  bool on = false;
+  cudaEvent_t ev[TGR_NUM_STAGES][PROF_MAX][2];
+  int made[TGR_NUM_STAGES] = {};
+  int used[TGR_NUM_STAGES] = {};
+};
+static ProfState g_prof;
+
+void prof_begin(int stage, cudaStream_t s) {
+  if (!g_prof.on) return;
+  int& u = g_prof.used[stage];
+  if (u >= PROF_MAX) return;
+  if (u >= g_prof.made[stage]) {
+    cudaEventCreate(&g_prof.ev[stage][u][0]);
+    cudaEventCreate(&g_prof.ev[stage][u][1]);
+    g_prof.made[stage] = u + 1;
+  }
+  cudaEventRecord(g_prof.ev[stage][u][0], s);
+}
+void prof_end(int stage, cudaStream_t s) {
+  if (!g_prof.on) return;
+  int& u = g_prof.used[stage];
+  if (u >= PROF_MAX) return;
+  cudaEventRecord(g_prof.ev[stage][u][1], s);
+  ++u;
 }
 
 static cudaEvent_t count_event() {
@@ -55,6 +88,31 @@ using namespace tgr;
 extern "C" {
 
 int tgr_abi_version(void) { return TGR_ABI_VERSION; }
+
+uint64_t tgr_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int tgr_profile_enable(int on) {
+  g_prof.on = on != 0;
+  for (int i = 0; i < TGR_NUM_STAGES; ++i) g_prof.used[i] = 0;
+  return 0;
+}
+
+int tgr_profile_collect(float* sum_ms, int32_t* launches) {
+  for (int st = 0; st < TGR_NUM_STAGES; ++st) {
+    float sum = 0.f;
+    for (int i = 0; i < g_prof.used[st]; ++i) {
+      cudaError_t e = cudaEventSynchronize(g_prof.ev[st][i][1]);
+      float ms = 0.f;
+      if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, g_prof.ev[st][i][0], g_prof.ev[st][i][1]);
+      if (e != cudaSuccess) { set_error("profile_collect: %s", cudaGetErrorString(e)); return 2; }
+      sum += ms;
+    }
+    if (sum_ms) sum_ms[st] = sum;
+    if (launches) launches[st] = g_prof.used[st];
+    g_prof.used[st] = 0;
+  }
+  return 0;
+}
 const char* tgr_last_error(void) { return g_err; }
 
 uint64_t tgr_geom_bytes(int32_t P) { return carve_geom(nullptr, P).bytes; }
@@ -76,15 +134,19 @@ int tgr_forward_preprocess(const tgr_params* p, const tgr_binding* bind, void* s
   if (!p->colors_precomp && (!p->shs || p->M < (p->D + 1) * (p->D + 1))) { set_error("need colors_precomp or shs with M >= (D+1)^2"); return 1; }
   GeomView g = carve_geom(p->geom_buffer, p->P);
   cudaMemsetAsync(g.header, 0, sizeof(GeomHeader), s);
+  prof_begin(TGR_STAGE_PREPROCESS, s);
   if (int rc = launch_preprocess(*p, bind, g, s)) return rc;
+  prof_end(TGR_STAGE_PREPROCESS, s);
   if (p->host_num_rendered) {
     cudaMemcpyAsync(p->host_num_rendered, &g.header->num_rendered, sizeof(uint32_t), cudaMemcpyDeviceToHost, s);
     cudaEventRecord(count_event(), s);
   }
   // (depth bits, id) order of the Gaussians: positive floats compare like their bit patterns; bit 31 is 0
   bool in_b = false;
+  prof_begin(TGR_STAGE_DEPTH_SORT, s);
   if (int rc = launch_sort_pairs((uint64_t)p->P, nullptr, g.depth_key, g.order, g.key_alt, g.val_alt, true, 0, 32,
                                  g.sort_temp, s, &in_b)) return rc;
+  prof_end(TGR_STAGE_DEPTH_SORT, s);
   if (in_b) { set_error("internal: depth sort must end in buffer A"); return 3; }
   return check_launch("forward_preprocess", p->debug != 0, s);
 }
@@ -111,16 +173,24 @@ int tgr_forward_render(const tgr_params* p, uint64_t cap, void* stream) {
   ImageView im = carve_image(p->image_buffer, p->W, p->H);
   const uint32_t T = (uint32_t)((p->W + TILE - 1) / TILE) * ((p->H + TILE - 1) / TILE);
   if (p->P > 0 && cap > 0) {
+    prof_begin(TGR_STAGE_EMIT, s);
     if (int rc = launch_emit(*p, g, b, cap, s)) return rc;
+    prof_end(TGR_STAGE_EMIT, s);
     bool in_b = false;
+    prof_begin(TGR_STAGE_TILE_SORT, s);
     if (int rc = launch_sort_pairs(cap, &g.header->num_rendered, b.key_a, b.val_a, b.key_b, b.val_b, false, 0,
                                    tile_bits(T), b.sort_temp, s, &in_b)) return rc;
+    prof_end(TGR_STAGE_TILE_SORT, s);
+    prof_begin(TGR_STAGE_RANGES, s);
     if (int rc = launch_ranges(*p, g, in_b ? b.key_b : b.key_a, im, cap, s)) return rc;
+    prof_end(TGR_STAGE_RANGES, s);
   } else {
     cudaMemsetAsync(im.ranges, 0, (size_t)T * sizeof(uint2), s);
   }
   const uint32_t* plist = sorted_vals(p, b);
+  prof_begin(TGR_STAGE_BLEND_FWD, s);
   if (int rc = launch_blend_fwd(*p, g, plist, im, s)) return rc;
+  prof_end(TGR_STAGE_BLEND_FWD, s);
   return check_launch("forward_render", p->debug != 0, s);
 }
 
@@ -133,8 +203,12 @@ int tgr_backward(const tgr_params* p, const tgr_binding* bind, uint64_t cap, voi
   BinView b = carve_bin(p->binning_buffer, p->P, cap);
   ImageView im = carve_image(p->image_buffer, p->W, p->H);
   cudaMemsetAsync(b.grad_acc, 0, (size_t)p->P * GRAD_ACC * sizeof(float), s);
+  prof_begin(TGR_STAGE_BLEND_BWD, s);
   if (int rc = launch_blend_bwd(*p, g, sorted_vals(p, b), im, b.grad_acc, s)) return rc;
+  prof_end(TGR_STAGE_BLEND_BWD, s);
+  prof_begin(TGR_STAGE_PREPROCESS_BWD, s);
   if (int rc = launch_preprocess_bwd(*p, bind, g, b.grad_acc, s)) return rc;
+  prof_end(TGR_STAGE_PREPROCESS_BWD, s);
   return check_launch("backward", p->debug != 0, s);
 }
 
@@ -188,6 +262,7 @@ int tgr_export_binning(const tgr_params* p, uint64_t R, uint64_t* keys, uint32_t
   const uint32_t* tk = in_b ? b.key_b : b.key_a;
   if (R > 0 && (keys || ids))
     export_keys_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>((uint32_t)R, tk, vals, g.rgb_depth, keys, ids);
+    count_launch();
   if (ranges) {
     const uint32_t T = (uint32_t)((p->W + TILE - 1) / TILE) * ((p->H + TILE - 1) / TILE);
     cudaMemcpyAsync(ranges, im.ranges, (size_t)T * 8, cudaMemcpyDeviceToDevice, s);
@@ -217,6 +292,7 @@ int tgr_export_geom(const tgr_params* p, float* depth, float* xy, float* conic_o
   if (p->P == 0) return 0;
   GeomView g = carve_geom(p->geom_buffer, p->P);
   export_geom_kernel<<<(p->P + 255) / 256, 256, 0, s>>>(p->P, g, depth, xy, conic_opacity, rgb, tiles_touched);
+  count_launch();
   return check_launch("export_geom", true, s);
 }
 

@@ -253,7 +253,11 @@ __device__ constexpr float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f,
 // host-side plumbing
 // ---------------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
+// per-stage event timing (c_abi.cu); no-ops unless tgr_profile_enable(1)
+void prof_begin(int stage, cudaStream_t s);
+void prof_end(int stage, cudaStream_t s);
 int check_launch(const char* what, bool debug, cudaStream_t s);
+void count_launch(int n = 1);  // bookkeeping for tgr_kernel_launches()
 
 // stage launchers (each in its own .cu)
 int launch_preprocess(const tgr_params& p, const tgr_binding* bind, const GeomView& g, cudaStream_t s);

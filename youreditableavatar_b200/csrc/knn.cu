@@ -209,16 +209,22 @@ extern "C" int tgr_dist2(int32_t P, const float* points, float* mean_dist2, void
   KnnView k = carve_knn(workspace, P);
   int* b = reinterpret_cast<int*>(k.bounds);
   knn_bounds_init<<<1, 32, 0, s>>>(b);
+  count_launch();
   const int blocks = (P + 255) / 256;
   knn_bounds_kernel<<<min(blocks, NUM_SM * 8), 256, 0, s>>>(P, points, b);
+  count_launch();
   knn_morton_kernel<<<blocks, 256, 0, s>>>(P, points, b, k.codes_a);
+  count_launch();
   bool in_b = false;
   if (int rc = launch_sort_pairs((uint64_t)P, nullptr, k.codes_a, k.idx_a, k.codes_b, k.idx_b, true, 0, 32, k.sort_temp, s, &in_b))
     return rc;
   const uint32_t* idx = in_b ? k.idx_b : k.idx_a;
   knn_gather_kernel<<<blocks, 256, 0, s>>>(P, points, idx, k.sorted_pts);
+  count_launch();
   const int nbox = (P + KBOX - 1) / KBOX;
   knn_box_kernel<<<nbox, 256, 0, s>>>(P, k.sorted_pts, k.box_min, k.box_max);
+  count_launch();
   knn_search_kernel<<<blocks, 256, 0, s>>>(P, k.sorted_pts, idx, k.box_min, k.box_max, mean_dist2);
+  count_launch();
   return check_launch("dist2", false, s);
 }

@@ -302,6 +302,7 @@ int launch_preprocess(const tgr_params& p, const tgr_binding* bind, const GeomVi
     if (staged) preprocess_kernel<false, true><<<blocks, 256, smem, s>>>(p, b, g);
     else preprocess_kernel<false, false><<<blocks, 256, 0, s>>>(p, b, g);
   }
+  count_launch();
   return check_launch("preprocess", p.debug != 0, s);
 }
 
@@ -319,6 +320,7 @@ int launch_mark_visible(int32_t P, const float* means3D, const float* view, cons
                         cudaStream_t s) {
   if (P <= 0) return 0;
   mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, view, present);
+  count_launch();
   return check_launch("mark_visible", false, s);
 }
 

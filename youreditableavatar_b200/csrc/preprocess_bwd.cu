@@ -8,8 +8,10 @@
 
 namespace tgr {
 
-__device__ __forceinline__ void store3(float* p, size_t i, float a, float b, float c) {
-  p[3 * i + 0] = a; p[3 * i + 1] = b; p[3 * i + 2] = c;
+// acc = true: add into the destination (multi-view gradient accumulation), else overwrite
+__device__ __forceinline__ void put(float* p, float v, bool acc) { *p = acc ? (*p + v) : v; }
+__device__ __forceinline__ void store3(float* p, size_t i, float a, float b, float c, bool acc) {
+  put(p + 3 * i + 0, a, acc); put(p + 3 * i + 1, b, acc); put(p + 3 * i + 2, c, acc);
 }
 
 constexpr int SH_ROW = 48;        // floats per SH row at M = 16
@@ -241,7 +243,8 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
         float* out = p.dL_dsh + i * (size_t)M * 3;
         for (int k = 0; k < M; ++k) {
           const float wk = (k < ncoef && k < 16) ? w[k] : 0.f;
-          out[3 * k + 0] = wk * dRGB[0]; out[3 * k + 1] = wk * dRGB[1]; out[3 * k + 2] = wk * dRGB[2];
+          const bool acc_sh = p.accumulate != 0;
+          put(out + 3 * k + 0, wk * dRGB[0], acc_sh); put(out + 3 * k + 1, wk * dRGB[1], acc_sh); put(out + 3 * k + 2, wk * dRGB[2], acc_sh);
         }
       }
       // ... into dL/dmean through the normalisation Jacobian (auxiliary.h:107-117)
@@ -283,21 +286,27 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
       for (int k = 0; k < SH_ROW; ++k) row[k] = 0.f;
     } else {
       float* out = p.dL_dsh + i * (size_t)M * 3;
-      for (int k = 0; k < M * 3; ++k) out[k] = 0.f;
+      if (!p.accumulate) for (int k = 0; k < M * 3; ++k) out[k] = 0.f;
     }
   }
 
   // ---- write every output row -------------------------------------------------------------------
-  if (p.dL_dmeans2D) store3(p.dL_dmeans2D, i, dm2[0], dm2[1], 0.f);
-  if (p.dL_dcolors) store3(p.dL_dcolors, i, dcol[0], dcol[1], dcol[2]);
-  if (p.dL_dopacity) p.dL_dopacity[i] = dop;
-  if (p.dL_dmeans3D) store3(p.dL_dmeans3D, i, dmean[0], dmean[1], dmean[2]);
+  const bool acc = p.accumulate != 0;
+  if (p.dL_dmeans2D) store3(p.dL_dmeans2D, i, dm2[0], dm2[1], 0.f, acc);
+  if (p.dL_dcolors) store3(p.dL_dcolors, i, dcol[0], dcol[1], dcol[2], acc);
+  if (p.dL_dopacity) put(p.dL_dopacity + i, dop, acc);
+  if (p.dL_dmeans3D) store3(p.dL_dmeans3D, i, dmean[0], dmean[1], dmean[2], acc);
   if (p.dL_dcov3D) {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) p.dL_dcov3D[6 * i + k] = dcov[k];
+    for (int k = 0; k < 6; ++k) put(p.dL_dcov3D + 6 * i + k, dcov[k], acc);
   }
-  if (p.dL_dscales) store3(p.dL_dscales, i, dscale[0], dscale[1], dscale[2]);
-  if (p.dL_drotations) reinterpret_cast<float4*>(p.dL_drotations)[i] = make_float4(drot[0], drot[1], drot[2], drot[3]);
+  if (p.dL_dscales) store3(p.dL_dscales, i, dscale[0], dscale[1], dscale[2], acc);
+  if (p.dL_drotations) {
+    float4* o = reinterpret_cast<float4*>(p.dL_drotations) + i;
+    float4 v = make_float4(drot[0], drot[1], drot[2], drot[3]);
+    if (acc) { const float4 old = *o; v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w; }
+    *o = v;
+  }
 
   if (BOUND) {
     // chain rule through points = ori + n*delta, scale = exp(.), q = normalize(.), o = sigmoid(.)
@@ -308,19 +317,21 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
 #pragma unroll
     for (int c = 0; c < 3; ++c)
       n[c] = w0 * bind.vert_normals[3 * i0 + c] + w1 * bind.vert_normals[3 * i1 + c] + w2 * bind.vert_normals[3 * i2 + c];
-    if (bind.dL_ddelta) bind.dL_ddelta[i] = n[0] * dmean[0] + n[1] * dmean[1] + n[2] * dmean[2];
-    if (bind.dL_dlog_scales) store3(bind.dL_dlog_scales, i, dscale[0] * scale.x, dscale[1] * scale.y, dscale[2] * scale.z);
+    if (bind.dL_ddelta) put(bind.dL_ddelta + i, n[0] * dmean[0] + n[1] * dmean[1] + n[2] * dmean[2], acc);
+    if (bind.dL_dlog_scales) store3(bind.dL_dlog_scales, i, dscale[0] * scale.x, dscale[1] * scale.y, dscale[2] * scale.z, acc);
     if (bind.dL_draw_quats) {
       const float4 q = reinterpret_cast<const float4*>(bind.raw_quats)[i];
       const float qn = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
       const float dotp = rot.x * drot[0] + rot.y * drot[1] + rot.z * drot[2] + rot.w * drot[3];
-      reinterpret_cast<float4*>(bind.dL_draw_quats)[i] =
-          make_float4((drot[0] - rot.x * dotp) / qn, (drot[1] - rot.y * dotp) / qn, (drot[2] - rot.z * dotp) / qn,
-                      (drot[3] - rot.w * dotp) / qn);
+      float4* o = reinterpret_cast<float4*>(bind.dL_draw_quats) + i;
+      float4 v = make_float4((drot[0] - rot.x * dotp) / qn, (drot[1] - rot.y * dotp) / qn, (drot[2] - rot.z * dotp) / qn,
+                             (drot[3] - rot.w * dotp) / qn);
+      if (acc) { const float4 old = *o; v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w; }
+      *o = v;
     }
     if (bind.dL_dopacity_logits) {
       const float o = bind.out_opacities[i];
-      bind.dL_dopacity_logits[i] = dop * o * (1.f - o);
+      put(bind.dL_dopacity_logits + i, dop * o * (1.f - o), acc);
     }
     if (bind.dL_dverts && radius > 0) {
       const int vi[3] = {i0, i1, i2};
@@ -338,7 +349,9 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
     for (int v = threadIdx.x; v < nrows * (SH_ROW / 4); v += blockDim.x) {
       const int e = v * 4;
       const float* d = s_rows + (e / SH_ROW) * SH_ROW_PAD + (e % SH_ROW);
-      dst[v] = make_float4(d[0], d[1], d[2], d[3]);
+      float4 o = make_float4(d[0], d[1], d[2], d[3]);
+      if (p.accumulate) { const float4 old = dst[v]; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+      dst[v] = o;
     }
   }
 }
@@ -366,6 +379,7 @@ int launch_preprocess_bwd(const tgr_params& p, const tgr_binding* bind, const Ge
     if (staged) preprocess_bwd_kernel<false, true><<<blocks, 256, smem, s>>>(p, b, g, grad_acc);
     else preprocess_bwd_kernel<false, false><<<blocks, 256, 0, s>>>(p, b, g, grad_acc);
   }
+  count_launch();
   return check_launch("preprocess_bwd", p.debug != 0, s);
 }
 

@@ -225,6 +225,7 @@ int launch_sort_pairs(uint64_t n_host, const uint32_t* n_dev, uint32_t* keys_a, 
   cudaMemsetAsync(temp, 0, zero_bytes, s);
   int hist_blocks = (int)std::min<uint64_t>((n_host + 256 * 16 - 1) / (256 * 16), (uint64_t)NUM_SM * 8);
   radix_hist_kernel<<<hist_blocks, 256, 0, s>>>(keys_a, (uint32_t)n_host, n_dev, plan, ghist);
+  count_launch();
   const uint32_t* kin = keys_a; const uint32_t* vin = vals_a;
   uint32_t* kout = keys_b; uint32_t* vout = vals_b;
   for (int ps = 0; ps < plan.npasses; ++ps) {
@@ -235,6 +236,7 @@ int launch_sort_pairs(uint64_t n_host, const uint32_t* n_dev, uint32_t* keys_a, 
     else
       radix_pass_kernel<false><<<(unsigned)ntiles, RS_THREADS, RS_SMEM, s>>>(
           kin, vin, kout, vout, (uint32_t)n_host, n_dev, plan.begin[ps], plan.bits[ps], ghist + ps * RS_BINS, tickets + ps, lb);
+    count_launch();
     const uint32_t* tk = kin; const uint32_t* tv = vin;
     kin = kout; vin = vout;
     kout = const_cast<uint32_t*>(tk); vout = const_cast<uint32_t*>(tv);

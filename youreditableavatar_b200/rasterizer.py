@@ -169,9 +169,12 @@ def c_rasterize_gaussians(bg, means3D, colors, opacity, scales, rotations, scale
 def c_rasterize_gaussians_backward(bg, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp,
                                    viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, sh, degree, campos,
                                    geomBuffer, R, binningBuffer, imageBuffer, debug, dL_dout_depth=None,
-                                   dL_dout_alpha=None, binding=None):
+                                   dL_dout_alpha=None, binding=None, accumulate_into=None, out=None):
     """`_C.rasterize_gaussians_backward` (rasterize_points.cu:117-196): same 21 positional args, same 8-tuple
-    (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)."""
+    (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations).
+    New: accumulate_into=<that 8-tuple from an earlier call> adds this view's gradients into those tensors
+    inside the kernels (multi-view batches) and returns them; out=<8-tuple> overwrites caller-provided tensors
+    (e.g. views into one flat all-reduce buffer) instead of allocating."""
     _require_cuda(means3D)
     device = means3D.device
     P = means3D.size(0)
@@ -197,21 +200,26 @@ def c_rasterize_gaussians_backward(bg, means3D, radii, colors, scales, rotations
         dL_dout_color = _f32c(dL_dout_color, "dL_dout_color", device)
         radii = radii.contiguous()
 
-        # every element is written by the kernels -> empty, not zeros (the reference fills nine zero tensors)
-        dL_dmeans3D = torch.empty(P, 3, **f32)
-        dL_dmeans2D = torch.empty(P, 3, **f32)
-        dL_dcolors = torch.empty(P, 3, **f32)
-        dL_dopacity = torch.empty(P, 1, **f32)
-        dL_dcov3D = torch.empty(P, 6, **f32)
         sh_path = M > 0 and colors.numel() == 0
-        dL_dsh = torch.empty(P, M, 3, **f32) if sh_path else torch.zeros(P, M, 3, **f32)
-        dL_dscales = torch.empty(P, 3, **f32)
-        dL_drotations = torch.empty(P, 4, **f32)
+        if accumulate_into is not None or out is not None:
+            (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales,
+             dL_drotations) = accumulate_into if accumulate_into is not None else out
+        else:
+            # every element is written by the kernels -> empty, not zeros (the reference fills nine zero tensors)
+            dL_dmeans3D = torch.empty(P, 3, **f32)
+            dL_dmeans2D = torch.empty(P, 3, **f32)
+            dL_dcolors = torch.empty(P, 3, **f32)
+            dL_dopacity = torch.empty(P, 1, **f32)
+            dL_dcov3D = torch.empty(P, 6, **f32)
+            dL_dsh = torch.empty(P, M, 3, **f32) if sh_path else torch.zeros(P, M, 3, **f32)
+            dL_dscales = torch.empty(P, 3, **f32)
+            dL_drotations = torch.empty(P, 4, **f32)
 
         p = TgrParams()
         _fill_common(p, bg, means3D, colors, None_t, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
                      projmatrix, tan_fovx, tan_fovy, H, W, sh, degree, campos, debug)
         p.extras = 1 if (dL_dout_depth is not None or dL_dout_alpha is not None) else 0
+        p.accumulate = 1 if accumulate_into is not None else 0
         p.geom_buffer, p.geom_bytes = geomBuffer.data_ptr(), geomBuffer.numel()
         p.binning_buffer, p.binning_bytes = binningBuffer.data_ptr(), binningBuffer.numel()
         p.image_buffer, p.image_bytes = imageBuffer.data_ptr(), imageBuffer.numel()
