@@ -37,7 +37,7 @@ UNIT = "views/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C3")
@@ -59,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -159,28 +159,84 @@ def cam_to_dev(cam):
     return {k: (v.cuda(non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in cam.items()}
 
 
+class HostFeeder:
+    """Per-view host<->device traffic of the e2e leg, overlapped with rendering on two side streams: the camera
+    and upstream gradients of view i+1 are copied from pinned memory while view i renders; rendered images go
+    back to pinned memory on a third stream.  The same feeder serves both arms."""
+
+    def __init__(self, host_cams, host_ups, out_pinned, n_up):
+        self.cams, self.ups, self.out, self.n_up = host_cams, host_ups, out_pinned, n_up
+        self.s_in, self.s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        self.keep = []
+        self.slot = {}
+
+    def begin_step(self):
+        self.keep.clear()
+        self.slot.clear()
+        self._prefetch(0)
+
+    def _prefetch(self, i):
+        if i >= len(self.cams):
+            return
+        with torch.cuda.stream(self.s_in):
+            cam = {k: (v.cuda(non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in self.cams[i].items()}
+            ups = tuple(t.cuda(non_blocking=True) for t in self.ups[i][:self.n_up])
+            ev = torch.cuda.Event()
+            ev.record(self.s_in)
+        self.slot[i] = (cam, ups, ev)
+
+    def view(self, i):
+        cam, ups, ev = self.slot[i]
+        torch.cuda.current_stream().wait_event(ev)
+        self.keep.append((cam, ups))
+        self._prefetch(i + 1)
+        return cam, ups
+
+    def image_out(self, i, color):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(ev)
+            self.out[i].copy_(color, non_blocking=True)
+        self.keep.append(color)
+
+    def end_step(self):
+        torch.cuda.current_stream().wait_stream(self.s_out)
+
+
 class OursRunner:
     name = "ours"
+    n_up = 3
 
     def __init__(self, P, res, act, extras=True):
         from youreditableavatar_b200.parallel import GradBucket
         self.act, self.extras = act, extras
-        self.bucket = GradBucket(P, 16, "cuda")
+        self.bucket = GradBucket(P, 16, "cuda", names=GradBucket.TRAINING)
 
-    def step(self, cams, ups, world, host_io=None):
-        from youreditableavatar_b200.parallel import render_batch_fwd_bwd
-        if host_io is None:
-            render_batch_fwd_bwd(self.act, cams, 3, lambda i, c, d, a: ups[i], self.bucket, extras=self.extras)
-        else:
-            host_cams, host_ups, out_pinned = host_io
-            dev_cams = [cam_to_dev(c) for c in host_cams]
-
-            def upstream(i, color, depth, alpha):
-                out_pinned[i].copy_(color, non_blocking=True)          # D2H of the rendered image
-                return tuple(t.cuda(non_blocking=True) for t in host_ups[i])  # H2D of this view's upstream grads
-            render_batch_fwd_bwd(self.act, dev_cams, 3, upstream, self.bucket, extras=self.extras)
+    def step(self, cams, ups, world, feeder=None):
+        from youreditableavatar_b200 import rasterizer as rz
+        e = torch.Tensor([])
+        act = self.act
+        if feeder is not None:
+            feeder.begin_step()
+        for i in range(len(cams)):
+            cam, up = (cams[i], ups[i]) if feeder is None else feeder.view(i)
+            fwd = rz.c_rasterize_gaussians(cam["bg"], act["means3D"], e, act["opacities"], act["scales"], act["rotations"],
+                                           1.0, e, cam["viewmatrix"], cam["projmatrix"], cam["tanfovx"], cam["tanfovy"],
+                                           cam["image_height"], cam["image_width"], act["shs"], 3, cam["campos"], False,
+                                           False, extras=self.extras)
+            R, color, radii, geom, binning, img = fwd[:6]
+            if feeder is not None:
+                feeder.image_out(i, color)
+            kw = dict(accumulate_into=self.bucket.views) if i > 0 else dict(out=self.bucket.views)
+            rz.c_rasterize_gaussians_backward(cam["bg"], act["means3D"], radii, e, act["scales"], act["rotations"], 1.0, e,
+                                              cam["viewmatrix"], cam["projmatrix"], cam["tanfovx"], cam["tanfovy"], up[0],
+                                              act["shs"], 3, cam["campos"], geom, R, binning, img, False,
+                                              dL_dout_depth=up[1] if self.extras else None,
+                                              dL_dout_alpha=up[2] if self.extras else None, **kw)
         self.bucket.all_reduce()
-        if host_io is not None:
+        if feeder is not None:
+            feeder.end_step()
             return float(self.bucket.flat[:1024].sum().item())           # D2H read of a gradient checksum
         return None
 
@@ -188,53 +244,53 @@ class OursRunner:
 class RefRunner:
     """The reference's own CUDA rasterizer (unmodified sources compiled into oracle/_ref)."""
     name = "reference"
+    n_up = 1  # it has no depth/alpha outputs to back-propagate
 
     def __init__(self, P, res, act):
         from oracle import ref_cuda
         self.ref, self.act = ref_cuda, act
         self.acc = None
 
-    def step(self, cams, ups, world, host_io=None):
-        if host_io is not None:
-            host_cams, host_ups, out_pinned = host_io
-            cams = [cam_to_dev(c) for c in host_cams]
-        for i, cam in enumerate(cams):
+    def step(self, cams, ups, world, feeder=None):
+        if feeder is not None:
+            feeder.begin_step()
+        for i in range(len(cams)):
+            cam, up = (cams[i], ups[i]) if feeder is None else feeder.view(i)
             fwd = self.ref.forward(self.act, cam, 3)
-            if host_io is not None:
-                out_pinned[i].copy_(fwd[1], non_blocking=True)
-                dLc = host_ups[i][0].cuda(non_blocking=True)
-            else:
-                dLc = ups[i][0]
-            grads = self.ref.backward(self.act, cam, 3, fwd, dLc)
+            if feeder is not None:
+                feeder.image_out(i, fwd[1])
+            grads = self.ref.backward(self.act, cam, 3, fwd, up[0])
+            need = (2, 3, 5, 6, 7)  # opacity, means3D, sh, scales, rotations — what ours accumulates too
             if i == 0:
-                self.acc = list(grads)            # first view: adopt the freshly zero-filled tensors
+                self.acc = [grads[k] for k in need]   # first view: adopt the freshly zero-filled tensors
             else:
-                for a, g in zip(self.acc, grads):  # later views: what a user of the reference has to do
-                    a.add_(g)
+                for a, k in zip(self.acc, need):        # later views: what a user of the reference has to do
+                    a.add_(grads[k])
         if world > 1:
             import torch.distributed as dist
             for a in self.acc:
                 dist.all_reduce(a)
-        if host_io is not None:
+        if feeder is not None:
+            feeder.end_step()
             return float(self.acc[0].flatten()[:1024].sum().item())
         return None
 
 
-def timed(runner, cams, ups, world, steps, warmup, host_io=None):
+def timed(runner, cams, ups, world, steps, warmup, feeder=None):
     for _ in range(warmup):
-        runner.step(cams, ups, world, host_io)
+        runner.step(cams, ups, world, feeder)
     barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        runner.step(cams, ups, world, host_io)
+        runner.step(cams, ups, world, feeder)
     e1.record()
     barrier(world)
     return max_over_ranks(e0.elapsed_time(e1), world)  # ms
 
 
 # ----------------------------------------------------------------------------------------------------
-def cpu_oracle_baseline(cfg, budget_tiles=24):
+def cpu_oracle_baseline(cfg, budget_tiles=160):
     """float64 oracle (oracle/oracle.py) on a bounded sample of the same workload: the full per-Gaussian
     preprocess + fwd+bwd blending of `budget_tiles` non-empty tiles, extrapolated by list entries."""
     import numpy as np
@@ -324,11 +380,11 @@ def main():
     # ---- end to end through the operator API with host buffers ------------------------------------------
     host_cams = [cam_to_host(c) for c in cams]
     out_pinned = [torch.empty(3, res, res).pin_memory() for _ in range(V)]
-    host_io = (host_cams, up_host, out_pinned)
-    ms_e2e = timed(runner, cams, up_dev, world, args.steps, max(1, args.warmup // 2), host_io)
+    feeder = HostFeeder(host_cams, up_host, out_pinned, runner.n_up)
+    ms_e2e = timed(runner, cams, up_dev, world, args.steps, max(1, args.warmup // 2), feeder)
     e2e_value = views / (ms_e2e / 1000.0)
     cam_bytes = sum(v.numel() * 4 for v in host_cams[0].values() if isinstance(v, torch.Tensor))
-    n_up = 3 if args.impl == "ours" else 1  # the reference has no depth/alpha outputs to back-propagate
+    n_up = runner.n_up
     h2d = V * (cam_bytes + sum(t.numel() * 4 for t in up_host[0][:n_up]))
     d2h = V * (3 * res * res * 4) + 4
 

@@ -14,6 +14,25 @@ __device__ __forceinline__ void store3(float* p, size_t i, float a, float b, flo
   put(p + 3 * i + 0, a, acc); put(p + 3 * i + 1, b, acc); put(p + 3 * i + 2, c, acc);
 }
 
+// Coalesced flush of a per-block output tile (NC floats per Gaussian) staged in shared memory: 16-byte
+// read-modify-write (acc) or store.  gdst + block_first*NC is 16-byte aligned because block_first % 256 == 0.
+template <int NC>
+__device__ __forceinline__ void flush_tile(float* __restrict__ gdst, const float* s_src, int block_first, int nrows,
+                                           bool acc) {
+  if (gdst == nullptr) return;
+  const int total = nrows * NC;
+  const int n4 = total >> 2;
+  float4* d4 = reinterpret_cast<float4*>(gdst + (size_t)block_first * NC);
+  const float4* s4 = reinterpret_cast<const float4*>(s_src);
+  for (int v = threadIdx.x; v < n4; v += blockDim.x) {
+    float4 o = s4[v];
+    if (acc) { const float4 old = d4[v]; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+    d4[v] = o;
+  }
+  float* dt = gdst + (size_t)block_first * NC;
+  for (int e = (n4 << 2) + threadIdx.x; e < total; e += blockDim.x) dt[e] = acc ? (dt[e] + s_src[e]) : s_src[e];
+}
+
 constexpr int SH_ROW = 48;        // floats per SH row at M = 16
 constexpr int SH_ROW_PAD = 49;    // padded shared-memory row stride: 49*t mod 32 is a bijection over a warp
 
@@ -39,6 +58,8 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
     __syncthreads();
   }
   float* const row = s_rows + threadIdx.x * SH_ROW_PAD;
+  float o_m2[2] = {0.f, 0.f}, o_col[3] = {0.f, 0.f, 0.f}, o_op = 0.f, o_mean[3] = {0.f, 0.f, 0.f};
+  float o_cov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, o_sc[3] = {0.f, 0.f, 0.f}, o_rot[4] = {0.f, 0.f, 0.f, 0.f};
   if (idx < p.P) {
   const size_t i = (size_t)idx;
   const int M = p.M;
@@ -290,23 +311,16 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
     }
   }
 
-  // ---- write every output row -------------------------------------------------------------------
-  const bool acc = p.accumulate != 0;
-  if (p.dL_dmeans2D) store3(p.dL_dmeans2D, i, dm2[0], dm2[1], 0.f, acc);
-  if (p.dL_dcolors) store3(p.dL_dcolors, i, dcol[0], dcol[1], dcol[2], acc);
-  if (p.dL_dopacity) put(p.dL_dopacity + i, dop, acc);
-  if (p.dL_dmeans3D) store3(p.dL_dmeans3D, i, dmean[0], dmean[1], dmean[2], acc);
-  if (p.dL_dcov3D) {
+  // ---- the P-sized outputs leave through shared memory (see the epilogue) ------------------------------
+  o_m2[0] = dm2[0]; o_m2[1] = dm2[1];
+  o_col[0] = dcol[0]; o_col[1] = dcol[1]; o_col[2] = dcol[2];
+  o_op = dop;
+  o_mean[0] = dmean[0]; o_mean[1] = dmean[1]; o_mean[2] = dmean[2];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) put(p.dL_dcov3D + 6 * i + k, dcov[k], acc);
-  }
-  if (p.dL_dscales) store3(p.dL_dscales, i, dscale[0], dscale[1], dscale[2], acc);
-  if (p.dL_drotations) {
-    float4* o = reinterpret_cast<float4*>(p.dL_drotations) + i;
-    float4 v = make_float4(drot[0], drot[1], drot[2], drot[3]);
-    if (acc) { const float4 old = *o; v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w; }
-    *o = v;
-  }
+  for (int k = 0; k < 6; ++k) o_cov[k] = dcov[k];
+  o_sc[0] = dscale[0]; o_sc[1] = dscale[1]; o_sc[2] = dscale[2];
+  o_rot[0] = drot[0]; o_rot[1] = drot[1]; o_rot[2] = drot[2]; o_rot[3] = drot[3];
+  const bool acc = p.accumulate != 0;
 
   if (BOUND) {
     // chain rule through points = ori + n*delta, scale = exp(.), q = normalize(.), o = sigmoid(.)
@@ -353,6 +367,35 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
       if (p.accumulate) { const float4 old = dst[v]; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
       dst[v] = o;
     }
+    __syncthreads();  // SH rows are out; the buffer is reused for the small outputs below
+  }
+  {
+    // stage [means3D 3 | scales 3 | rot 4 | opacity 1 | means2D 3 | colors 3 | cov3D 6] x 256 and flush coalesced
+    float* t_mean = s_rows;
+    float* t_sc = t_mean + 256 * 3;
+    float* t_rot = t_sc + 256 * 3;
+    float* t_op = t_rot + 256 * 4;
+    float* t_m2 = t_op + 256;
+    float* t_col = t_m2 + 256 * 3;
+    float* t_cov = t_col + 256 * 3;
+    const int t = threadIdx.x;
+    t_mean[3 * t] = o_mean[0]; t_mean[3 * t + 1] = o_mean[1]; t_mean[3 * t + 2] = o_mean[2];
+    t_sc[3 * t] = o_sc[0]; t_sc[3 * t + 1] = o_sc[1]; t_sc[3 * t + 2] = o_sc[2];
+    reinterpret_cast<float4*>(t_rot)[t] = make_float4(o_rot[0], o_rot[1], o_rot[2], o_rot[3]);
+    t_op[t] = o_op;
+    t_m2[3 * t] = o_m2[0]; t_m2[3 * t + 1] = o_m2[1]; t_m2[3 * t + 2] = 0.f;
+    t_col[3 * t] = o_col[0]; t_col[3 * t + 1] = o_col[1]; t_col[3 * t + 2] = o_col[2];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) t_cov[6 * t + k] = o_cov[k];
+    __syncthreads();
+    const bool accf = p.accumulate != 0;
+    flush_tile<3>(p.dL_dmeans3D, t_mean, block_first, nrows, accf);
+    flush_tile<3>(p.dL_dscales, t_sc, block_first, nrows, accf);
+    flush_tile<4>(p.dL_drotations, t_rot, block_first, nrows, accf);
+    flush_tile<1>(p.dL_dopacity, t_op, block_first, nrows, accf);
+    flush_tile<3>(p.dL_dmeans2D, t_m2, block_first, nrows, accf);
+    flush_tile<3>(p.dL_dcolors, t_col, block_first, nrows, accf);
+    flush_tile<6>(p.dL_dcov3D, t_cov, block_first, nrows, accf);
   }
 }
 
@@ -363,7 +406,7 @@ int launch_preprocess_bwd(const tgr_params& p, const tgr_binding* bind, const Ge
   const bool has_sh = (p.shs != nullptr && p.colors_precomp == nullptr && p.M > 0);
   const bool staged = has_sh && p.M == 16 && p.D >= 2 && p.dL_dsh != nullptr &&
                       (reinterpret_cast<uintptr_t>(p.shs) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.dL_dsh) & 15) == 0;
-  const size_t smem = staged ? (size_t)256 * SH_ROW_PAD * sizeof(float) : 0;
+  const size_t smem = staged ? (size_t)256 * SH_ROW_PAD * sizeof(float) : (size_t)256 * 23 * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(preprocess_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * SH_ROW_PAD * 4);
@@ -374,10 +417,10 @@ int launch_preprocess_bwd(const tgr_params& p, const tgr_binding* bind, const Ge
   const tgr_binding& b = bind ? *bind : none;
   if (bind) {
     if (staged) preprocess_bwd_kernel<true, true><<<blocks, 256, smem, s>>>(p, b, g, grad_acc);
-    else preprocess_bwd_kernel<true, false><<<blocks, 256, 0, s>>>(p, b, g, grad_acc);
+    else preprocess_bwd_kernel<true, false><<<blocks, 256, smem, s>>>(p, b, g, grad_acc);
   } else {
     if (staged) preprocess_bwd_kernel<false, true><<<blocks, 256, smem, s>>>(p, b, g, grad_acc);
-    else preprocess_bwd_kernel<false, false><<<blocks, 256, 0, s>>>(p, b, g, grad_acc);
+    else preprocess_bwd_kernel<false, false><<<blocks, 256, smem, s>>>(p, b, g, grad_acc);
   }
   count_launch();
   return check_launch("preprocess_bwd", p.debug != 0, s);

@@ -32,11 +32,19 @@ class GradBucket:
     `.views` are the eight gradient tensors aliasing it.  Offsets are multiples of 4 floats (16-byte vector
     stores in the kernels need the SH / rotation views 16-byte aligned)."""
 
-    def __init__(self, P: int, M: int, device="cuda"):
+    # what an optimizer over (means/delta, opacity, SH, scales, rotations) consumes; the other three exist in the
+    # reference's return tuple only because its kernels produce them on the way
+    TRAINING = ("dL_dopacity", "dL_dmeans3D", "dL_dsh", "dL_dscales", "dL_drotations")
+
+    def __init__(self, P: int, M: int, device="cuda", names: Optional[Sequence[str]] = None):
         self.P, self.M = P, M
         self.shapes = grad_shapes(P, M)
+        self.names = tuple(GRAD_NAMES if names is None else names)
         offs, total = [], 0
-        for shp in self.shapes:
+        for name, shp in zip(GRAD_NAMES, self.shapes):
+            if name not in self.names:
+                offs.append(None)
+                continue
             offs.append(total)
             n = 1
             for d in shp:
@@ -44,7 +52,7 @@ class GradBucket:
             total += (n + 3) // 4 * 4
         self.offsets = offs
         self.flat = torch.zeros(max(total, 1), dtype=torch.float32, device=device)
-        self.views = tuple(self._view(o, shp) for o, shp in zip(offs, self.shapes))
+        self.views = tuple(None if o is None else self._view(o, shp) for o, shp in zip(offs, self.shapes))
 
     def _view(self, off, shp):
         n = 1

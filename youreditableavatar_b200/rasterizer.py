@@ -231,14 +231,15 @@ def c_rasterize_gaussians_backward(bg, means3D, radii, colors, scales, rotations
         if dL_dout_alpha is not None:
             dL_dout_alpha = _f32c(dL_dout_alpha, "dL_dout_alpha", device)
             p.dL_dout_alpha = dL_dout_alpha.data_ptr()
-        p.dL_dmeans2D = dL_dmeans2D.data_ptr()
-        p.dL_dcolors = dL_dcolors.data_ptr()
-        p.dL_dopacity = dL_dopacity.data_ptr()
-        p.dL_dmeans3D = dL_dmeans3D.data_ptr()
-        p.dL_dcov3D = dL_dcov3D.data_ptr()
-        p.dL_dsh = dL_dsh.data_ptr() if sh_path else None
-        p.dL_dscales = dL_dscales.data_ptr()
-        p.dL_drotations = dL_drotations.data_ptr()
+        # a None entry (only possible through out= / accumulate_into=) means "do not produce this gradient"
+        p.dL_dmeans2D = _ptr(dL_dmeans2D)
+        p.dL_dcolors = _ptr(dL_dcolors)
+        p.dL_dopacity = _ptr(dL_dopacity)
+        p.dL_dmeans3D = _ptr(dL_dmeans3D)
+        p.dL_dcov3D = _ptr(dL_dcov3D)
+        p.dL_dsh = _ptr(dL_dsh) if sh_path else None
+        p.dL_dscales = _ptr(dL_dscales)
+        p.dL_drotations = _ptr(dL_drotations)
         bptr = C.byref(binding) if binding is not None else None
         check(L.tgr_backward(C.byref(p), bptr, int(R), _stream(device)), "tgr_backward")
 
