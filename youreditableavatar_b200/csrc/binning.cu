@@ -69,26 +69,37 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_kernel(int P, const uint32_
     if (w < warp) woff += s_warp[w];
     btotal += s_warp[w];
   }
-  // chained scan across CTAs
-  if (tid == 0) {
+  // chained scan across CTAs: warp 0 looks back 32 predecessors per round trip (a one-word-per-hop walk by a
+  // single thread made the ~1000 resident CTAs a serial chain; ncu: 28 of 35 stall cycles were barrier waits)
+  if (warp == 0) {
     uint32_t excl = 0;
     if (tile == 0) {
-      stv(&scan_state[0], SC_FLAG_INC | btotal);
+      if (lane == 0) stv(&scan_state[0], SC_FLAG_INC | btotal);
     } else {
-      stv(&scan_state[tile], SC_FLAG_AGG | btotal);
-      const uint32_t* q = &scan_state[tile - 1];
+      if (lane == 0) stv(&scan_state[tile], SC_FLAG_AGG | btotal);
+      int t = (int)tile - 1;
       while (true) {
-        uint32_t v = ldv(q);
-        if ((v & ~SC_VALUE) == 0) continue;
-        excl += v & SC_VALUE;
-        if (v & SC_FLAG_INC) break;
-        --q;
+        const int idx = t - lane;
+        const uint32_t v = idx >= 0 ? ldv(&scan_state[idx]) : SC_FLAG_INC;
+        const uint32_t ready = __ballot_sync(0xffffffffu, (v & ~SC_VALUE) != 0);
+        const uint32_t incl = __ballot_sync(0xffffffffu, (v & SC_FLAG_INC) != 0);
+        // lanes 0..n-1 are contiguous ready entries; stop at the first inclusive one among them
+        const int n_ready = __ffs(~ready) - 1 < 0 ? 32 : __ffs(~ready) - 1;
+        const int first_inc = incl ? __ffs(incl) - 1 : 32;
+        const int take = min(n_ready, first_inc + 1);
+        uint32_t part = lane < take ? (v & SC_VALUE) : 0u;
+        part = __reduce_add_sync(0xffffffffu, part);
+        excl += part;
+        if (first_inc < n_ready) break;
+        t -= take;
       }
-      stv(&scan_state[tile], SC_FLAG_INC | (excl + btotal));
+      if (lane == 0) stv(&scan_state[tile], SC_FLAG_INC | (excl + btotal));
     }
-    s_prefix = excl;
-    const uint32_t ntiles = ((uint32_t)P + EMIT_TILE - 1) / EMIT_TILE;
-    if (tile == ntiles - 1 && excl + btotal > cap) header->overflow = 1u;
+    if (lane == 0) {
+      s_prefix = excl;
+      const uint32_t ntiles = ((uint32_t)P + EMIT_TILE - 1) / EMIT_TILE;
+      if (tile == ntiles - 1 && excl + btotal > cap) header->overflow = 1u;
+    }
   }
   __syncthreads();
   uint32_t off = s_prefix + woff + inc - tsum;
