@@ -118,7 +118,7 @@ const char* tgr_last_error(void);     /* thread-local message of the last non-ze
 /* ---- workspace sizes (pure functions of the arguments; rasterizer_impl.h:66-72 `required<T>`) ---- */
 uint64_t tgr_geom_bytes(int32_t P);
 uint64_t tgr_image_bytes(int32_t W, int32_t H);
-uint64_t tgr_binning_bytes(int32_t P, uint64_t num_rendered_capacity);
+uint64_t tgr_binning_bytes(int32_t P, uint64_t num_rendered_capacity, int32_t W, int32_t H);
 
 /* ---- forward: replaces CudaRasterizer::Rasterizer::forward (rasterizer_impl.cu:198-336) ----
  * Stage 1: per-Gaussian preprocess (forward.cu:155-256), depth ordering, total instance count.

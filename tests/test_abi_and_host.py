@@ -33,8 +33,8 @@ def test_workspace_sizes_are_pure_functions():
     a, b = L.tgr_geom_bytes(1000), L.tgr_geom_bytes(1000)
     assert a == b and L.tgr_geom_bytes(2000) > a
     assert L.tgr_image_bytes(1024, 1024) >= 1024 * 1024 * 8
-    assert L.tgr_binning_bytes(1000, 5000) > L.tgr_binning_bytes(1000, 1000)
-    assert L.tgr_binning_bytes(10, 10 ** 8) > 16 * 10 ** 8  # 64-bit sizes (C5-class instance counts)
+    assert L.tgr_binning_bytes(1000, 5000, 64, 64) > L.tgr_binning_bytes(1000, 1000, 64, 64)
+    assert L.tgr_binning_bytes(10, 10 ** 8, 64, 64) > 16 * 10 ** 8  # 64-bit sizes (C5-class instance counts)
     assert L.tgr_sort_temp_bytes(1 << 20) > 0 and L.tgr_knn_bytes(1000) > 0
 
 

@@ -186,7 +186,8 @@ constexpr int TO_BUCKETS = 4096;
 __global__ void __launch_bounds__(1024) tile_order_kernel(const uint2* __restrict__ ranges,
                                                           const uint32_t* __restrict__ tile_last, uint32_t T,
                                                           uint32_t* __restrict__ order,
-                                                          uint32_t* __restrict__ queue_counters) {
+                                                          uint32_t* __restrict__ queue_counters,
+                                                          uint32_t* __restrict__ seg_base) {
   __shared__ uint32_t s_cnt[TO_BUCKETS];
   __shared__ uint32_t s_warp[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -229,6 +230,79 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const uint2* __restric
   for (int k = 0; k < 4; ++k) { s_cnt[tid * 4 + k] = base; base += c[k]; }
   __syncthreads();
   for (uint32_t t = tid; t < T; t += 1024) order[atomicAdd(&s_cnt[bucket_of(t)], 1u)] = t;
+
+  // checkpoint slots: seg_base[t] = exclusive scan (tile-index order) of ceil(len_t / SEG); seg_base[T] = total
+  if (seg_base != nullptr) {
+    __shared__ uint32_t s_carry;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t t0 = 0; t0 < T; t0 += 1024) {
+      const uint32_t t = t0 + tid;
+      uint32_t n = 0;
+      if (t < T) { const uint2 r = ranges[t]; n = (r.y - r.x + SEG - 1) / SEG; }
+      uint32_t incl = n;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (lane == 31) s_warp[warp] = incl;
+      __syncthreads();
+      uint32_t woff = 0, tot = 0;
+#pragma unroll
+      for (int w = 0; w < 32; ++w) { if (w < warp) woff += s_warp[w]; tot += s_warp[w]; }
+      const uint32_t carry = s_carry;
+      if (t < T) seg_base[t] = carry + woff + incl - n;
+      __syncthreads();
+      if (tid == 0) s_carry = carry + tot;
+      __syncthreads();
+    }
+    if (tid == 0) seg_base[T] = s_carry;
+  }
+}
+
+// Backward work units: tile t contributes ceil(min(tile_last_t, len_t) / SEG) units (tile, segment).
+__global__ void __launch_bounds__(1024) unit_build_kernel(const uint2* __restrict__ ranges,
+                                                          const uint32_t* __restrict__ tile_last, uint32_t T,
+                                                          uint2* __restrict__ units, uint32_t units_cap,
+                                                          uint32_t* __restrict__ unit_count) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (uint32_t t0 = 0; t0 < T; t0 += 1024) {
+    const uint32_t t = t0 + tid;
+    uint32_t n = 0;
+    if (t < T) { const uint2 r = ranges[t]; n = (min(r.y - r.x, tile_last[t]) + SEG - 1) / SEG; }
+    uint32_t incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) { if (w < warp) woff += s_warp[w]; tot += s_warp[w]; }
+    const uint32_t carry = s_carry;
+    uint32_t u = carry + woff + incl - n;
+    // heaviest segment (the deepest one is usually shorter) first is irrelevant: units are <= SEG entries each
+    for (uint32_t k = 0; k < n; ++k, ++u)
+      if (u < units_cap) units[u] = make_uint2(t, k);
+    __syncthreads();
+    if (tid == 0) s_carry = carry + tot;
+    __syncthreads();
+  }
+  if (tid == 0) *unit_count = min(s_carry, units_cap);
+}
+
+int launch_unit_build(const uint2* ranges, const uint32_t* tile_last, uint32_t T, uint2* units, uint32_t units_cap,
+                      uint32_t* unit_count, cudaStream_t s) {
+  unit_build_kernel<<<1, 1024, 0, s>>>(ranges, tile_last, T, units, units_cap, unit_count);
+  count_launch();
+  return check_launch("unit_build", false, s);
 }
 
 uint32_t num_queues() {
@@ -246,8 +320,8 @@ uint32_t num_queues() {
 }
 
 int launch_tile_order(const uint2* ranges, const uint32_t* tile_last, uint32_t T, uint32_t* order,
-                      uint32_t* queue_counters, cudaStream_t s) {
-  tile_order_kernel<<<1, 1024, 0, s>>>(ranges, tile_last, T, order, queue_counters);
+                      uint32_t* queue_counters, uint32_t* seg_base, cudaStream_t s) {
+  tile_order_kernel<<<1, 1024, 0, s>>>(ranges, tile_last, T, order, queue_counters, seg_base);
   count_launch();
   return check_launch("tile_order", false, s);
 }

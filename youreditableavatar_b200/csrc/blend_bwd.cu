@@ -13,6 +13,7 @@
 //   * all per-Gaussian 2D gradients land in one packed accumulator row grad_acc[g][12]
 //     {dmean2D.x, dmean2D.y, dconic.xx, dconic.xy, dconic.yy, dopacity, dr, dg, db, dz, -, -};
 //   * extras: gradients of the depth / alpha images flow through the same recurrence.
+#include <algorithm>
 #include "common.cuh"
 #include "pipeline.cuh"
 
@@ -54,17 +55,21 @@ __device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
 }
 
 template <bool EXTRAS>
-__global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint32_t* __restrict__ order, uint32_t* __restrict__ queue_counters,
-                                                               uint32_t num_tiles, uint32_t num_queues,
+__global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint2* __restrict__ units,
+                                                               const uint32_t* __restrict__ unit_count,
                                                                const uint2* __restrict__ ranges,
                                                                const uint32_t* __restrict__ point_list, int W, int H,
                                                                const float* __restrict__ bg,
                                                                const float4* __restrict__ xy_ext,
                                                                const float4* __restrict__ conic_opacity,
                                                                const float4* __restrict__ rgb_depth,
-                                                               const float* __restrict__ final_T,
+                                                               const float4* __restrict__ final_state,
+                                                               const float* __restrict__ final_depth,
                                                                const uint32_t* __restrict__ n_contrib,
                                                                const uint32_t* __restrict__ tile_last,
+                                                               const uint32_t* __restrict__ seg_base,
+                                                               const float4* __restrict__ ckpt,
+                                                               const float* __restrict__ ckpt_z,
                                                                const float* __restrict__ dL_dpix,
                                                                const float* __restrict__ dL_ddepth,
                                                                const float* __restrict__ dL_dalpha_img,
@@ -76,21 +81,20 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint32_t* _
   __shared__ uint32_t s_ball[BL_STAGES][8][BL_CHUNKS];
   __shared__ __align__(8) uint64_t s_full[BL_STAGES], s_empty[BL_STAGES];
 
+  // ---- work unit = (tile, segment): list positions [seg*SEG, min((seg+1)*SEG, total)) of one tile -------
+  if (blockIdx.x >= *unit_count) return;
+  const uint2 unit = units[blockIdx.x];
+  const uint32_t tile_id = unit.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t tiles_x = (W + TILE - 1) / TILE;
-  __shared__ uint32_t s_rank;
-  if (warp == 0) {
-    const uint32_t r = fetch_tile_rank(queue_counters, num_tiles, num_queues, lane);
-    if (lane == 0) s_rank = r;
-  }
-  __syncthreads();
-  if (s_rank == NO_TILE) return;
-  const uint32_t tile_id = order[s_rank];
   const uint32_t tile_bx = tile_id % tiles_x, tile_by = tile_id / tiles_x;
   const uint2 range = ranges[tile_id];
   const int total = (int)min(tile_last[tile_id], range.y - range.x);  // entries [0,total) can contribute
-  if (total == 0) return;
-  const int rounds = (total + BL_BATCH - 1) / BL_BATCH;
+  const int seg_lo = (int)unit.y * SEG;
+  const int seg_hi = min(seg_lo + SEG, total);                        // exclusive
+  const int count = seg_hi - seg_lo;
+  if (count <= 0) return;
+  const int rounds = (count + BL_BATCH - 1) / BL_BATCH;
 
   if (tid == 0) {
     for (int s = 0; s < BL_STAGES; ++s) {
@@ -101,25 +105,25 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint32_t* _
   __syncthreads();
 
   if (warp == 8) {
-    // ======================= PRODUCER: back-to-front gather =======================
+    // ======================= PRODUCER: back-to-front gather of this segment =======================
     const float tile_x0 = (float)(tile_bx * TILE), tile_y0 = (float)(tile_by * TILE);
-    const uint32_t* list = point_list + range.x;
+    const uint32_t* list = point_list + range.x + seg_lo;   // segment-local list; entry e <-> position count-1-e
     uint32_t ids[BL_CHUNKS];
-    prod_load_ids(list, total, 0, true, lane, ids);
+    prod_load_ids(list, count, 0, true, lane, ids);
     prod_issue(ids, xy_ext, conic_opacity, rgb_depth, s_xy[0], s_co[0], s_cd[0], s_id[0], lane);
-    prod_load_ids(list, total, BL_BATCH, true, lane, ids);
+    prod_load_ids(list, count, BL_BATCH, true, lane, ids);
     for (int b = 0; b < rounds; ++b) {
       const int stage = b % BL_STAGES;
       if (b + 1 < rounds) {  // put the gathers of batch b+1 in flight, prefetch the ids of batch b+2
         const int nstage = (b + 1) % BL_STAGES;
         if (b + 1 >= BL_STAGES) mbar_wait(&s_empty[nstage], (((b + 1) / BL_STAGES) - 1) & 1);
         prod_issue(ids, xy_ext, conic_opacity, rgb_depth, s_xy[nstage], s_co[nstage], s_cd[nstage], s_id[nstage], lane);
-        prod_load_ids(list, total, (b + 2) * BL_BATCH, true, lane, ids);
+        prod_load_ids(list, count, (b + 2) * BL_BATCH, true, lane, ids);
         cp_async_wait<1>();
       } else {
         cp_async_wait<0>();
       }
-      prod_classify(total, b * BL_BATCH, s_xy[stage], s_ball[stage], tile_x0, tile_y0, lane);
+      prod_classify(count, b * BL_BATCH, s_xy[stage], s_ball[stage], tile_x0, tile_y0, lane);
       mbar_arrive(&s_full[stage]);
     }
     return;
@@ -131,11 +135,29 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint32_t* _
   const bool inside = px < (uint32_t)W && py < (uint32_t)H;
   const uint32_t pix_id = (uint32_t)W * py + px;
   const float2 pixf = {(float)px, (float)py};
+  const int pix_in_tile = warp * 32 + lane;
 
-  const float T_final = inside ? final_T[pix_id] : 0.f;
-  float T = T_final;
   const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
   const int warp_last = __reduce_max_sync(0xffffffffu, last_contributor);
+
+  // State of the forward recurrence at the END of this segment.  Behind-colour B = sum_{j >= seg_hi} c_j a_j T_j
+  // = C_final - C(before seg_hi); T = transmittance before entry seg_hi.  If nothing contributes at or after
+  // seg_hi (it is the tile's last needed segment) the end state is the final state.
+  float T_final = 0.f, T = 0.f;
+  float B[3] = {0.f, 0.f, 0.f};
+  float Bz = 0.f;
+  if (inside) {
+    const float4 fs = final_state[pix_id];
+    T_final = fs.x;
+    T = fs.x;
+    if (seg_hi < total) {
+      const size_t slot = ((size_t)seg_base[tile_id] + (size_t)(seg_hi / SEG)) * TILE_PIX + pix_in_tile;
+      const float4 ck = ckpt[slot];
+      T = ck.x;
+      B[0] = fs.y - ck.y; B[1] = fs.z - ck.z; B[2] = fs.w - ck.w;
+      if (EXTRAS) Bz = final_depth[pix_id] - ckpt_z[slot];
+    }
+  }
 
   const size_t HW = (size_t)H * W;
   float dpix[3] = {0.f, 0.f, 0.f};
@@ -152,30 +174,25 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint32_t* _
   // d(out)/dalpha_i through the final transmittance: colour gets +T_final*bg, the alpha image -T_final
   float tail = bg[0] * dpix[0] + bg[1] * dpix[1] + bg[2] * dpix[2];
   if (EXTRAS) tail -= dalp;
-
-  float accum_rec[3] = {0.f, 0.f, 0.f}, last_color[3] = {0.f, 0.f, 0.f};
-  float accum_z = 0.f, last_z = 0.f;
-  float last_alpha = 0.f;
   const float ddelx_dx = 0.5f * W;
   const float ddely_dy = 0.5f * H;
 
   for (int b = 0; b < rounds; ++b) {
     const int stage = b % BL_STAGES;
-    const int batch_first_pos = total - 1 - b * BL_BATCH;  // list position of batch entry 0 (descending)
+    const int batch_first_pos = seg_hi - 1 - b * BL_BATCH;  // list position of batch entry 0 (descending)
     mbar_wait(&s_full[stage], (b / BL_STAGES) & 1);
     if (batch_first_pos - (BL_BATCH - 1) < warp_last) {  // else: whole batch lies behind this block's last contributor
 #pragma unroll 1
       for (int c = 0; c < BL_CHUNKS; ++c) {
         uint32_t m = s_ball[stage][warp][c];
         // Candidates are taken BG at a time so the loads / power / exp of one overlap the serial
-        // transmittance + colour recurrences and the butterfly reduction of the other.
+        // transmittance + behind-colour recurrences and the butterfly reduction of the other.
         while (m) {
           int j[BG];
-          bool valid[BG];
-          float G[BG], alpha[BG];
+          bool has[BG], valid[BG];
+          float G[BG], alpha[BG], rinv[BG];
           float2 d[BG];
           float4 con_o[BG], cd[BG];
-          bool has[BG];
           int jmax = 0;
 #pragma unroll
           for (int k = 0; k < BG; ++k) {
@@ -196,6 +213,7 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint32_t* _
                 -0.5f * (con_o[k].x * d[k].x * d[k].x + con_o[k].z * d[k].y * d[k].y) - con_o[k].y * d[k].x * d[k].y;
             G[k] = expf(power);
             alpha[k] = min(0.99f, con_o[k].w * G[k]);
+            rinv[k] = __frcp_rn(1.f - alpha[k]);
             valid[k] = has[k] && (pos < last_contributor) && (power <= 0.0f) && (alpha[k] >= 1.0f / 255.0f);
           }
 #pragma unroll
@@ -205,28 +223,24 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint32_t* _
 #pragma unroll
             for (int q = 0; q < 16; ++q) v[q] = 0.f;
             if (valid[k]) {
-              T = __fdividef(T, 1.f - alpha[k]);
-              const float dchannel_dcolor = alpha[k] * T;
-              const float c3[3] = {cd[k].x, cd[k].y, cd[k].z};
-              float dL_dalpha = 0.0f;
-#pragma unroll
-              for (int ch = 0; ch < 3; ++ch) {
-                accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
-                last_color[ch] = c3[ch];
-                dL_dalpha += (c3[ch] - accum_rec[ch]) * dpix[ch];
-              }
-              v[6] = dchannel_dcolor * dpix[0];
-              v[7] = dchannel_dcolor * dpix[1];
-              v[8] = dchannel_dcolor * dpix[2];
+              // T holds the transmittance AFTER this entry; Ti before it.  With B the (unnormalised) colour
+              // blended behind this entry:  dC/dalpha_i = c_i*Ti - B/(1-alpha_i)
+              // (same quantity as backward.cu:515-525's (c - accum_rec)*T, written without the running average)
+              const float Ti = T * rinv[k];
+              const float w = alpha[k] * Ti;
+              float dL_dalpha = (cd[k].x * Ti - B[0] * rinv[k]) * dpix[0] + (cd[k].y * Ti - B[1] * rinv[k]) * dpix[1] +
+                                (cd[k].z * Ti - B[2] * rinv[k]) * dpix[2];
+              v[6] = w * dpix[0];
+              v[7] = w * dpix[1];
+              v[8] = w * dpix[2];
+              B[0] += cd[k].x * w; B[1] += cd[k].y * w; B[2] += cd[k].z * w;
               if (EXTRAS) {
-                accum_z = last_alpha * last_z + (1.f - last_alpha) * accum_z;
-                last_z = cd[k].w;
-                dL_dalpha += (cd[k].w - accum_z) * ddep;
-                v[9] = dchannel_dcolor * ddep;
+                dL_dalpha += (cd[k].w * Ti - Bz * rinv[k]) * ddep;
+                v[9] = w * ddep;
+                Bz += cd[k].w * w;
               }
-              dL_dalpha *= T;
-              last_alpha = alpha[k];
-              dL_dalpha += __fdividef(-T_final, 1.f - alpha[k]) * tail;
+              T = Ti;
+              dL_dalpha += (-T_final * rinv[k]) * tail;
 
               const float dL_dG = con_o[k].w * dL_dalpha;
               const float gdx = G[k] * d[k].x;
@@ -255,19 +269,25 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint32_t* _
 }
 
 int launch_blend_bwd(const tgr_params& p, const GeomView& g, const uint32_t* point_list, const ImageView& im,
-                     float* grad_acc, cudaStream_t s) {
+                     const BinView& b, cudaStream_t s) {
   const uint32_t T = (uint32_t)((p.W + TILE - 1) / TILE) * ((p.H + TILE - 1) / TILE);
-  if (int rc = launch_tile_order(im.ranges, im.tile_last, T, im.order_bwd, im.queue_counters, s)) return rc;
-  const dim3 grid(T, 1, 1);
+  const uint32_t ucap = (uint32_t)std::min<uint64_t>(b.units_cap, 0x7fffffffull);
+  if (int rc = launch_unit_build(im.ranges, im.tile_last, T, b.units, ucap, im.unit_count, s)) return rc;
+  // one CTA per work unit; the grid is sized for the capacity, surplus CTAs exit on the device-side count
+  const dim3 grid(ucap, 1, 1);
   const bool ex = p.extras && (p.dL_dout_depth || p.dL_dout_alpha);
   if (ex)
-    blend_bwd_kernel<true><<<grid, BL_THREADS, 0, s>>>(im.order_bwd, im.queue_counters, T, num_queues(), im.ranges, point_list, p.W, p.H, p.background, g.xy_ext, g.conic_opacity,
-                                               g.rgb_depth, im.final_T, im.n_contrib, im.tile_last, p.dL_dout_color,
-                                               p.dL_dout_depth, p.dL_dout_alpha, grad_acc);
+    blend_bwd_kernel<true><<<grid, BL_THREADS, 0, s>>>(b.units, im.unit_count, im.ranges, point_list, p.W, p.H,
+                                                       p.background, g.xy_ext, g.conic_opacity, g.rgb_depth,
+                                                       im.final_state, im.final_z, im.n_contrib, im.tile_last,
+                                                       im.seg_base, b.ckpt, b.ckpt_z, p.dL_dout_color, p.dL_dout_depth,
+                                                       p.dL_dout_alpha, b.grad_acc);
   else
-    blend_bwd_kernel<false><<<grid, BL_THREADS, 0, s>>>(im.order_bwd, im.queue_counters, T, num_queues(), im.ranges, point_list, p.W, p.H, p.background, g.xy_ext, g.conic_opacity,
-                                                g.rgb_depth, im.final_T, im.n_contrib, im.tile_last, p.dL_dout_color,
-                                                nullptr, nullptr, grad_acc);
+    blend_bwd_kernel<false><<<grid, BL_THREADS, 0, s>>>(b.units, im.unit_count, im.ranges, point_list, p.W, p.H,
+                                                        p.background, g.xy_ext, g.conic_opacity, g.rgb_depth,
+                                                        im.final_state, nullptr, im.n_contrib, im.tile_last,
+                                                        im.seg_base, b.ckpt, b.ckpt_z, p.dL_dout_color, nullptr, nullptr,
+                                                        b.grad_acc);
   count_launch();
   return check_launch("blend_bwd", p.debug != 0, s);
 }

@@ -38,7 +38,10 @@ __global__ void __launch_bounds__(BL_THREADS) blend_fwd_kernel(const uint32_t* _
                                                                uint32_t* __restrict__ n_contrib,
                                                                uint32_t* __restrict__ tile_last,
                                                                float* __restrict__ out_color, float* __restrict__ out_depth,
-                                                               float* __restrict__ out_alpha) {
+                                                               float* __restrict__ out_alpha,
+                                                               const uint32_t* __restrict__ seg_base,
+                                                               float4* __restrict__ ckpt, float* __restrict__ ckpt_z,
+                                                               float4* __restrict__ final_state, float* __restrict__ final_z) {
   __shared__ __align__(16) float4 s_xy[BL_STAGES][BL_BATCH];   // x, y, hx, hy
   __shared__ __align__(16) float4 s_co[BL_STAGES][BL_BATCH];   // conic xx, xy, yy, opacity
   __shared__ __align__(16) float4 s_cd[BL_STAGES][BL_BATCH];   // r, g, b, depth
@@ -121,8 +124,17 @@ __global__ void __launch_bounds__(BL_THREADS) blend_fwd_kernel(const uint32_t* _
   float C[3] = {0.f, 0.f, 0.f};
   float Dz = 0.f;
 
+  const uint32_t ckpt_base = seg_base[tile_id];
+  const int pix_in_tile = warp * 32 + lane;
   for (int b = 0; b < rounds; ++b) {
     const int stage = b % BL_STAGES;
+    // checkpoint of the recurrence state at every SEG-th list position: lets the backward replay the
+    // tile's list in independent segments (blend_bwd.cu)
+    if (b > 0 && (b % (SEG / BL_BATCH)) == 0) {
+      const size_t slot = ((size_t)ckpt_base + (size_t)(b / (SEG / BL_BATCH))) * TILE_PIX + pix_in_tile;
+      ckpt[slot] = make_float4(T, C[0], C[1], C[2]);
+      if (EXTRAS) ckpt_z[slot] = Dz;
+    }
     if (!warp_done && __all_sync(0xffffffffu, done)) {
       warp_done = true;
       if (lane == 0) atomicAdd(&s_done_warps, 1u);
@@ -185,6 +197,8 @@ __global__ void __launch_bounds__(BL_THREADS) blend_fwd_kernel(const uint32_t* _
   if (inside) {
     final_T[pix_id] = T;
     n_contrib[pix_id] = last_contributor;
+    final_state[pix_id] = make_float4(T, C[0], C[1], C[2]);
+    if (EXTRAS) final_z[pix_id] = Dz;
     const size_t HW = (size_t)H * W;
     out_color[0 * HW + pix_id] = C[0] + T * bg[0];
     out_color[1 * HW + pix_id] = C[1] + T * bg[1];
@@ -207,18 +221,20 @@ __global__ void __launch_bounds__(BL_THREADS) blend_fwd_kernel(const uint32_t* _
 }
 
 int launch_blend_fwd(const tgr_params& p, const GeomView& g, const uint32_t* point_list, const ImageView& im,
-                     cudaStream_t s) {
+                     const BinView& b, cudaStream_t s) {
   const uint32_t T = (uint32_t)((p.W + TILE - 1) / TILE) * ((p.H + TILE - 1) / TILE);
-  if (int rc = launch_tile_order(im.ranges, nullptr, T, im.order_fwd, im.queue_counters, s)) return rc;
+  if (int rc = launch_tile_order(im.ranges, nullptr, T, im.order_fwd, im.queue_counters, im.seg_base, s)) return rc;
   const dim3 grid(T, 1, 1);
   if (p.extras && p.out_depth && p.out_alpha)
     blend_fwd_kernel<true><<<grid, BL_THREADS, 0, s>>>(im.order_fwd, im.queue_counters, T, num_queues(), im.ranges, point_list, p.W, p.H, g.xy_ext, g.conic_opacity,
                                                        g.rgb_depth, p.background, im.final_T, im.n_contrib,
-                                                       im.tile_last, p.out_color, p.out_depth, p.out_alpha);
+                                                       im.tile_last, p.out_color, p.out_depth, p.out_alpha, im.seg_base, b.ckpt, b.ckpt_z,
+                                                       im.final_state, im.final_z);
   else
     blend_fwd_kernel<false><<<grid, BL_THREADS, 0, s>>>(im.order_fwd, im.queue_counters, T, num_queues(), im.ranges, point_list, p.W, p.H, g.xy_ext, g.conic_opacity,
                                                         g.rgb_depth, p.background, im.final_T, im.n_contrib,
-                                                        im.tile_last, p.out_color, nullptr, nullptr);
+                                                        im.tile_last, p.out_color, nullptr, nullptr, im.seg_base, b.ckpt, b.ckpt_z,
+                                                        im.final_state, im.final_z);
   count_launch();
   return check_launch("blend_fwd", p.debug != 0, s);
 }

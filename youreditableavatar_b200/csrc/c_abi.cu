@@ -73,7 +73,7 @@ static int validate(const tgr_params* p, bool need_bin, uint64_t cap) {
   if (p->D < 0 || p->D > 3) { set_error("SH degree %d not in 0..3", p->D); return 1; }
   if (!p->geom_buffer || p->geom_bytes < tgr_geom_bytes(p->P)) { set_error("geom buffer too small"); return 1; }
   if (!p->image_buffer || p->image_bytes < tgr_image_bytes(p->W, p->H)) { set_error("image buffer too small"); return 1; }
-  if (need_bin && (!p->binning_buffer || p->binning_bytes < tgr_binning_bytes(p->P, cap))) {
+  if (need_bin && (!p->binning_buffer || p->binning_bytes < tgr_binning_bytes(p->P, cap, p->W, p->H))) {
     set_error("binning buffer too small for capacity %llu", (unsigned long long)cap);
     return 1;
   }
@@ -117,7 +117,7 @@ const char* tgr_last_error(void) { return g_err; }
 
 uint64_t tgr_geom_bytes(int32_t P) { return carve_geom(nullptr, P).bytes; }
 uint64_t tgr_image_bytes(int32_t W, int32_t H) { return carve_image(nullptr, W, H).bytes; }
-uint64_t tgr_binning_bytes(int32_t P, uint64_t cap) { return carve_bin(nullptr, P, cap).bytes; }
+uint64_t tgr_binning_bytes(int32_t P, uint64_t cap, int32_t W, int32_t H) { return carve_bin(nullptr, P, cap, W, H).bytes; }
 uint64_t tgr_sort_temp_bytes(uint64_t n) { return sort_temp_bytes(n); }
 
 int tgr_forward_preprocess(const tgr_params* p, const tgr_binding* bind, void* stream) {
@@ -169,7 +169,7 @@ int tgr_forward_render(const tgr_params* p, uint64_t cap, void* stream) {
   if (int rc = validate(p, true, cap)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   GeomView g = carve_geom(p->geom_buffer, p->P);
-  BinView b = carve_bin(p->binning_buffer, p->P, cap);
+  BinView b = carve_bin(p->binning_buffer, p->P, cap, p->W, p->H);
   ImageView im = carve_image(p->image_buffer, p->W, p->H);
   const uint32_t T = (uint32_t)((p->W + TILE - 1) / TILE) * ((p->H + TILE - 1) / TILE);
   if (p->P > 0 && cap > 0) {
@@ -189,7 +189,7 @@ int tgr_forward_render(const tgr_params* p, uint64_t cap, void* stream) {
   }
   const uint32_t* plist = sorted_vals(p, b);
   prof_begin(TGR_STAGE_BLEND_FWD, s);
-  if (int rc = launch_blend_fwd(*p, g, plist, im, s)) return rc;
+  if (int rc = launch_blend_fwd(*p, g, plist, im, b, s)) return rc;
   prof_end(TGR_STAGE_BLEND_FWD, s);
   return check_launch("forward_render", p->debug != 0, s);
 }
@@ -200,11 +200,11 @@ int tgr_backward(const tgr_params* p, const tgr_binding* bind, uint64_t cap, voi
   if (p->P == 0) return 0;
   if (!p->dL_dout_color) { set_error("dL_dout_color missing"); return 1; }
   GeomView g = carve_geom(p->geom_buffer, p->P);
-  BinView b = carve_bin(p->binning_buffer, p->P, cap);
+  BinView b = carve_bin(p->binning_buffer, p->P, cap, p->W, p->H);
   ImageView im = carve_image(p->image_buffer, p->W, p->H);
   cudaMemsetAsync(b.grad_acc, 0, (size_t)p->P * GRAD_ACC * sizeof(float), s);
   prof_begin(TGR_STAGE_BLEND_BWD, s);
-  if (int rc = launch_blend_bwd(*p, g, sorted_vals(p, b), im, b.grad_acc, s)) return rc;
+  if (int rc = launch_blend_bwd(*p, g, sorted_vals(p, b), im, b, s)) return rc;
   prof_end(TGR_STAGE_BLEND_BWD, s);
   prof_begin(TGR_STAGE_PREPROCESS_BWD, s);
   if (int rc = launch_preprocess_bwd(*p, bind, g, b.grad_acc, s)) return rc;
@@ -255,7 +255,7 @@ int tgr_export_binning(const tgr_params* p, uint64_t R, uint64_t* keys, uint32_t
   if (int rc = validate(p, true, R)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   GeomView g = carve_geom(p->geom_buffer, p->P);
-  BinView b = carve_bin(p->binning_buffer, p->P, R);
+  BinView b = carve_bin(p->binning_buffer, p->P, R, p->W, p->H);
   ImageView im = carve_image(p->image_buffer, p->W, p->H);
   bool in_b = false;
   const uint32_t* vals = sorted_vals(p, b, &in_b);

@@ -113,6 +113,7 @@ __host__ __device__ inline GeomView carve_geom(void* base, int32_t P) {
 }
 
 constexpr int MAX_QUEUES = 1024;
+constexpr int SEG = 512;  // list entries per backward work unit (a tile's list is replayed in independent segments)
 
 struct ImageView {
   float* final_T;        // [N] transmittance left after blending
@@ -122,6 +123,10 @@ struct ImageView {
   uint32_t* order_fwd;   // [T] tile ids, heaviest (longest list) first: CTA i of blend_fwd renders tile order_fwd[i]
   uint32_t* order_bwd;   // [T] same for the backward, by tile_last
   uint32_t* queue_counters;  // [MAX_QUEUES] per-SM work-queue cursors of the blend kernels (zeroed by tile_order)
+  float4* final_state;   // [N] (T_final, C_r, C_g, C_b) without background: end state of the forward recurrence
+  float* final_z;        // [N] depth accumulator at the end of the forward (extras)
+  uint32_t* seg_base;    // [T+1] first checkpoint slot of each tile (exclusive scan of ceil(len/SEG))
+  uint32_t* unit_count;  // [1] number of backward work units of this view
   uint64_t bytes;
 };
 
@@ -137,6 +142,10 @@ __host__ __device__ inline ImageView carve_image(void* base, int32_t W, int32_t 
   v.order_fwd = carve<uint32_t>(p, T);
   v.order_bwd = carve<uint32_t>(p, T);
   v.queue_counters = carve<uint32_t>(p, MAX_QUEUES);
+  v.final_state = carve<float4>(p, N);
+  v.final_z = carve<float>(p, N);
+  v.seg_base = carve<uint32_t>(p, T + 1);
+  v.unit_count = carve<uint32_t>(p, 32);
   v.bytes = (uint64_t)(p - static_cast<char*>(base)) + 128;
   return v;
 }
@@ -149,12 +158,22 @@ struct BinView {
   uint32_t* sort_temp;
   float* grad_acc;   // [P*GRAD_ACC] backward accumulators (see blend_bwd.cu); lives here so it is
                      // allocated with the call that needs it and freed with the autograd node
+  float4* ckpt;      // [units_cap*256] forward state (T, C) of every pixel at every SEG-th list position
+  float* ckpt_z;     // [units_cap*256] same for the depth accumulator (extras)
+  uint2* units;      // [units_cap] backward work units (tile, segment)
+  uint64_t units_cap;
   uint64_t bytes;
 };
 
 constexpr int GRAD_ACC = 12;  // mean2D.xy, conic.xyz, opacity, rgb, depth, 2 pad
 
-__host__ __device__ inline BinView carve_bin(void* base, int32_t P, uint64_t R) {
+// upper bound of sum_t ceil(len_t / SEG): every non-empty tile adds at most one partial segment
+__host__ __device__ inline uint64_t units_capacity(uint64_t R, int32_t W, int32_t H) {
+  const uint64_t T = (uint64_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+  return R / SEG + (T < R ? T : R) + 1;
+}
+
+__host__ __device__ inline BinView carve_bin(void* base, int32_t P, uint64_t R, int32_t W, int32_t H) {
   BinView b;
   char* p = static_cast<char*>(base);
   b.key_a = carve<uint32_t>(p, R);
@@ -163,6 +182,10 @@ __host__ __device__ inline BinView carve_bin(void* base, int32_t P, uint64_t R) 
   b.val_b = carve<uint32_t>(p, R);
   b.sort_temp = carve<uint32_t>(p, sort_temp_bytes(R) / 4);
   b.grad_acc = carve<float>(p, (uint64_t)(P > 0 ? P : 0) * GRAD_ACC);
+  b.units_cap = units_capacity(R, W, H);
+  b.ckpt = carve<float4>(p, b.units_cap * TILE_PIX);
+  b.ckpt_z = carve<float>(p, b.units_cap * TILE_PIX);
+  b.units = carve<uint2>(p, b.units_cap);
   b.bytes = (uint64_t)(p - static_cast<char*>(base)) + 128;
   return b;
 }
@@ -266,14 +289,16 @@ int launch_sort_pairs(uint64_t n_host, const uint32_t* n_dev, uint32_t* keys_a, 
                       bool* result_in_b);
 int launch_emit(const tgr_params& p, const GeomView& g, const BinView& b, uint64_t cap, cudaStream_t s);
 int launch_tile_order(const uint2* ranges, const uint32_t* tile_last, uint32_t T, uint32_t* order,
-                      uint32_t* queue_counters, cudaStream_t s);
+                      uint32_t* queue_counters, uint32_t* seg_base, cudaStream_t s);
+int launch_unit_build(const uint2* ranges, const uint32_t* tile_last, uint32_t T, uint2* units, uint32_t units_cap,
+                      uint32_t* unit_count, cudaStream_t s);
 uint32_t num_queues();  // number of SMs of the current device (one work queue per SM)
 int launch_ranges(const tgr_params& p, const GeomView& g, const uint32_t* sorted_keys, const ImageView& im,
                   uint64_t cap, cudaStream_t s);
 int launch_blend_fwd(const tgr_params& p, const GeomView& g, const uint32_t* point_list, const ImageView& im,
-                     cudaStream_t s);
+                     const BinView& b, cudaStream_t s);
 int launch_blend_bwd(const tgr_params& p, const GeomView& g, const uint32_t* point_list, const ImageView& im,
-                     float* grad_acc, cudaStream_t s);
+                     const BinView& b, cudaStream_t s);
 int launch_preprocess_bwd(const tgr_params& p, const tgr_binding* bind, const GeomView& g, const float* grad_acc,
                           cudaStream_t s);
 int launch_mark_visible(int32_t P, const float* means3D, const float* view, const float* proj, uint8_t* present,

@@ -156,7 +156,7 @@ def c_rasterize_gaussians(bg, means3D, colors, opacity, scales, rotations, scale
         # the GPU keeps sorting Gaussians by depth while the host waits for the count
         check(L.tgr_wait_num_rendered(), "tgr_wait_num_rendered")
         R = int(slot.item())
-        binning = torch.empty(L.tgr_binning_bytes(P, R), **u8)
+        binning = torch.empty(L.tgr_binning_bytes(P, R, W, H), **u8)
         p.binning_buffer, p.binning_bytes = binning.data_ptr(), binning.numel()
         check(L.tgr_forward_render(C.byref(p), R, stream), "tgr_forward_render")
 
