@@ -26,8 +26,9 @@
 extern "C" {
 #endif
 
-#define TGR_ABI_VERSION 1
+#define TGR_ABI_VERSION 2
 #define TGR_TILE 16 /* 16x16 pixel tiles, config.h:16-17 */
+#define TGR_MAX_BATCH 8 /* views served by one launch of the per-Gaussian kernels (longer batches are chunked) */
 
 /* Per-call description of one view and one set of Gaussians.  POD only. */
 typedef struct tgr_params {
@@ -138,6 +139,29 @@ int tgr_wait_num_rendered(void);
 
 /* ---- backward: replaces CudaRasterizer::Rasterizer::backward (rasterizer_impl.cu:340-434) ---- */
 int tgr_backward(const tgr_params* p, const tgr_binding* bind, uint64_t num_rendered_capacity, void* stream);
+
+/* ---- multi-view batches (new; the reference renders one view per call, tetgs_texture/refine.py:54) ----
+ * `views` is an array of n_views tgr_params that describe the SAME Gaussians (identical P, D, M, Gaussian
+ * tensors) seen from different cameras, each with its own workspaces and outputs.  The per-Gaussian
+ * kernels visit every Gaussian once per batch: parameters (236 B per Gaussian with degree-3 SH) are read once
+ * instead of once per view, and the parameter gradients are written once instead of accumulated per view.
+ * The per-view stages in between are independent and may be issued on different streams:
+ *
+ *   tgr_forward_preprocess_batch(views, n, bind, s0)       one launch per <= TGR_MAX_BATCH views; every view's
+ *                                                          instance count goes to its host_num_rendered slot
+ *   tgr_wait_num_rendered()                                (size the binning buffers)
+ *   for v: tgr_forward_depth_sort(&views[v], s_v); tgr_forward_render(&views[v], cap_v, s_v)
+ *   ... upstream gradients ...
+ *   for v: tgr_backward_blend(&views[v], cap_v, s_v)       2-D gradients of view v (blend stage only)
+ *   tgr_backward_preprocess_batch(views, caps, n, bind, s0) after all s_v joined s0: chain rule to the
+ *                                                          parameters, summed over the batch; outputs and the
+ *                                                          accumulate flag are taken from views[0]
+ * tgr_forward_preprocess == preprocess_batch of one view + depth sort; tgr_backward == blend + batch of one. */
+int tgr_forward_preprocess_batch(const tgr_params* views, int32_t n_views, const tgr_binding* bind, void* stream);
+int tgr_forward_depth_sort(const tgr_params* p, void* stream);
+int tgr_backward_blend(const tgr_params* p, uint64_t num_rendered_capacity, void* stream);
+int tgr_backward_preprocess_batch(const tgr_params* views, const uint64_t* num_rendered_capacities, int32_t n_views,
+                                  const tgr_binding* bind, void* stream);
 
 /* Synchronously reads {num_rendered, overflow, num_visible, reserved} from a geom buffer header. */
 int tgr_read_header(const void* geom_buffer, uint32_t out[4], void* stream);

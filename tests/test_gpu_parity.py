@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 import torch
 
+from youreditableavatar_b200 import scene
 from helpers import (export_binning, export_geom, export_image_state, ours_backward, ours_forward, random_cloud,
                      rel_l2, small_scene, to_dev)
 
@@ -341,3 +342,68 @@ def test_work_queue_covers_every_tile_many_sizes():
             # background is white: an unrendered (garbage / zero) tile shows up as alpha+colour inconsistency
             bgmask = out[7][0] == 0
             assert torch.allclose(out[1][:, bgmask], torch.ones_like(out[1][:, bgmask]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_streams", [1, 3])
+@pytest.mark.parametrize("V", [1, 3, 11])
+def test_multiview_batch_matches_per_view_calls(V, n_streams):
+    """tgr_*_batch: per-view forward results are bit-identical to single-view calls; the summed gradients agree
+    with per-view calls + accumulate to fp32 summation order (V = 11 spans two chunks of TGR_MAX_BATCH)."""
+    from youreditableavatar_b200 import multiview as mv
+    from youreditableavatar_b200.parallel import settings_from_cam
+    _, inp, _ = small_scene(2500, 32, 112, 0)
+    P = inp["means3D"].shape[0]
+    cams = [to_dev(scene.orbit_camera(v, V, 112, 112, device="cpu"), "cuda") for v in range(V)]
+    g = torch.Generator().manual_seed(5)
+    dLc = (torch.randn(V, 3, 112, 112, generator=g) / (3 * 112 * 112)).cuda()
+    dLd = (torch.randn(V, 1, 112, 112, generator=g) / (112 * 112)).cuda()
+    dLa = (torch.randn(V, 1, 112, 112, generator=g) / (112 * 112)).cuda()
+    e = torch.Tensor([])
+    res = mv.c_rasterize_views([settings_from_cam(c, 3) for c in cams], inp["means3D"], e, inp["opacities"], inp["scales"],
+                               inp["rotations"], e, inp["shs"], extras=True, n_streams=n_streams)
+    state, color, radii, depth, alpha = res
+    grads = mv.c_rasterize_views_backward(state, dLc, dL_dout_depth=dLd, dL_dout_alpha=dLa)
+    ref_sum = None
+    for v in range(V):
+        fo = ours_forward(inp, cams[v], 3, extras=True)
+        assert fo[0] == state.counts[v]
+        assert torch.equal(fo[1], color[v]) and torch.equal(fo[2], radii[v])
+        assert torch.equal(fo[6], depth[v]) and torch.equal(fo[7], alpha[v])
+        go = ours_backward(inp, cams[v], 3, fo, dLc[v], dLd[v], dLa[v])
+        ref_sum = [x.clone() for x in go] if ref_sum is None else [a + b for a, b in zip(ref_sum, go)]
+    for name, a, b in zip(["m2D", "col", "op", "m3D", "cov", "sh", "sc", "rot"], grads, ref_sum):
+        assert rel_l2(a, b) <= 2e-6, (name, rel_l2(a, b))
+    # accumulate=True adds a second batch on top
+    grads2 = mv.c_rasterize_views_backward(state, dLc, dL_dout_depth=dLd, dL_dout_alpha=dLa, accumulate_into=grads)
+    for a, b in zip(grads2, ref_sum):
+        assert rel_l2(a, 2 * b) <= 2e-6
+
+
+@pytest.mark.gpu
+def test_multiview_module_autograd_matches_single_view_modules():
+    from youreditableavatar_b200.multiview import MultiViewRasterizer
+    from youreditableavatar_b200.parallel import settings_from_cam
+    from diff_gaussian_rasterization import GaussianRasterizer
+    _, inp, _ = small_scene(1500, 32, 96, 0)
+    V = 4
+    cams = [to_dev(scene.orbit_camera(v, V, 96, 96, device="cpu"), "cuda") for v in range(V)]
+    settings = [settings_from_cam(c, 3) for c in cams]
+    leaves = {k: v.clone().requires_grad_(True) for k, v in inp.items()}
+    m2 = torch.zeros_like(leaves["means3D"], requires_grad=True)
+    color, radii, depth, alpha = MultiViewRasterizer(settings, extra_outputs=True, n_streams=2)(
+        means3D=leaves["means3D"], means2D=m2, opacities=leaves["opacities"], shs=leaves["shs"],
+        scales=leaves["scales"], rotations=leaves["rotations"])
+    w = torch.linspace(0.5, 1.5, V, device="cuda").view(V, 1, 1, 1)
+    ((color * w).sum() + 0.3 * depth.sum() - 0.2 * alpha.sum()).backward()
+    leaves1 = {k: v.clone().requires_grad_(True) for k, v in inp.items()}
+    loss = 0
+    for v in range(V):
+        c1, r1, d1, a1 = GaussianRasterizer(settings[v], extra_outputs=True)(
+            means3D=leaves1["means3D"], means2D=torch.zeros_like(m2, requires_grad=True), opacities=leaves1["opacities"],
+            shs=leaves1["shs"], scales=leaves1["scales"], rotations=leaves1["rotations"])
+        assert torch.equal(c1, color[v]) and torch.equal(r1, radii[v])
+        loss = loss + (c1 * w[v]).sum() + 0.3 * d1.sum() - 0.2 * a1.sum()
+    loss.backward()
+    for k in leaves:
+        assert rel_l2(leaves[k].grad, leaves1[k].grad) <= 2e-6, k

@@ -60,6 +60,11 @@ SYMBOLS = {
     "tgr_forward_render": (C.c_int, [C.POINTER(TgrParams), C.c_uint64, C.c_void_p]),
     "tgr_wait_num_rendered": (C.c_int, []),
     "tgr_backward": (C.c_int, [C.POINTER(TgrParams), C.POINTER(TgrBinding), C.c_uint64, C.c_void_p]),
+    "tgr_forward_preprocess_batch": (C.c_int, [C.POINTER(TgrParams), C.c_int32, C.POINTER(TgrBinding), C.c_void_p]),
+    "tgr_forward_depth_sort": (C.c_int, [C.POINTER(TgrParams), C.c_void_p]),
+    "tgr_backward_blend": (C.c_int, [C.POINTER(TgrParams), C.c_uint64, C.c_void_p]),
+    "tgr_backward_preprocess_batch": (C.c_int, [C.POINTER(TgrParams), C.POINTER(C.c_uint64), C.c_int32,
+                                                C.POINTER(TgrBinding), C.c_void_p]),
     "tgr_read_header": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32 * 4), C.c_void_p]),
     "tgr_mark_visible": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tgr_knn_bytes": (C.c_uint64, [C.c_int32]),
@@ -75,6 +80,8 @@ SYMBOLS = {
                                      C.c_void_p, C.c_uint64, C.c_void_p]),
 }
 
+ABI_VERSION = 2
+MAX_BATCH = 8
 NUM_STAGES = 8
 STAGE_NAMES = ["preprocess", "depth_sort", "emit", "tile_sort", "ranges", "blend_fwd", "blend_bwd", "preprocess_bwd"]
 
@@ -98,7 +105,7 @@ def lib() -> C.CDLL:
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.tgr_abi_version() != 1:
+        if l.tgr_abi_version() != ABI_VERSION:
             raise TgrError("ABI version mismatch")
         _lib = l
     return _lib

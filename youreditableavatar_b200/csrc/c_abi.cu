@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <atomic>
 #include "common.cuh"
 
@@ -120,27 +121,27 @@ uint64_t tgr_image_bytes(int32_t W, int32_t H) { return carve_image(nullptr, W, 
 uint64_t tgr_binning_bytes(int32_t P, uint64_t cap, int32_t W, int32_t H) { return carve_bin(nullptr, P, cap, W, H).bytes; }
 uint64_t tgr_sort_temp_bytes(uint64_t n) { return sort_temp_bytes(n); }
 
-int tgr_forward_preprocess(const tgr_params* p, const tgr_binding* bind, void* stream) {
-  if (int rc = validate(p, false, 0)) return rc;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (p->P == 0) {
-    if (p->host_num_rendered) *p->host_num_rendered = 0;
-    return 0;
-  }
+static int check_gaussians(const tgr_params* p, const tgr_binding* bind) {
   if (!bind) {
     if (!p->means3D || !p->opacities) { set_error("means3D/opacities missing"); return 1; }
     if (!p->cov3D_precomp && (!p->scales || !p->rotations)) { set_error("need scales+rotations or cov3D_precomp"); return 1; }
   }
   if (!p->colors_precomp && (!p->shs || p->M < (p->D + 1) * (p->D + 1))) { set_error("need colors_precomp or shs with M >= (D+1)^2"); return 1; }
-  GeomView g = carve_geom(p->geom_buffer, p->P);
-  cudaMemsetAsync(g.header, 0, sizeof(GeomHeader), s);
-  prof_begin(TGR_STAGE_PREPROCESS, s);
-  if (int rc = launch_preprocess(*p, bind, g, s)) return rc;
-  prof_end(TGR_STAGE_PREPROCESS, s);
-  if (p->host_num_rendered) {
-    cudaMemcpyAsync(p->host_num_rendered, &g.header->num_rendered, sizeof(uint32_t), cudaMemcpyDeviceToHost, s);
-    cudaEventRecord(count_event(), s);
+  return 0;
+}
+
+// every view of a batch must describe the same Gaussians (only cameras, sizes, workspaces and outputs differ)
+static int check_same_gaussians(const tgr_params* a, const tgr_params* b) {
+  if (a->P != b->P || a->D != b->D || a->M != b->M || a->means3D != b->means3D || a->shs != b->shs ||
+      a->colors_precomp != b->colors_precomp || a->opacities != b->opacities || a->scales != b->scales ||
+      a->rotations != b->rotations || a->cov3D_precomp != b->cov3D_precomp || a->scale_modifier != b->scale_modifier) {
+    set_error("batch: all views must share the same Gaussian tensors, P, D, M and scale_modifier");
+    return 1;
   }
+  return 0;
+}
+
+static int depth_sort(const tgr_params* p, const GeomView& g, cudaStream_t s) {
   // (depth bits, id) order of the Gaussians: positive floats compare like their bit patterns; bit 31 is 0
   bool in_b = false;
   prof_begin(TGR_STAGE_DEPTH_SORT, s);
@@ -148,7 +149,67 @@ int tgr_forward_preprocess(const tgr_params* p, const tgr_binding* bind, void* s
                                  g.sort_temp, s, &in_b)) return rc;
   prof_end(TGR_STAGE_DEPTH_SORT, s);
   if (in_b) { set_error("internal: depth sort must end in buffer A"); return 3; }
+  return 0;
+}
+
+// One preprocess launch per chunk of <= TGR_MAX_BATCH views; instance counts go to each view's pinned slot.
+static int preprocess_views(const tgr_params* views, int32_t n, const tgr_binding* bind, cudaStream_t s) {
+  for (int32_t v = 0; v < n; ++v) {
+    if (int rc = validate(&views[v], false, 0)) return rc;
+    if (v && check_same_gaussians(&views[0], &views[v])) return 1;
+  }
+  const tgr_params* p0 = &views[0];
+  if (p0->P == 0) {
+    for (int32_t v = 0; v < n; ++v)
+      if (views[v].host_num_rendered) *views[v].host_num_rendered = 0;
+    return 0;
+  }
+  if (int rc = check_gaussians(p0, bind)) return rc;
+  for (int32_t v0 = 0; v0 < n; v0 += MAX_BATCH) {
+    ViewBatch vb{};
+    vb.V = std::min<int32_t>(MAX_BATCH, n - v0);
+    for (int32_t k = 0; k < vb.V; ++k) {
+      GeomView g = carve_geom(views[v0 + k].geom_buffer, p0->P);
+      cudaMemsetAsync(g.header, 0, sizeof(GeomHeader), s);
+      vb.v[k] = make_view_desc(views[v0 + k], g, nullptr);
+    }
+    prof_begin(TGR_STAGE_PREPROCESS, s);
+    if (int rc = launch_preprocess(*p0, bind, vb, s)) return rc;
+    prof_end(TGR_STAGE_PREPROCESS, s);
+  }
+  bool any = false;
+  for (int32_t v = 0; v < n; ++v) {
+    if (!views[v].host_num_rendered) continue;
+    GeomView g = carve_geom(views[v].geom_buffer, p0->P);
+    cudaMemcpyAsync(views[v].host_num_rendered, &g.header->num_rendered, sizeof(uint32_t), cudaMemcpyDeviceToHost, s);
+    any = true;
+  }
+  if (any) cudaEventRecord(count_event(), s);
+  return 0;
+}
+
+int tgr_forward_preprocess(const tgr_params* p, const tgr_binding* bind, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!p) { set_error("null params"); return 1; }
+  if (int rc = preprocess_views(p, 1, bind, s)) return rc;
+  if (p->P == 0) return 0;
+  if (int rc = depth_sort(p, carve_geom(p->geom_buffer, p->P), s)) return rc;
   return check_launch("forward_preprocess", p->debug != 0, s);
+}
+
+int tgr_forward_preprocess_batch(const tgr_params* views, int32_t n_views, const tgr_binding* bind, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!views || n_views <= 0) { set_error("batch: no views"); return 1; }
+  if (int rc = preprocess_views(views, n_views, bind, s)) return rc;
+  return check_launch("forward_preprocess_batch", views[0].debug != 0, s);
+}
+
+int tgr_forward_depth_sort(const tgr_params* p, void* stream) {
+  if (int rc = validate(p, false, 0)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p->P == 0) return 0;
+  if (int rc = depth_sort(p, carve_geom(p->geom_buffer, p->P), s)) return rc;
+  return check_launch("forward_depth_sort", p->debug != 0, s);
 }
 
 int tgr_wait_num_rendered(void) {
@@ -194,10 +255,7 @@ int tgr_forward_render(const tgr_params* p, uint64_t cap, void* stream) {
   return check_launch("forward_render", p->debug != 0, s);
 }
 
-int tgr_backward(const tgr_params* p, const tgr_binding* bind, uint64_t cap, void* stream) {
-  if (int rc = validate(p, true, cap)) return rc;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (p->P == 0) return 0;
+static int backward_blend(const tgr_params* p, uint64_t cap, cudaStream_t s) {
   if (!p->dL_dout_color) { set_error("dL_dout_color missing"); return 1; }
   GeomView g = carve_geom(p->geom_buffer, p->P);
   BinView b = carve_bin(p->binning_buffer, p->P, cap, p->W, p->H);
@@ -206,10 +264,55 @@ int tgr_backward(const tgr_params* p, const tgr_binding* bind, uint64_t cap, voi
   prof_begin(TGR_STAGE_BLEND_BWD, s);
   if (int rc = launch_blend_bwd(*p, g, sorted_vals(p, b), im, b, s)) return rc;
   prof_end(TGR_STAGE_BLEND_BWD, s);
+  return 0;
+}
+
+int tgr_backward(const tgr_params* p, const tgr_binding* bind, uint64_t cap, void* stream) {
+  if (int rc = validate(p, true, cap)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p->P == 0) return 0;
+  if (int rc = backward_blend(p, cap, s)) return rc;
+  ViewBatch vb{};
+  vb.V = 1;
+  vb.v[0] = make_view_desc(*p, carve_geom(p->geom_buffer, p->P), carve_bin(p->binning_buffer, p->P, cap, p->W, p->H).grad_acc);
   prof_begin(TGR_STAGE_PREPROCESS_BWD, s);
-  if (int rc = launch_preprocess_bwd(*p, bind, g, b.grad_acc, s)) return rc;
+  if (int rc = launch_preprocess_bwd(*p, bind, vb, s)) return rc;
   prof_end(TGR_STAGE_PREPROCESS_BWD, s);
   return check_launch("backward", p->debug != 0, s);
+}
+
+int tgr_backward_blend(const tgr_params* p, uint64_t cap, void* stream) {
+  if (int rc = validate(p, true, cap)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p->P == 0) return 0;
+  if (int rc = backward_blend(p, cap, s)) return rc;
+  return check_launch("backward_blend", p->debug != 0, s);
+}
+
+int tgr_backward_preprocess_batch(const tgr_params* views, const uint64_t* caps, int32_t n_views, const tgr_binding* bind,
+                                  void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!views || !caps || n_views <= 0) { set_error("batch: no views"); return 1; }
+  for (int32_t v = 0; v < n_views; ++v) {
+    if (int rc = validate(&views[v], true, caps[v])) return rc;
+    if (v && check_same_gaussians(&views[0], &views[v])) return 1;
+  }
+  if (views[0].P == 0) return 0;
+  tgr_params p0 = views[0];  // Gaussians + output gradient tensors + accumulate flag of the batch
+  for (int32_t v0 = 0; v0 < n_views; v0 += MAX_BATCH) {
+    ViewBatch vb{};
+    vb.V = std::min<int32_t>(MAX_BATCH, n_views - v0);
+    for (int32_t k = 0; k < vb.V; ++k) {
+      const tgr_params& pv = views[v0 + k];
+      vb.v[k] = make_view_desc(pv, carve_geom(pv.geom_buffer, pv.P),
+                               carve_bin(pv.binning_buffer, pv.P, caps[v0 + k], pv.W, pv.H).grad_acc);
+    }
+    prof_begin(TGR_STAGE_PREPROCESS_BWD, s);
+    if (int rc = launch_preprocess_bwd(p0, bind, vb, s)) return rc;
+    prof_end(TGR_STAGE_PREPROCESS_BWD, s);
+    p0.accumulate = 1;  // later chunks add to what the first one wrote
+  }
+  return check_launch("backward_preprocess_batch", views[0].debug != 0, s);
 }
 
 int tgr_read_header(const void* geom_buffer, uint32_t out[4], void* stream) {

@@ -167,6 +167,42 @@ struct BinView {
 
 constexpr int GRAD_ACC = 12;  // mean2D.xy, conic.xyz, opacity, rgb, depth, 2 pad
 
+// ---------------------------------------------------------------------------------------------
+// Multi-view batches: the per-Gaussian kernels (preprocess forward / backward) visit every Gaussian ONCE and
+// loop over the views of the batch, so the 236 B of parameters per Gaussian (SH above all) are read once per
+// batch instead of once per view, and the gradients are written once per batch instead of read-modify-written
+// once per view.  A single-view call is a batch of one.
+// ---------------------------------------------------------------------------------------------
+constexpr int MAX_BATCH = TGR_MAX_BATCH;
+
+struct ViewDesc {
+  const float* viewmatrix;
+  const float* projmatrix;
+  const float* campos;
+  float tan_fovx, tan_fovy;
+  int32_t W, H;
+  // forward outputs of this view
+  int32_t* radii;
+  GeomHeader* header;
+  uint32_t* depth_key;
+  ushort4* rect;
+  float4* xy_ext;
+  float4* conic_opacity;
+  float4* rgb_depth;
+  uint8_t* clamped;
+  // backward input of this view (packed 2-D gradient rows filled by blend_bwd)
+  const float* grad_acc;
+};
+
+struct ViewBatch {
+  int32_t V;
+  int32_t pad;
+  ViewDesc v[MAX_BATCH];
+};
+
+// camera block staged in shared memory by the batched kernels: [view 16 | proj 16 | campos 3 | pad] per view
+constexpr int CAM_FLOATS = 36;
+
 // upper bound of sum_t ceil(len_t / SEG): every non-empty tile adds at most one partial segment
 __host__ __device__ inline uint64_t units_capacity(uint64_t R, int32_t W, int32_t H) {
   const uint64_t T = (uint64_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
@@ -283,7 +319,8 @@ int check_launch(const char* what, bool debug, cudaStream_t s);
 void count_launch(int n = 1);  // bookkeeping for tgr_kernel_launches()
 
 // stage launchers (each in its own .cu)
-int launch_preprocess(const tgr_params& p, const tgr_binding* bind, const GeomView& g, cudaStream_t s);
+ViewDesc make_view_desc(const tgr_params& p, const GeomView& g, const float* grad_acc);
+int launch_preprocess(const tgr_params& p, const tgr_binding* bind, const ViewBatch& vb, cudaStream_t s);
 int launch_sort_pairs(uint64_t n_host, const uint32_t* n_dev, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b,
                       uint32_t* vals_b, bool iota_vals, int begin_bit, int end_bit, uint32_t* temp, cudaStream_t s,
                       bool* result_in_b);
@@ -299,8 +336,7 @@ int launch_blend_fwd(const tgr_params& p, const GeomView& g, const uint32_t* poi
                      const BinView& b, cudaStream_t s);
 int launch_blend_bwd(const tgr_params& p, const GeomView& g, const uint32_t* point_list, const ImageView& im,
                      const BinView& b, cudaStream_t s);
-int launch_preprocess_bwd(const tgr_params& p, const tgr_binding* bind, const GeomView& g, const float* grad_acc,
-                          cudaStream_t s);
+int launch_preprocess_bwd(const tgr_params& p, const tgr_binding* bind, const ViewBatch& vb, cudaStream_t s);
 int launch_mark_visible(int32_t P, const float* means3D, const float* view, const float* proj, uint8_t* present,
                         cudaStream_t s);
 

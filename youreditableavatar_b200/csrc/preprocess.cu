@@ -124,12 +124,26 @@ constexpr int SH_ROW_PAD = 49;    // padded shared-memory row stride (bank-confl
 
 // STAGED: the block's 256 SH rows (48 KB, contiguous in HBM) are moved global -> shared with fully coalesced
 // 16-byte loads; each thread then reads its own padded row.  Used when M == 16 and degree >= 2.
+// The kernel serves a BATCH of views (ViewBatch, common.cuh): the Gaussian's parameters, its SH row and its 3D
+// covariance are fetched / computed once and every view of the batch is projected from registers.
 template <bool BOUND, bool STAGED>
-__global__ void __launch_bounds__(256) preprocess_kernel(const tgr_params p, const tgr_binding bind, GeomView g) {
+__global__ void __launch_bounds__(256) preprocess_kernel(const tgr_params p, const tgr_binding bind,
+                                                         const __grid_constant__ ViewBatch vb) {
   extern __shared__ float s_rows[];
+  __shared__ float s_cam[MAX_BATCH][CAM_FLOATS];
+  __shared__ uint32_t s_cnt[MAX_BATCH][2];
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int P = p.P;
-  uint32_t my_tiles = 0, my_vis = 0;
+  const int V = vb.V;
+  for (int e = threadIdx.x; e < V * CAM_FLOATS; e += blockDim.x) {
+    const int v = e / CAM_FLOATS, k = e % CAM_FLOATS;
+    float x = 0.f;
+    if (k < 16) x = vb.v[v].viewmatrix[k];
+    else if (k < 32) x = vb.v[v].projmatrix[k - 16];
+    else if (k < 35) x = vb.v[v].campos[k - 32];
+    s_cam[v][k] = x;
+  }
+  if (threadIdx.x < 2 * MAX_BATCH) s_cnt[threadIdx.x >> 1][threadIdx.x & 1] = 0;
   if (STAGED) {
     const int block_first = blockIdx.x * blockDim.x;
     const int nrows = min((int)blockDim.x, P - block_first);
@@ -140,18 +154,20 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const tgr_params p, con
       float* d = s_rows + (e / SH_ROW) * SH_ROW_PAD + (e % SH_ROW);
       d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
     }
-    __syncthreads();
   }
+  __syncthreads();
 
-  if (idx < P) {
-    int radius_out = 0;
-    ushort4 rect_out = make_ushort4(0, 0, 0, 0);
-    uint32_t key_out = 0x7fffffffu;
-
-    float3 p_orig;
-    float3 scale = {0.f, 0.f, 0.f};
-    float4 rot = {1.f, 0.f, 0.f, 0.f};
-    float opacity;
+  const bool live = idx < P;
+  float3 p_orig = {0.f, 0.f, 0.f};
+  float3 scale = {0.f, 0.f, 0.f};
+  float4 rot = {1.f, 0.f, 0.f, 0.f};
+  float opacity = 0.f;
+  Cov3 c3;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) c3.c[k] = 0.f;
+  float sh_local[STAGED ? 1 : 48];
+  float hx_tau = 0.f;
+  if (live) {
     if (BOUND) {
       // mean = sum_k w_k V[f_k] + (sum_k w_k N[f_k]) * delta      (tetgs_model.py:252-258, 335-377)
       const int f = bind.face_index[idx];
@@ -178,112 +194,130 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const tgr_params p, con
       p_orig = {p.means3D[3 * idx], p.means3D[3 * idx + 1], p.means3D[3 * idx + 2]};
       opacity = p.opacities[idx];
     }
-
-    // near culling (auxiliary.h:139-164): keep iff view-space z > 0.2
-    const float3 p_view = xform4x3(p_orig, p.viewmatrix);
-    if (p_view.z > 0.2f) {
-      const float4 p_hom = xform4x4(p_orig, p.projmatrix);
-      const float p_w = 1.0f / (p_hom.w + 0.0000001f);
-      const float3 p_proj = {p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w};
-
-      Cov3 c3;
-      if (p.cov3D_precomp != nullptr && !BOUND) {
+    if (p.cov3D_precomp != nullptr && !BOUND) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) c3.c[k] = p.cov3D_precomp[6 * (size_t)idx + k];
-      } else {
-        if (!BOUND) {
-          scale = {p.scales[3 * idx], p.scales[3 * idx + 1], p.scales[3 * idx + 2]};
-          rot = reinterpret_cast<const float4*>(p.rotations)[idx];
-        }
-        c3 = cov3d_from_scale_rot(scale, p.scale_modifier, rot);
+      for (int k = 0; k < 6; ++k) c3.c[k] = p.cov3D_precomp[6 * (size_t)idx + k];
+    } else {
+      if (!BOUND) {
+        scale = {p.scales[3 * idx], p.scales[3 * idx + 1], p.scales[3 * idx + 2]};
+        rot = reinterpret_cast<const float4*>(p.rotations)[idx];
       }
-
-      const float focal_y = p.H / (2.0f * p.tan_fovy);
-      const float focal_x = p.W / (2.0f * p.tan_fovx);
-      const float3 cov = cov2d(p_orig, focal_x, focal_y, p.tan_fovx, p.tan_fovy, c3.c, p.viewmatrix);
-
-      const float det = (cov.x * cov.z - cov.y * cov.y);
-      if (det != 0.0f) {
-        const float det_inv = 1.f / det;
-        const float3 conic = {cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv};
-        const float mid = 0.5f * (cov.x + cov.z);
-        const float lambda1 = mid + sqrtf(max(0.1f, mid * mid - det));
-        const float lambda2 = mid - sqrtf(max(0.1f, mid * mid - det));
-        const float my_radius = ceilf(3.f * sqrtf(max(lambda1, lambda2)));
-        const float2 point_image = {ndc2pix(p_proj.x, p.W), ndc2pix(p_proj.y, p.H)};
-        const uint32_t gx = (p.W + TILE - 1) / TILE, gy = (p.H + TILE - 1) / TILE;
-        uint2 rmin, rmax;
-        tile_rect(point_image, (int)my_radius, gx, gy, rmin, rmax);
-        const uint32_t ntiles = (rmax.x - rmin.x) * (rmax.y - rmin.y);
-        if (ntiles != 0) {
-          float3 rgb;
-          uint8_t clamped = 0;
-          if (p.colors_precomp != nullptr) {
-            rgb = {p.colors_precomp[3 * idx], p.colors_precomp[3 * idx + 1], p.colors_precomp[3 * idx + 2]};
-          } else {
-            const float3 cam = {p.campos[0], p.campos[1], p.campos[2]};
-            if (STAGED) {
-              rgb = sh_to_rgb(p.D, s_rows + threadIdx.x * SH_ROW_PAD, p_orig, cam, clamped);
-            } else {
-              float sh[48];
-              const int ncoef = (p.D + 1) * (p.D + 1);
-              load_sh(p.shs, (size_t)idx, p.M, ncoef, sh);
-              rgb = sh_to_rgb(p.D, sh, p_orig, cam, clamped);
-            }
-          }
-          // Conservative footprint of {alpha >= 1/255}: |dx| <= sqrt(2 tau Sxx), |dy| <= sqrt(2 tau Syy) with
-          // tau = ln(255 o) and S the inverse of the conic actually used by the blend kernels.  Margins cover
-          // fp32 rounding of power/exp; ill-conditioned conics disable culling (huge extents).  Pairs outside
-          // this box fail the reference's alpha < 1/255 test (forward.cu:343-345), so skipping them is exact.
-          float hx = -1.f, hy = -1.f;
-          if (!(opacity < 1.0f / 255.0f)) {
-            const float tau = logf(255.0f * opacity) * 1.01f + 0.01f;
-            const float ac = conic.x * conic.z, bb = conic.y * conic.y;
-            const float det_lo = (ac - bb) - 1e-6f * (fabsf(ac) + bb);
-            if (det_lo > 0.f && ac <= 1000.f * det_lo && tau < 1e30f) {
-              hx = sqrtf(2.f * tau * conic.z / det_lo) * 1.001f + 0.01f;
-              hy = sqrtf(2.f * tau * conic.x / det_lo) * 1.001f + 0.01f;
-            } else {
-              hx = hy = 1e30f;
-            }
-          }
-          g.xy_ext[idx] = make_float4(point_image.x, point_image.y, hx, hy);
-          g.conic_opacity[idx] = {conic.x, conic.y, conic.z, opacity};
-          g.rgb_depth[idx] = {rgb.x, rgb.y, rgb.z, p_view.z};
-          g.clamped[idx] = clamped;
-          radius_out = (int)my_radius;
-          rect_out = make_ushort4((unsigned short)rmin.x, (unsigned short)rmin.y, (unsigned short)rmax.x,
-                                  (unsigned short)rmax.y);
-          key_out = __float_as_uint(p_view.z);
-          my_tiles = ntiles;
-          my_vis = 1;
-        }
-      }
+      c3 = cov3d_from_scale_rot(scale, p.scale_modifier, rot);
     }
-    p.radii[idx] = radius_out;
-    g.rect[idx] = rect_out;
-    g.depth_key[idx] = key_out;
+    if (!STAGED && p.colors_precomp == nullptr) {
+      const int ncoef = (p.D + 1) * (p.D + 1);
+      load_sh(p.shs, (size_t)idx, p.M, ncoef, sh_local);
+    }
+    // view-independent part of the alpha >= 1/255 footprint (see below): tau = ln(255 o) with margins
+    hx_tau = (opacity < 1.0f / 255.0f) ? -1.f : (logf(255.0f * opacity) * 1.01f + 0.01f);
   }
 
-  // instance count: warp reduce -> block reduce -> one atomic per block
-  __shared__ uint32_t s_t[8], s_v[8];
-  uint32_t wt = __reduce_add_sync(0xffffffffu, my_tiles);
-  uint32_t wv = __reduce_add_sync(0xffffffffu, my_vis);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { s_t[warp] = wt; s_v[warp] = wv; }
+  for (int v = 0; v < V; ++v) {
+    const ViewDesc& vd = vb.v[v];
+    const float* view = s_cam[v];
+    const float* proj = s_cam[v] + 16;
+    uint32_t my_tiles = 0, my_vis = 0;
+    if (live) {
+      int radius_out = 0;
+      ushort4 rect_out = make_ushort4(0, 0, 0, 0);
+      uint32_t key_out = 0x7fffffffu;
+
+      // near culling (auxiliary.h:139-164): keep iff view-space z > 0.2
+      const float3 p_view = xform4x3(p_orig, view);
+      if (p_view.z > 0.2f) {
+        const float4 p_hom = xform4x4(p_orig, proj);
+        const float p_w = 1.0f / (p_hom.w + 0.0000001f);
+        const float3 p_proj = {p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w};
+
+        const float focal_y = vd.H / (2.0f * vd.tan_fovy);
+        const float focal_x = vd.W / (2.0f * vd.tan_fovx);
+        const float3 cov = cov2d(p_orig, focal_x, focal_y, vd.tan_fovx, vd.tan_fovy, c3.c, view);
+
+        const float det = (cov.x * cov.z - cov.y * cov.y);
+        if (det != 0.0f) {
+          const float det_inv = 1.f / det;
+          const float3 conic = {cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv};
+          const float mid = 0.5f * (cov.x + cov.z);
+          const float lambda1 = mid + sqrtf(max(0.1f, mid * mid - det));
+          const float lambda2 = mid - sqrtf(max(0.1f, mid * mid - det));
+          const float my_radius = ceilf(3.f * sqrtf(max(lambda1, lambda2)));
+          const float2 point_image = {ndc2pix(p_proj.x, vd.W), ndc2pix(p_proj.y, vd.H)};
+          const uint32_t gx = (vd.W + TILE - 1) / TILE, gy = (vd.H + TILE - 1) / TILE;
+          uint2 rmin, rmax;
+          tile_rect(point_image, (int)my_radius, gx, gy, rmin, rmax);
+          const uint32_t ntiles = (rmax.x - rmin.x) * (rmax.y - rmin.y);
+          if (ntiles != 0) {
+            float3 rgb;
+            uint8_t clamped = 0;
+            if (p.colors_precomp != nullptr) {
+              rgb = {p.colors_precomp[3 * idx], p.colors_precomp[3 * idx + 1], p.colors_precomp[3 * idx + 2]};
+            } else {
+              const float3 cam = {view[32], view[33], view[34]};
+              rgb = sh_to_rgb(p.D, STAGED ? (s_rows + threadIdx.x * SH_ROW_PAD) : sh_local, p_orig, cam, clamped);
+            }
+            // Conservative footprint of {alpha >= 1/255}: |dx| <= sqrt(2 tau Sxx), |dy| <= sqrt(2 tau Syy) with
+            // tau = ln(255 o) and S the inverse of the conic actually used by the blend kernels.  Margins cover
+            // fp32 rounding of power/exp; ill-conditioned conics disable culling (huge extents).  Pairs outside
+            // this box fail the reference's alpha < 1/255 test (forward.cu:343-345), so skipping them is exact.
+            float hx = -1.f, hy = -1.f;
+            if (!(opacity < 1.0f / 255.0f)) {
+              const float tau = hx_tau;
+              const float ac = conic.x * conic.z, bb = conic.y * conic.y;
+              const float det_lo = (ac - bb) - 1e-6f * (fabsf(ac) + bb);
+              if (det_lo > 0.f && ac <= 1000.f * det_lo && tau < 1e30f) {
+                hx = sqrtf(2.f * tau * conic.z / det_lo) * 1.001f + 0.01f;
+                hy = sqrtf(2.f * tau * conic.x / det_lo) * 1.001f + 0.01f;
+              } else {
+                hx = hy = 1e30f;
+              }
+            }
+            vd.xy_ext[idx] = make_float4(point_image.x, point_image.y, hx, hy);
+            vd.conic_opacity[idx] = {conic.x, conic.y, conic.z, opacity};
+            vd.rgb_depth[idx] = {rgb.x, rgb.y, rgb.z, p_view.z};
+            vd.clamped[idx] = clamped;
+            radius_out = (int)my_radius;
+            rect_out = make_ushort4((unsigned short)rmin.x, (unsigned short)rmin.y, (unsigned short)rmax.x,
+                                    (unsigned short)rmax.y);
+            key_out = __float_as_uint(p_view.z);
+            my_tiles = ntiles;
+            my_vis = 1;
+          }
+        }
+      }
+      vd.radii[idx] = radius_out;
+      vd.rect[idx] = rect_out;
+      vd.depth_key[idx] = key_out;
+    }
+    // instance count of this view: warp reduce -> shared atomics -> one global atomic per block (below)
+    const uint32_t wt = __reduce_add_sync(0xffffffffu, my_tiles);
+    const uint32_t wv = __reduce_add_sync(0xffffffffu, my_vis);
+    if ((threadIdx.x & 31) == 0) {
+      if (wt) atomicAdd(&s_cnt[v][0], wt);
+      if (wv) atomicAdd(&s_cnt[v][1], wv);
+    }
+  }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t t = 0, v = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) { t += s_t[w]; v += s_v[w]; }
-    if (t) atomicAdd(&g.header->num_rendered, t);
-    if (v) atomicAdd(&g.header->num_visible, v);
+  if (threadIdx.x < V) {
+    const uint32_t t = s_cnt[threadIdx.x][0], n = s_cnt[threadIdx.x][1];
+    if (t) atomicAdd(&vb.v[threadIdx.x].header->num_rendered, t);
+    if (n) atomicAdd(&vb.v[threadIdx.x].header->num_visible, n);
   }
 }
 
-int launch_preprocess(const tgr_params& p, const tgr_binding* bind, const GeomView& g, cudaStream_t s) {
+ViewDesc make_view_desc(const tgr_params& p, const GeomView& g, const float* grad_acc) {
+  ViewDesc d{};
+  d.viewmatrix = p.viewmatrix; d.projmatrix = p.projmatrix; d.campos = p.campos;
+  d.tan_fovx = p.tan_fovx; d.tan_fovy = p.tan_fovy; d.W = p.W; d.H = p.H;
+  d.radii = p.radii; d.header = g.header; d.depth_key = g.depth_key; d.rect = g.rect;
+  d.xy_ext = g.xy_ext; d.conic_opacity = g.conic_opacity; d.rgb_depth = g.rgb_depth; d.clamped = g.clamped;
+  d.grad_acc = grad_acc;
+  return d;
+}
+
+// `p` carries the Gaussians (shared by every view of the batch); cameras and per-view outputs come from `vb`.
+int launch_preprocess(const tgr_params& p, const tgr_binding* bind, const ViewBatch& vb, cudaStream_t s) {
   const int blocks = (p.P + 255) / 256;
-  if (blocks == 0) return 0;
+  if (blocks == 0 || vb.V <= 0) return 0;
   const bool staged = p.colors_precomp == nullptr && p.shs != nullptr && p.M == 16 && p.D >= 2 &&
                       (reinterpret_cast<uintptr_t>(p.shs) & 15) == 0;
   const size_t smem = staged ? (size_t)256 * SH_ROW_PAD * sizeof(float) : 0;
@@ -296,11 +330,11 @@ int launch_preprocess(const tgr_params& p, const tgr_binding* bind, const GeomVi
   tgr_binding none{};
   const tgr_binding& b = bind ? *bind : none;
   if (bind) {
-    if (staged) preprocess_kernel<true, true><<<blocks, 256, smem, s>>>(p, b, g);
-    else preprocess_kernel<true, false><<<blocks, 256, 0, s>>>(p, b, g);
+    if (staged) preprocess_kernel<true, true><<<blocks, 256, smem, s>>>(p, b, vb);
+    else preprocess_kernel<true, false><<<blocks, 256, 0, s>>>(p, b, vb);
   } else {
-    if (staged) preprocess_kernel<false, true><<<blocks, 256, smem, s>>>(p, b, g);
-    else preprocess_kernel<false, false><<<blocks, 256, 0, s>>>(p, b, g);
+    if (staged) preprocess_kernel<false, true><<<blocks, 256, smem, s>>>(p, b, vb);
+    else preprocess_kernel<false, false><<<blocks, 256, 0, s>>>(p, b, vb);
   }
   count_launch();
   return check_launch("preprocess", p.debug != 0, s);

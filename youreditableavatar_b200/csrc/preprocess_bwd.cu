@@ -40,13 +40,27 @@ constexpr int SH_ROW_PAD = 49;    // padded shared-memory row stride: 49*t mod 3
 // 16-byte loads, each thread then walks its own padded row bank-conflict-free; dL/dsh goes back the same way.
 // (One thread per Gaussian reading 48 floats at a 192-byte stride straight from global costs 32 sectors per
 // request — ncu showed the unstaged kernel at ~30% of HBM bandwidth.)
-template <bool BOUND, bool STAGED>
-__global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p, const tgr_binding bind, GeomView g,
-                                                             const float* __restrict__ grad_acc) {
+// MULTI: the kernel serves a batch of views (ViewBatch, common.cuh).  Parameters are read once, every view's
+// packed 2-D gradient row is chained back to 3-D and summed in registers / a second shared-memory SH tile, and
+// the parameter gradients are written ONCE — per-view calls would read-modify-write 236 B per Gaussian and view.
+// With MULTI = false (one view) the SH row is overwritten in place by its gradient, as before.
+template <bool BOUND, bool STAGED, bool MULTI>
+__global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p, const tgr_binding bind,
+                                                             const __grid_constant__ ViewBatch vb) {
   extern __shared__ float s_rows[];
+  __shared__ float s_cam[MAX_BATCH][CAM_FLOATS];
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int block_first = blockIdx.x * blockDim.x;
   const int nrows = min((int)blockDim.x, p.P - block_first);
+  const int V = MULTI ? vb.V : 1;
+  for (int e = threadIdx.x; e < V * CAM_FLOATS; e += blockDim.x) {
+    const int v = e / CAM_FLOATS, k = e % CAM_FLOATS;
+    float x = 0.f;
+    if (k < 16) x = vb.v[v].viewmatrix[k];
+    else if (k < 32) x = vb.v[v].projmatrix[k - 16];
+    else if (k < 35) x = vb.v[v].campos[k - 32];
+    s_cam[v][k] = x;
+  }
   if (STAGED) {
     const float4* src = reinterpret_cast<const float4*>(p.shs + (size_t)block_first * SH_ROW);
     for (int v = threadIdx.x; v < nrows * (SH_ROW / 4); v += blockDim.x) {
@@ -55,9 +69,17 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
       float* d = s_rows + (e / SH_ROW) * SH_ROW_PAD + (e % SH_ROW);
       d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
     }
-    __syncthreads();
   }
   float* const row = s_rows + threadIdx.x * SH_ROW_PAD;
+  // gradient tile of the SH rows: a second tile when several views are summed, else the SH row itself
+  float* const s_out = (STAGED && MULTI) ? (s_rows + 256 * SH_ROW_PAD) : s_rows;
+  float* const orow = s_out + threadIdx.x * SH_ROW_PAD;
+  if (STAGED && MULTI) {
+#pragma unroll
+    for (int k = 0; k < SH_ROW; ++k) orow[k] = 0.f;
+  }
+  __syncthreads();
+
   float o_m2[2] = {0.f, 0.f}, o_col[3] = {0.f, 0.f, 0.f}, o_op = 0.f, o_mean[3] = {0.f, 0.f, 0.f};
   float o_cov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, o_sc[3] = {0.f, 0.f, 0.f}, o_rot[4] = {0.f, 0.f, 0.f, 0.f};
   if (idx < p.P) {
@@ -65,7 +87,6 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
   const int M = p.M;
   const bool has_sh = (p.shs != nullptr && p.colors_precomp == nullptr && M > 0);
   const bool has_sr = BOUND || (p.scales != nullptr && p.rotations != nullptr && p.cov3D_precomp == nullptr);
-  const int radius = p.radii[idx];
 
   float dmean[3] = {0.f, 0.f, 0.f};
   float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -76,53 +97,70 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
   float3 mean = {0.f, 0.f, 0.f};
   float3 scale = {0.f, 0.f, 0.f};
   float4 rot = {1.f, 0.f, 0.f, 0.f};
-
-  if (radius > 0) {
-    const float4* acc4 = reinterpret_cast<const float4*>(grad_acc + i * GRAD_ACC);
-    const float4 a0 = acc4[0], a1 = acc4[1], a2 = acc4[2];
-    dm2[0] = a0.x; dm2[1] = a0.y;
-    const float dconx = a0.z, dcony = a0.w, dconz = a1.x;
-    dop = a1.y;
-    dcol[0] = a1.z; dcol[1] = a1.w; dcol[2] = a2.x;
-    const float dz = a2.y;
-
-    if (BOUND) {
-      mean = {bind.out_means3D[3 * i], bind.out_means3D[3 * i + 1], bind.out_means3D[3 * i + 2]};
-      scale = {bind.out_scales[3 * i], bind.out_scales[3 * i + 1], bind.out_scales[3 * i + 2]};
-      rot = reinterpret_cast<const float4*>(bind.out_rotations)[i];
-    } else {
-      mean = {p.means3D[3 * i], p.means3D[3 * i + 1], p.means3D[3 * i + 2]};
-      if (has_sr) {
-        scale = {p.scales[3 * i], p.scales[3 * i + 1], p.scales[3 * i + 2]};
-        rot = reinterpret_cast<const float4*>(p.rotations)[i];
-      }
-    }
-    const float* view = p.viewmatrix;
-    const float* proj = p.projmatrix;
-
-    // ---- 3D covariance (recomputed rather than stored by the forward) ---------------------------
-    float c3[6];
-    float r = rot.x, x = rot.y, y = rot.z, z = rot.w;
-    M3 R = m3(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
-              2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x),
-              2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y));
-    const float3 s = {p.scale_modifier * scale.x, p.scale_modifier * scale.y, p.scale_modifier * scale.z};
-    M3 Mm;
+  if (BOUND) {
+    mean = {bind.out_means3D[3 * i], bind.out_means3D[3 * i + 1], bind.out_means3D[3 * i + 2]};
+    scale = {bind.out_scales[3 * i], bind.out_scales[3 * i + 1], bind.out_scales[3 * i + 2]};
+    rot = reinterpret_cast<const float4*>(bind.out_rotations)[i];
+  } else {
+    mean = {p.means3D[3 * i], p.means3D[3 * i + 1], p.means3D[3 * i + 2]};
     if (has_sr) {
-      M3 S = m3(s.x, 0.f, 0.f, 0.f, s.y, 0.f, 0.f, 0.f, s.z);
-      Mm = m3_mul(S, R);
-      M3 Sg = m3_mul(m3_T(Mm), Mm);
-      c3[0] = Sg.m[0][0]; c3[1] = Sg.m[0][1]; c3[2] = Sg.m[0][2]; c3[3] = Sg.m[1][1]; c3[4] = Sg.m[1][2]; c3[5] = Sg.m[2][2];
-    } else {
-#pragma unroll
-      for (int k = 0; k < 6; ++k) c3[k] = p.cov3D_precomp[6 * i + k];
+      scale = {p.scales[3 * i], p.scales[3 * i + 1], p.scales[3 * i + 2]};
+      rot = reinterpret_cast<const float4*>(p.rotations)[i];
     }
+  }
+
+  // ---- 3D covariance (recomputed rather than stored by the forward; view-independent) ------------
+  float c3[6];
+  const float r = rot.x, x = rot.y, y = rot.z, z = rot.w;
+  M3 R = m3(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
+            2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x),
+            2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y));
+  const float3 s = {p.scale_modifier * scale.x, p.scale_modifier * scale.y, p.scale_modifier * scale.z};
+  M3 Mm;
+  if (has_sr) {
+    M3 S = m3(s.x, 0.f, 0.f, 0.f, s.y, 0.f, 0.f, 0.f, s.z);
+    Mm = m3_mul(S, R);
+    M3 Sg = m3_mul(m3_T(Mm), Mm);
+    c3[0] = Sg.m[0][0]; c3[1] = Sg.m[0][1]; c3[2] = Sg.m[0][2]; c3[3] = Sg.m[1][1]; c3[4] = Sg.m[1][2]; c3[5] = Sg.m[2][2];
+  } else {
+    Mm = m3(0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) c3[k] = p.cov3D_precomp[6 * i + k];
+  }
+  float sh_local[STAGED ? 1 : 48];
+  if (!STAGED && has_sh) {
+    const int ncoef = (p.D + 1) * (p.D + 1);
+    const float* base = p.shs + i * (size_t)M * 3;
+#pragma unroll
+    for (int k = 0; k < 48; ++k)
+      if (k < ncoef * 3) sh_local[k] = __ldg(base + k);
+  }
+  bool any_visible = false;
+
+  for (int vi = 0; vi < V; ++vi) {
+  const ViewDesc& vd = vb.v[vi];
+  const int radius = vd.radii[idx];
+  // non-staged SH path writes global memory directly: views after the first always add
+  const bool acc_sh = p.accumulate != 0 || vi > 0;
+  if (radius > 0) {
+    any_visible = true;
+    const float4* acc4 = reinterpret_cast<const float4*>(vd.grad_acc + i * GRAD_ACC);
+    const float4 a0 = acc4[0], a1 = acc4[1], a2 = acc4[2];
+    const float vm2[2] = {a0.x, a0.y};
+    dm2[0] += a0.x; dm2[1] += a0.y;
+    const float dconx = a0.z, dcony = a0.w, dconz = a1.x;
+    dop += a1.y;
+    const float vcol[3] = {a1.z, a1.w, a2.x};
+    dcol[0] += a1.z; dcol[1] += a1.w; dcol[2] += a2.x;
+    const float dz = a2.y;
+    const float* view = s_cam[vi];
+    const float* proj = s_cam[vi] + 16;
 
     // ---- conic -> cov2D -> cov3D and the covariance part of dL/dmean (backward.cu:144-274) --------
     {
-      const float h_x = p.W / (2.0f * p.tan_fovx), h_y = p.H / (2.0f * p.tan_fovy);
+      const float h_x = vd.W / (2.0f * vd.tan_fovx), h_y = vd.H / (2.0f * vd.tan_fovy);
       float3 t = xform4x3(mean, view);
-      const float limx = 1.3f * p.tan_fovx, limy = 1.3f * p.tan_fovy;
+      const float limx = 1.3f * vd.tan_fovx, limy = 1.3f * vd.tan_fovy;
       const float txtz = t.x / t.z, tytz = t.y / t.z;
       t.x = min(limx, max(-limx, txtz)) * t.z;
       t.y = min(limy, max(-limy, tytz)) * t.z;
@@ -143,12 +181,12 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
         dL_dc = denom2inv * (-a * a * dconz + 2 * a * b * dcony + (denom - a * c) * dconx);
         dL_db = denom2inv * 2 * (b * c * dconx - (denom + 2 * b * b) * dcony + a * b * dconz);
         const float (*Tm)[3] = T.m;
-        dcov[0] = (Tm[0][0] * Tm[0][0] * dL_da + Tm[0][0] * Tm[1][0] * dL_db + Tm[1][0] * Tm[1][0] * dL_dc);
-        dcov[3] = (Tm[0][1] * Tm[0][1] * dL_da + Tm[0][1] * Tm[1][1] * dL_db + Tm[1][1] * Tm[1][1] * dL_dc);
-        dcov[5] = (Tm[0][2] * Tm[0][2] * dL_da + Tm[0][2] * Tm[1][2] * dL_db + Tm[1][2] * Tm[1][2] * dL_dc);
-        dcov[1] = 2 * Tm[0][0] * Tm[0][1] * dL_da + (Tm[0][0] * Tm[1][1] + Tm[0][1] * Tm[1][0]) * dL_db + 2 * Tm[1][0] * Tm[1][1] * dL_dc;
-        dcov[2] = 2 * Tm[0][0] * Tm[0][2] * dL_da + (Tm[0][0] * Tm[1][2] + Tm[0][2] * Tm[1][0]) * dL_db + 2 * Tm[1][0] * Tm[1][2] * dL_dc;
-        dcov[4] = 2 * Tm[0][2] * Tm[0][1] * dL_da + (Tm[0][1] * Tm[1][2] + Tm[0][2] * Tm[1][1]) * dL_db + 2 * Tm[1][1] * Tm[1][2] * dL_dc;
+        dcov[0] += (Tm[0][0] * Tm[0][0] * dL_da + Tm[0][0] * Tm[1][0] * dL_db + Tm[1][0] * Tm[1][0] * dL_dc);
+        dcov[3] += (Tm[0][1] * Tm[0][1] * dL_da + Tm[0][1] * Tm[1][1] * dL_db + Tm[1][1] * Tm[1][1] * dL_dc);
+        dcov[5] += (Tm[0][2] * Tm[0][2] * dL_da + Tm[0][2] * Tm[1][2] * dL_db + Tm[1][2] * Tm[1][2] * dL_dc);
+        dcov[1] += 2 * Tm[0][0] * Tm[0][1] * dL_da + (Tm[0][0] * Tm[1][1] + Tm[0][1] * Tm[1][0]) * dL_db + 2 * Tm[1][0] * Tm[1][1] * dL_dc;
+        dcov[2] += 2 * Tm[0][0] * Tm[0][2] * dL_da + (Tm[0][0] * Tm[1][2] + Tm[0][2] * Tm[1][0]) * dL_db + 2 * Tm[1][0] * Tm[1][2] * dL_dc;
+        dcov[4] += 2 * Tm[0][2] * Tm[0][1] * dL_da + (Tm[0][1] * Tm[1][2] + Tm[0][2] * Tm[1][1]) * dL_db + 2 * Tm[1][1] * Tm[1][2] * dL_dc;
       }
       // dL/dT (upper 2x3), then dL/dJ, then dL/dt
       float dT0[3], dT1[3];
@@ -167,9 +205,9 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
       const float dtx = x_grad_mul * -h_x * tz2 * dJ02;
       const float dty = y_grad_mul * -h_y * tz2 * dJ12;
       const float dtz = -h_x * tz2 * dJ00 - h_y * tz2 * dJ11 + (2 * h_x * t.x) * tz3 * dJ02 + (2 * h_y * t.y) * tz3 * dJ12;
-      dmean[0] = view[0] * dtx + view[1] * dty + view[2] * dtz;
-      dmean[1] = view[4] * dtx + view[5] * dty + view[6] * dtz;
-      dmean[2] = view[8] * dtx + view[9] * dty + view[10] * dtz;
+      dmean[0] += view[0] * dtx + view[1] * dty + view[2] * dtz;
+      dmean[1] += view[4] * dtx + view[5] * dty + view[6] * dtz;
+      dmean[2] += view[8] * dtx + view[9] * dty + view[10] * dtz;
     }
 
     // ---- screen-space mean -> 3D mean through the projective divide (backward.cu:370-387) -------
@@ -178,9 +216,9 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
       const float m_w = 1.0f / (m_hom.w + 0.0000001f);
       const float mul1 = (proj[0] * mean.x + proj[4] * mean.y + proj[8] * mean.z + proj[12]) * m_w * m_w;
       const float mul2 = (proj[1] * mean.x + proj[5] * mean.y + proj[9] * mean.z + proj[13]) * m_w * m_w;
-      dmean[0] += (proj[0] * m_w - proj[3] * mul1) * dm2[0] + (proj[1] * m_w - proj[3] * mul2) * dm2[1];
-      dmean[1] += (proj[4] * m_w - proj[7] * mul1) * dm2[0] + (proj[5] * m_w - proj[7] * mul2) * dm2[1];
-      dmean[2] += (proj[8] * m_w - proj[11] * mul1) * dm2[0] + (proj[9] * m_w - proj[11] * mul2) * dm2[1];
+      dmean[0] += (proj[0] * m_w - proj[3] * mul1) * vm2[0] + (proj[1] * m_w - proj[3] * mul2) * vm2[1];
+      dmean[1] += (proj[4] * m_w - proj[7] * mul1) * vm2[0] + (proj[5] * m_w - proj[7] * mul2) * vm2[1];
+      dmean[2] += (proj[8] * m_w - proj[11] * mul1) * vm2[0] + (proj[9] * m_w - proj[11] * mul2) * vm2[1];
       // extras: depth image gradient reaches the mean through row 2 of the view matrix
       dmean[0] += view[2] * dz; dmean[1] += view[6] * dz; dmean[2] += view[10] * dz;
     }
@@ -189,22 +227,15 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
     if (has_sh) {
       const int D = p.D;
       const int ncoef = (D + 1) * (D + 1);
-      float sh_local[STAGED ? 1 : 48];
-      if (!STAGED) {
-        const float* base = p.shs + i * (size_t)M * 3;
-#pragma unroll
-        for (int k = 0; k < 48; ++k)
-          if (k < ncoef * 3) sh_local[k] = __ldg(base + k);
-      }
       const float* sh = STAGED ? row : sh_local;
-      const float3 cam = {p.campos[0], p.campos[1], p.campos[2]};
+      const float3 cam = {view[32], view[33], view[34]};
       const float3 dir_orig = {mean.x - cam.x, mean.y - cam.y, mean.z - cam.z};
       const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
       const float dx = dir_orig.x / len, dy = dir_orig.y / len, dzv = dir_orig.z / len;
-      const uint8_t cl = g.clamped[i];
+      const uint8_t cl = vd.clamped[i];
       float dRGB[3];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) dRGB[c] = ((cl >> c) & 1) ? 0.f : dcol[c];
+      for (int c = 0; c < 3; ++c) dRGB[c] = ((cl >> c) & 1) ? 0.f : vcol[c];
 
       float w[16];  // d(colour)/d(sh_k) basis weights
 #pragma unroll
@@ -249,7 +280,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
           }
         }
       }
-      // view-direction term first (it still needs the SH values that the staged row is about to lose)
+      // view-direction term first (with one view the staged SH row is about to be overwritten by its gradient)
       const float ddir[3] = {dRGBdx[0] * dRGB[0] + dRGBdx[1] * dRGB[1] + dRGBdx[2] * dRGB[2],
                              dRGBdy[0] * dRGB[0] + dRGBdy[1] * dRGB[1] + dRGBdy[2] * dRGB[2],
                              dRGBdz[0] * dRGB[0] + dRGBdz[1] * dRGB[1] + dRGBdz[2] * dRGB[2]};
@@ -258,13 +289,16 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
           const float wk = (k < ncoef) ? w[k] : 0.f;
-          row[3 * k + 0] = wk * dRGB[0]; row[3 * k + 1] = wk * dRGB[1]; row[3 * k + 2] = wk * dRGB[2];
+          if (MULTI) {
+            orow[3 * k + 0] += wk * dRGB[0]; orow[3 * k + 1] += wk * dRGB[1]; orow[3 * k + 2] += wk * dRGB[2];
+          } else {
+            orow[3 * k + 0] = wk * dRGB[0]; orow[3 * k + 1] = wk * dRGB[1]; orow[3 * k + 2] = wk * dRGB[2];
+          }
         }
       } else {
         float* out = p.dL_dsh + i * (size_t)M * 3;
         for (int k = 0; k < M; ++k) {
           const float wk = (k < ncoef && k < 16) ? w[k] : 0.f;
-          const bool acc_sh = p.accumulate != 0;
           put(out + 3 * k + 0, wk * dRGB[0], acc_sh); put(out + 3 * k + 1, wk * dRGB[1], acc_sh); put(out + 3 * k + 2, wk * dRGB[2], acc_sh);
         }
       }
@@ -276,39 +310,42 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
       dmean[1] += (-v.x * v.y * ddir[0] + (sum2 - v.y * v.y) * ddir[1] - v.z * v.y * ddir[2]) * invsum32;
       dmean[2] += (-v.x * v.z * ddir[0] - v.y * v.z * ddir[1] + (sum2 - v.z * v.z) * ddir[2]) * invsum32;
     }
-
-    // ---- 3D covariance -> scale / quaternion (backward.cu:278-341) --------------------------------
-    if (has_sr) {
-      M3 dSigma = m3(dcov[0], 0.5f * dcov[1], 0.5f * dcov[2], 0.5f * dcov[1], dcov[3], 0.5f * dcov[4],
-                     0.5f * dcov[2], 0.5f * dcov[4], dcov[5]);
-      M3 M2;
-#pragma unroll
-      for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int rr = 0; rr < 3; ++rr) M2.m[c][rr] = 2.0f * Mm.m[c][rr];
-      M3 dM = m3_mul(M2, dSigma);
-      M3 Rt = m3_T(R);
-      M3 dMt = m3_T(dM);
-      dscale[0] = Rt.m[0][0] * dMt.m[0][0] + Rt.m[0][1] * dMt.m[0][1] + Rt.m[0][2] * dMt.m[0][2];
-      dscale[1] = Rt.m[1][0] * dMt.m[1][0] + Rt.m[1][1] * dMt.m[1][1] + Rt.m[1][2] * dMt.m[1][2];
-      dscale[2] = Rt.m[2][0] * dMt.m[2][0] + Rt.m[2][1] * dMt.m[2][1] + Rt.m[2][2] * dMt.m[2][2];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) { dMt.m[0][k] *= s.x; dMt.m[1][k] *= s.y; dMt.m[2][k] *= s.z; }
-      const float (*D)[3] = dMt.m;
-      drot[0] = 2 * z * (D[0][1] - D[1][0]) + 2 * y * (D[2][0] - D[0][2]) + 2 * x * (D[1][2] - D[2][1]);
-      drot[1] = 2 * y * (D[1][0] + D[0][1]) + 2 * z * (D[2][0] + D[0][2]) + 2 * r * (D[1][2] - D[2][1]) - 4 * x * (D[2][2] + D[1][1]);
-      drot[2] = 2 * x * (D[1][0] + D[0][1]) + 2 * r * (D[2][0] - D[0][2]) + 2 * z * (D[1][2] + D[2][1]) - 4 * y * (D[2][2] + D[0][0]);
-      drot[3] = 2 * r * (D[0][1] - D[1][0]) + 2 * x * (D[2][0] + D[0][2]) + 2 * y * (D[1][2] + D[2][1]) - 4 * z * (D[1][1] + D[0][0]);
-    }
   } else if (has_sh) {
-    // culled Gaussian: its SH gradient rows are zero
+    // Gaussian culled in this view: its SH gradient rows are zero
     if (STAGED) {
+      if (!MULTI) {
 #pragma unroll
-      for (int k = 0; k < SH_ROW; ++k) row[k] = 0.f;
+        for (int k = 0; k < SH_ROW; ++k) orow[k] = 0.f;
+      }
     } else {
       float* out = p.dL_dsh + i * (size_t)M * 3;
-      if (!p.accumulate) for (int k = 0; k < M * 3; ++k) out[k] = 0.f;
+      if (!acc_sh) for (int k = 0; k < M * 3; ++k) out[k] = 0.f;
     }
+  }
+  }  // views
+
+  // ---- 3D covariance -> scale / quaternion (backward.cu:278-341); linear in dcov, so once per batch ----
+  if (has_sr && any_visible) {
+    M3 dSigma = m3(dcov[0], 0.5f * dcov[1], 0.5f * dcov[2], 0.5f * dcov[1], dcov[3], 0.5f * dcov[4],
+                   0.5f * dcov[2], 0.5f * dcov[4], dcov[5]);
+    M3 M2;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int rr = 0; rr < 3; ++rr) M2.m[c][rr] = 2.0f * Mm.m[c][rr];
+    M3 dM = m3_mul(M2, dSigma);
+    M3 Rt = m3_T(R);
+    M3 dMt = m3_T(dM);
+    dscale[0] = Rt.m[0][0] * dMt.m[0][0] + Rt.m[0][1] * dMt.m[0][1] + Rt.m[0][2] * dMt.m[0][2];
+    dscale[1] = Rt.m[1][0] * dMt.m[1][0] + Rt.m[1][1] * dMt.m[1][1] + Rt.m[1][2] * dMt.m[1][2];
+    dscale[2] = Rt.m[2][0] * dMt.m[2][0] + Rt.m[2][1] * dMt.m[2][1] + Rt.m[2][2] * dMt.m[2][2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { dMt.m[0][k] *= s.x; dMt.m[1][k] *= s.y; dMt.m[2][k] *= s.z; }
+    const float (*D)[3] = dMt.m;
+    drot[0] = 2 * z * (D[0][1] - D[1][0]) + 2 * y * (D[2][0] - D[0][2]) + 2 * x * (D[1][2] - D[2][1]);
+    drot[1] = 2 * y * (D[1][0] + D[0][1]) + 2 * z * (D[2][0] + D[0][2]) + 2 * r * (D[1][2] - D[2][1]) - 4 * x * (D[2][2] + D[1][1]);
+    drot[2] = 2 * x * (D[1][0] + D[0][1]) + 2 * r * (D[2][0] - D[0][2]) + 2 * z * (D[1][2] + D[2][1]) - 4 * y * (D[2][2] + D[0][0]);
+    drot[3] = 2 * r * (D[0][1] - D[1][0]) + 2 * x * (D[2][0] + D[0][2]) + 2 * y * (D[1][2] + D[2][1]) - 4 * z * (D[1][1] + D[0][0]);
   }
 
   // ---- the P-sized outputs leave through shared memory (see the epilogue) ------------------------------
@@ -347,7 +384,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
       const float o = bind.out_opacities[i];
       put(bind.dL_dopacity_logits + i, dop * o * (1.f - o), acc);
     }
-    if (bind.dL_dverts && radius > 0) {
+    if (bind.dL_dverts && any_visible) {
       const int vi[3] = {i0, i1, i2};
       const float wv[3] = {w0, w1, w2};
 #pragma unroll
@@ -362,7 +399,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
     float4* dst = reinterpret_cast<float4*>(p.dL_dsh + (size_t)block_first * SH_ROW);
     for (int v = threadIdx.x; v < nrows * (SH_ROW / 4); v += blockDim.x) {
       const int e = v * 4;
-      const float* d = s_rows + (e / SH_ROW) * SH_ROW_PAD + (e % SH_ROW);
+      const float* d = s_out + (e / SH_ROW) * SH_ROW_PAD + (e % SH_ROW);
       float4 o = make_float4(d[0], d[1], d[2], d[3]);
       if (p.accumulate) { const float4 old = dst[v]; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
       dst[v] = o;
@@ -399,29 +436,36 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
   }
 }
 
-int launch_preprocess_bwd(const tgr_params& p, const tgr_binding* bind, const GeomView& g, const float* grad_acc,
-                          cudaStream_t s) {
+// `p` carries the Gaussians and the output gradient tensors (shared by the batch); cameras, radii, clamp flags
+// and the packed 2-D gradient rows of every view come from `vb`.
+int launch_preprocess_bwd(const tgr_params& p, const tgr_binding* bind, const ViewBatch& vb, cudaStream_t s) {
   const int blocks = (p.P + 255) / 256;
-  if (blocks == 0) return 0;
+  if (blocks == 0 || vb.V <= 0) return 0;
   const bool has_sh = (p.shs != nullptr && p.colors_precomp == nullptr && p.M > 0);
   const bool staged = has_sh && p.M == 16 && p.D >= 2 && p.dL_dsh != nullptr &&
                       (reinterpret_cast<uintptr_t>(p.shs) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.dL_dsh) & 15) == 0;
-  const size_t smem = staged ? (size_t)256 * SH_ROW_PAD * sizeof(float) : (size_t)256 * 23 * sizeof(float);
+  const bool multi = vb.V > 1;
+  const size_t tile = (size_t)256 * SH_ROW_PAD * sizeof(float);
+  const size_t smem = staged ? (multi ? 2 * tile : tile) : (size_t)256 * 23 * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(preprocess_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * SH_ROW_PAD * 4);
-    cudaFuncSetAttribute(preprocess_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * SH_ROW_PAD * 4);
+    cudaFuncSetAttribute(preprocess_bwd_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile);
+    cudaFuncSetAttribute(preprocess_bwd_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile);
+    cudaFuncSetAttribute(preprocess_bwd_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * tile));
+    cudaFuncSetAttribute(preprocess_bwd_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * tile));
     attr_set = true;
   }
   tgr_binding none{};
   const tgr_binding& b = bind ? *bind : none;
+#define TGR_PB_LAUNCH(B, S, M) preprocess_bwd_kernel<B, S, M><<<blocks, 256, smem, s>>>(p, b, vb)
   if (bind) {
-    if (staged) preprocess_bwd_kernel<true, true><<<blocks, 256, smem, s>>>(p, b, g, grad_acc);
-    else preprocess_bwd_kernel<true, false><<<blocks, 256, smem, s>>>(p, b, g, grad_acc);
+    if (staged) { if (multi) TGR_PB_LAUNCH(true, true, true); else TGR_PB_LAUNCH(true, true, false); }
+    else        { if (multi) TGR_PB_LAUNCH(true, false, true); else TGR_PB_LAUNCH(true, false, false); }
   } else {
-    if (staged) preprocess_bwd_kernel<false, true><<<blocks, 256, smem, s>>>(p, b, g, grad_acc);
-    else preprocess_bwd_kernel<false, false><<<blocks, 256, smem, s>>>(p, b, g, grad_acc);
+    if (staged) { if (multi) TGR_PB_LAUNCH(false, true, true); else TGR_PB_LAUNCH(false, true, false); }
+    else        { if (multi) TGR_PB_LAUNCH(false, false, true); else TGR_PB_LAUNCH(false, false, false); }
   }
+#undef TGR_PB_LAUNCH
   count_launch();
   return check_launch("preprocess_bwd", p.debug != 0, s);
 }

@@ -1,0 +1,296 @@
+"""Multi-view batches of the rasterizer: V cameras over the SAME Gaussians in one operator call.
+
+The reference renders one view per call and per optimizer step (Edit_core/tetgs_texture/refine.py:54,
+tetgs_scene/tetgs_model.py:467-614); its SDS / inpainting stages loop over views in Python.  On a B200 that leaves
+two things on the table, which this module picks up (C ABI: tgr_*_batch in include/tetgs_rast.h):
+
+  * the per-Gaussian kernels are HBM-bound and re-read 236 B of parameters per Gaussian and view (and the
+    backward re-writes as much gradient per view).  Here one launch projects every Gaussian into all V views
+    (`tgr_forward_preprocess_batch`) and one launch chains all V packed 2-D gradients back to the parameters
+    (`tgr_backward_preprocess_batch`): parameters are read once, gradients written once per batch;
+  * the per-view stages in between (depth sort, binning, tile sort, blending) are independent across views and
+    individually leave SMs idle (latency-bound sorts, the tail of the heaviest tile); they are issued round-robin
+    on a few CUDA streams so one view's tail is filled by the next view's kernels.
+
+PyTorch is plumbing only: memory, streams/events, autograd bookkeeping.  There is no CPU path.
+"""
+from typing import List, Optional, Sequence
+
+import ctypes as C
+import torch
+
+from . import _lib
+from ._lib import TgrParams, check
+from . import rasterizer as rz
+
+__all__ = ["c_rasterize_views", "c_rasterize_views_backward", "rasterize_views", "MultiViewRasterizer", "ViewBatchState"]
+
+_side = {}
+
+
+def _side_streams(device: torch.device, n: int) -> List[torch.cuda.Stream]:
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    pool = _side.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:n]
+
+
+_pinned_counts = {}
+
+
+def _count_slots(device: torch.device, n: int) -> torch.Tensor:
+    """Pinned int32 slots for the asynchronous instance-count read-back of a batch (double-buffered)."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    ent = _pinned_counts.get(key)
+    if ent is None or ent[0].shape[1] < n:
+        ent = [torch.zeros(2, max(n, 64), dtype=torch.int32).pin_memory(), 0]
+        _pinned_counts[key] = ent
+    ent[1] ^= 1
+    return ent[0][ent[1], :n]
+
+
+class ViewBatchState:
+    """Everything the backward needs from a batched forward (the analogue of the tensors the reference's
+    autograd Function saves, diff_gaussian_rasterization/__init__.py:97): parameter structs, the per-view
+    instance counts and the opaque workspaces."""
+
+    def __init__(self):
+        self.params = None      # (TgrParams * V)
+        self.counts = None      # list[int]
+        self.tensors = None     # keeps every buffer the structs point into alive
+        self.V = 0
+        self.extras = False
+        self.n_streams = 1
+        self.binding = None
+
+
+def _align(x: int, a: int = 256) -> int:
+    return (x + a - 1) // a * a
+
+
+def c_rasterize_views(settings: Sequence, means3D, colors, opacity, scales, rotations, cov3D_precomp, sh,
+                      extras: bool = False, n_streams: int = 4, binding=None):
+    """Forward of V views.  `settings` is a sequence of GaussianRasterizationSettings (same image size, SH degree
+    and scale_modifier; cameras differ).  Returns (state, color[V,3,H,W], radii[V,P] int32[, depth[V,1,H,W],
+    alpha[V,1,H,W]]).  The per-view results are bit-identical to V single-view `c_rasterize_gaussians` calls."""
+    V = len(settings)
+    if V == 0:
+        raise RuntimeError("rasterize_views: empty batch")
+    if means3D.ndimension() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    rz._require_cuda(means3D)
+    s0 = settings[0]
+    H, W = int(s0.image_height), int(s0.image_width)
+    for st in settings:
+        if int(st.image_height) != H or int(st.image_width) != W or st.sh_degree != s0.sh_degree or \
+                float(st.scale_modifier) != float(s0.scale_modifier):
+            raise RuntimeError("rasterize_views: all views of a batch must share image size, SH degree and scale_modifier")
+    device = means3D.device
+    P = means3D.size(0)
+    f32 = dict(dtype=torch.float32, device=device)
+    u8 = dict(dtype=torch.uint8, device=device)
+    state = ViewBatchState()
+    state.V, state.extras, state.binding = V, extras, binding
+
+    color = torch.empty(V, 3, H, W, **f32) if P else torch.zeros(V, 3, H, W, **f32)
+    radii = torch.empty(V, P, dtype=torch.int32, device=device)
+    depth = alpha = None
+    if extras:
+        depth = torch.empty(V, 1, H, W, **f32) if P else torch.zeros(V, 1, H, W, **f32)
+        alpha = torch.empty(V, 1, H, W, **f32) if P else torch.zeros(V, 1, H, W, **f32)
+    if P == 0:
+        state.counts = [0] * V
+        return (state, color, radii) + ((depth, alpha) if extras else ())
+
+    with torch.cuda.device(device):
+        L = _lib.lib()
+        means3D = rz._f32c(means3D, "means3D", device)
+        colors = rz._f32c(colors, "colors_precomp", device)
+        opacity = rz._f32c(opacity, "opacities", device)
+        scales = rz._f32c(scales, "scales", device)
+        rotations = rz._f32c(rotations, "rotations", device)
+        cov3D_precomp = rz._f32c(cov3D_precomp, "cov3D_precomp", device)
+        sh = rz._f32c(sh, "sh", device)
+
+        gbytes = _align(L.tgr_geom_bytes(P))
+        ibytes = _align(L.tgr_image_bytes(W, H))
+        geom = torch.empty(V, gbytes, **u8)
+        img = torch.empty(V, ibytes, **u8)
+        slots = _count_slots(device, V)
+        params = (TgrParams * V)()
+        cams = []
+        for v, st in enumerate(settings):
+            bg = rz._f32c(st.bg, "bg", device)
+            vm = rz._f32c(st.viewmatrix, "viewmatrix", device)
+            pm = rz._f32c(st.projmatrix, "projmatrix", device)
+            cp = rz._f32c(st.campos, "campos", device)
+            cams.append((bg, vm, pm, cp))
+            p = params[v]
+            rz._fill_common(p, bg, means3D, colors, opacity, scales, rotations, st.scale_modifier, cov3D_precomp, vm, pm,
+                            st.tanfovx, st.tanfovy, H, W, sh, st.sh_degree, cp, st.debug)
+            p.prefiltered = 1 if st.prefiltered else 0
+            p.extras = 1 if extras else 0
+            p.geom_buffer, p.geom_bytes = geom[v].data_ptr(), gbytes
+            p.image_buffer, p.image_bytes = img[v].data_ptr(), ibytes
+            p.out_color = color[v].data_ptr()
+            p.radii = radii[v].data_ptr()
+            if extras:
+                p.out_depth = depth[v].data_ptr()
+                p.out_alpha = alpha[v].data_ptr()
+            p.host_num_rendered = slots[v:v + 1].data_ptr()
+
+        main = torch.cuda.current_stream(device)
+        bptr = C.byref(binding) if binding is not None else None
+        check(L.tgr_forward_preprocess_batch(params, V, bptr, main.cuda_stream), "tgr_forward_preprocess_batch")
+        # the one host<->device sync of the batch (the reference has one per view, rasterizer_impl.cu:281)
+        check(L.tgr_wait_num_rendered(), "tgr_wait_num_rendered")
+        counts = [int(x) for x in slots.tolist()]
+
+        S = max(1, min(int(n_streams), V))
+        streams = _side_streams(device, S) if S > 1 else [main]
+        fork = torch.cuda.Event()
+        fork.record(main)
+        binnings = []
+        for v in range(V):
+            p = params[v]
+            binning = torch.empty(L.tgr_binning_bytes(P, counts[v], W, H), **u8)
+            binnings.append(binning)
+            p.binning_buffer, p.binning_bytes = binning.data_ptr(), binning.numel()
+            s = streams[v % S]
+            if S > 1 and v < S:
+                s.wait_event(fork)
+            check(L.tgr_forward_depth_sort(C.byref(p), s.cuda_stream), "tgr_forward_depth_sort")
+            check(L.tgr_forward_render(C.byref(p), counts[v], s.cuda_stream), "tgr_forward_render")
+        if S > 1:
+            for s in streams:
+                main.wait_stream(s)
+
+    state.params, state.counts, state.n_streams = params, counts, S
+    state.tensors = (means3D, colors, opacity, scales, rotations, cov3D_precomp, sh, cams, geom, img, binnings, radii)
+    return (state, color, radii) + ((depth, alpha) if extras else ())
+
+
+def c_rasterize_views_backward(state: ViewBatchState, dL_dout_color, dL_dout_depth=None, dL_dout_alpha=None,
+                               accumulate_into=None, out=None):
+    """Backward of a batch: dL_dout_color[V,3,H,W] (+ depth / alpha gradients [V,1,H,W]) -> the 8-tuple of
+    `_C.rasterize_gaussians_backward` (rasterize_points.cu:117-196), summed over the V views.  `out` /
+    `accumulate_into` as in `c_rasterize_gaussians_backward`."""
+    V = state.V
+    means3D, colors, opacity, scales, rotations, cov3D_precomp, sh = state.tensors[:7] if state.tensors else (None,) * 7
+    params = state.params
+    if params is None:  # P == 0
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dL_dout_color.device)
+        return z(0, 3), z(0, 3), z(0, 1), z(0, 3), z(0, 6), z(0, 0, 3), z(0, 3), z(0, 4)
+    device = means3D.device
+    P = means3D.size(0)
+    M = int(sh.size(1)) if sh.numel() != 0 else 0
+    f32 = dict(dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        L = _lib.lib()
+        dL_dout_color = rz._f32c(dL_dout_color, "dL_dout_color", device)
+        if dL_dout_color.shape[0] != V:
+            raise RuntimeError("dL_dout_color must have one image per view")
+        if dL_dout_depth is not None:
+            dL_dout_depth = rz._f32c(dL_dout_depth, "dL_dout_depth", device)
+        if dL_dout_alpha is not None:
+            dL_dout_alpha = rz._f32c(dL_dout_alpha, "dL_dout_alpha", device)
+        sh_path = M > 0 and colors.numel() == 0
+        if accumulate_into is not None or out is not None:
+            grads = accumulate_into if accumulate_into is not None else out
+        else:
+            grads = (torch.empty(P, 3, **f32), torch.empty(P, 3, **f32), torch.empty(P, 1, **f32), torch.empty(P, 3, **f32),
+                     torch.empty(P, 6, **f32), torch.empty(P, M, 3, **f32) if sh_path else torch.zeros(P, M, 3, **f32),
+                     torch.empty(P, 3, **f32), torch.empty(P, 4, **f32))
+        (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations) = grads
+        use_extras = dL_dout_depth is not None or dL_dout_alpha is not None
+        for v in range(V):
+            p = params[v]
+            p.extras = 1 if use_extras else 0
+            p.dL_dout_color = dL_dout_color[v].data_ptr()
+            p.dL_dout_depth = dL_dout_depth[v].data_ptr() if dL_dout_depth is not None else None
+            p.dL_dout_alpha = dL_dout_alpha[v].data_ptr() if dL_dout_alpha is not None else None
+        p0 = params[0]
+        p0.accumulate = 1 if accumulate_into is not None else 0
+        p0.dL_dmeans2D = rz._ptr(dL_dmeans2D)
+        p0.dL_dcolors = rz._ptr(dL_dcolors)
+        p0.dL_dopacity = rz._ptr(dL_dopacity)
+        p0.dL_dmeans3D = rz._ptr(dL_dmeans3D)
+        p0.dL_dcov3D = rz._ptr(dL_dcov3D)
+        p0.dL_dsh = rz._ptr(dL_dsh) if sh_path else None
+        p0.dL_dscales = rz._ptr(dL_dscales)
+        p0.dL_drotations = rz._ptr(dL_drotations)
+
+        main = torch.cuda.current_stream(device)
+        S = state.n_streams
+        streams = _side_streams(device, S) if S > 1 else [main]
+        if S > 1:
+            fork = torch.cuda.Event()
+            fork.record(main)
+        for v in range(V):
+            s = streams[v % S]
+            if S > 1 and v < S:
+                s.wait_event(fork)
+            check(L.tgr_backward_blend(C.byref(params[v]), state.counts[v], s.cuda_stream), "tgr_backward_blend")
+        if S > 1:
+            for s in streams:
+                main.wait_stream(s)
+        caps = (C.c_uint64 * V)(*state.counts)
+        bptr = C.byref(state.binding) if state.binding is not None else None
+        check(L.tgr_backward_preprocess_batch(params, caps, V, bptr, main.cuda_stream), "tgr_backward_preprocess_batch")
+        state.keep_bwd = (dL_dout_color, dL_dout_depth, dL_dout_alpha)
+    return grads
+
+
+class _RasterizeViews(torch.autograd.Function):
+    """Batched counterpart of `_RasterizeGaussians` (diff_gaussian_rasterization/__init__.py:48-155): same
+    tensor arguments, a sequence of settings instead of one."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, settings,
+                extras, n_streams):
+        res = c_rasterize_views(settings, means3D, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, sh,
+                                extras=extras, n_streams=n_streams)
+        ctx.state = res[0]
+        ctx.extras = extras
+        ctx.mark_non_differentiable(res[2])
+        return tuple(res[1:])
+
+    @staticmethod
+    def backward(ctx, grad_color, _grad_radii, grad_depth=None, grad_alpha=None):
+        kw = dict(dL_dout_depth=grad_depth, dL_dout_alpha=grad_alpha) if ctx.extras else {}
+        (g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rots) = c_rasterize_views_backward(
+            ctx.state, grad_color, **kw)
+        ctx.state = None
+        return (g_means3D, g_means2D, g_sh, g_colors, g_opac, g_scales, g_rots, g_cov3D, None, None, None)
+
+
+def rasterize_views(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, settings,
+                    extras=False, n_streams=4):
+    return _RasterizeViews.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                                 list(settings), extras, n_streams)
+
+
+class MultiViewRasterizer(torch.nn.Module):
+    """`GaussianRasterizer` for a batch of cameras: forward(...) takes the same keyword arguments
+    (diff_gaussian_rasterization/__init__.py:186-220) and returns (color[V,3,H,W], radii[V,P]) — plus
+    depth[V,1,H,W], alpha[V,1,H,W] with extra_outputs=True."""
+
+    def __init__(self, raster_settings: Sequence, extra_outputs: bool = False, n_streams: int = 4):
+        super().__init__()
+        self.raster_settings = list(raster_settings)
+        self.extra_outputs = extra_outputs
+        self.n_streams = n_streams
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        e = torch.Tensor([])
+        return rasterize_views(means3D, means2D, e if shs is None else shs, e if colors_precomp is None else colors_precomp,
+                               opacities, e if scales is None else scales, e if rotations is None else rotations,
+                               e if cov3D_precomp is None else cov3D_precomp, self.raster_settings,
+                               self.extra_outputs, self.n_streams)

@@ -98,3 +98,34 @@ def render_batch_fwd_bwd(inp: Dict[str, torch.Tensor], cams: Sequence[Dict[str, 
         if keep_images:
             images.append(color)
     return images
+
+
+def settings_from_cam(cam: Dict[str, object], degree: int):
+    """Camera dict (scene.orbit_camera) -> the reference's GaussianRasterizationSettings."""
+    from .rasterizer import GaussianRasterizationSettings
+    return GaussianRasterizationSettings(
+        image_height=int(cam["image_height"]), image_width=int(cam["image_width"]), tanfovx=cam["tanfovx"],
+        tanfovy=cam["tanfovy"], bg=cam["bg"], scale_modifier=cam.get("scale_modifier", 1.0),
+        viewmatrix=cam["viewmatrix"], projmatrix=cam["projmatrix"], sh_degree=degree, campos=cam["campos"],
+        prefiltered=False, debug=False)
+
+
+def render_views_fwd_bwd(inp: Dict[str, torch.Tensor], cams: Sequence[Dict[str, object]], degree: int, upstream,
+                         bucket: GradBucket, extras: bool = False, n_streams: int = 4, accumulate: bool = False):
+    """Batched forward + backward of this rank's views (youreditableavatar_b200.multiview): one preprocess launch
+    for all views, per-view binning / blending on `n_streams` streams, one backward-preprocess launch that writes
+    the summed gradients into `bucket` (overwrite, or add with accumulate=True).
+    `upstream(color[V,3,H,W], depth[V,1,H,W] | None, alpha | None)` -> (dL_dcolor[V,3,H,W], dL_ddepth | None,
+    dL_dalpha | None).  Returns the rendered images."""
+    from . import multiview as mv
+    e = torch.Tensor([])
+    g = lambda k: inp[k] if inp.get(k) is not None else e
+    settings = [settings_from_cam(c, degree) for c in cams]
+    res = mv.c_rasterize_views(settings, g("means3D"), g("colors_precomp"), g("opacities"), g("scales"), g("rotations"),
+                               g("cov3D_precomp"), g("shs"), extras=extras, n_streams=n_streams)
+    state, color = res[0], res[1]
+    depth, alpha = (res[3], res[4]) if extras else (None, None)
+    dLc, dLd, dLa = upstream(color, depth, alpha)
+    kw = dict(accumulate_into=bucket.views) if accumulate else dict(out=bucket.views)
+    mv.c_rasterize_views_backward(state, dLc, dL_dout_depth=dLd, dL_dout_alpha=dLa, **kw)
+    return color
