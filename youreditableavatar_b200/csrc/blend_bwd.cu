@@ -54,11 +54,11 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint2* __re
                                                                const float* __restrict__ dL_ddepth,
                                                                const float* __restrict__ dL_dalpha_img,
                                                                float* __restrict__ grad_acc) {
-  __shared__ uint32_t s_id[BL_STAGES][BL_BATCH];
-  __shared__ __align__(16) float4 s_xy[BL_STAGES][BL_BATCH];
-  __shared__ __align__(16) float4 s_co[BL_STAGES][BL_BATCH];
-  __shared__ __align__(16) float4 s_cd[BL_STAGES][BL_BATCH];
-  __shared__ uint32_t s_ball[BL_STAGES][8][BL_CHUNKS];
+  __shared__ uint32_t s_id[BL_STAGES][BL_BATCH + 1];
+  __shared__ __align__(16) float4 s_xy[BL_STAGES][BL_BATCH + 1];   // +1: the PAD_ENTRY dummy record
+  __shared__ __align__(16) float4 s_co[BL_STAGES][BL_BATCH + 1];
+  __shared__ __align__(16) float4 s_cd[BL_STAGES][BL_BATCH + 1];
+  __shared__ __align__(4) uint8_t s_list[8][LIST_BYTES];            // per consumer warp: candidates of the current batch
   __shared__ __align__(8) uint64_t s_full[BL_STAGES], s_empty[BL_STAGES];
 
   // ---- work unit = (tile, segment): list positions [seg*SEG, min((seg+1)*SEG, total)) of one tile -------
@@ -82,30 +82,17 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint2* __re
       mbar_init(&s_empty[s], 8);
     }
   }
+  if (tid < BL_STAGES) {
+    init_pad_record(s_xy[tid], s_co[tid], s_cd[tid]);
+    s_id[tid][PAD_ENTRY] = 0;
+  }
   __syncthreads();
 
   if (warp == 8) {
     // ======================= PRODUCER: back-to-front gather of this segment =======================
-    const float tile_x0 = (float)(tile_bx * TILE), tile_y0 = (float)(tile_by * TILE);
-    const uint32_t* list = point_list + range.x + seg_lo;   // segment-local list; entry e <-> position count-1-e
-    uint32_t ids[BL_CHUNKS];
-    prod_load_ids(list, count, 0, true, lane, ids);
-    prod_issue(ids, xy_ext, conic_opacity, rgb_depth, s_xy[0], s_co[0], s_cd[0], s_id[0], lane);
-    prod_load_ids(list, count, BL_BATCH, true, lane, ids);
-    for (int b = 0; b < rounds; ++b) {
-      const int stage = b % BL_STAGES;
-      if (b + 1 < rounds) {  // put the gathers of batch b+1 in flight, prefetch the ids of batch b+2
-        const int nstage = (b + 1) % BL_STAGES;
-        if (b + 1 >= BL_STAGES) mbar_wait(&s_empty[nstage], (((b + 1) / BL_STAGES) - 1) & 1);
-        prod_issue(ids, xy_ext, conic_opacity, rgb_depth, s_xy[nstage], s_co[nstage], s_cd[nstage], s_id[nstage], lane);
-        prod_load_ids(list, count, (b + 2) * BL_BATCH, true, lane, ids);
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
-      }
-      prod_classify(count, b * BL_BATCH, s_xy[stage], s_ball[stage], tile_x0, tile_y0, lane);
-      mbar_arrive(&s_full[stage]);
-    }
+    // segment-local list; batch entry e <-> list position count-1-e
+    producer_loop<BL_STAGES, true, true>(point_list + range.x + seg_lo, count, rounds, xy_ext, conic_opacity, rgb_depth,
+                                            s_xy, s_co, s_cd, s_id, s_full, s_empty, lane, [](int) { return false; });
     return;
   }
 
@@ -116,6 +103,8 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint2* __re
   const uint32_t pix_id = (uint32_t)W * py + px;
   const float2 pixf = {(float)px, (float)py};
   const int pix_in_tile = warp * 32 + lane;
+  const float bx0 = (float)(tile_bx * TILE + (warp & 1) * 8), bx1 = bx0 + 7.f;   // this warp's pixel block
+  const float by0 = (float)(tile_by * TILE + (warp >> 1) * 4), by1 = by0 + 3.f;
 
   const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
   const int warp_last = __reduce_max_sync(0xffffffffu, last_contributor);
@@ -162,26 +151,24 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint2* __re
     const int batch_first_pos = seg_hi - 1 - b * BL_BATCH;  // list position of batch entry 0 (descending)
     mbar_wait(&s_full[stage], (b / BL_STAGES) & 1);
     if (batch_first_pos - (BL_BATCH - 1) < warp_last) {  // else: whole batch lies behind this block's last contributor
+      // entries at list positions >= warp_last lie behind this block's last contributor: batch entry e sits at
+      // position batch_first_pos - e, so only e > batch_first_pos - warp_last can matter
+      const int ncand = cons_classify(max(0, batch_first_pos - warp_last + 1), min(BL_BATCH, count - b * BL_BATCH),
+                                      s_xy[stage], s_list[warp], bx0, bx1, by0, by1, lane);
+      const uint16_t* cand = reinterpret_cast<const uint16_t*>(s_list[warp]);
+      // Candidates are taken BG at a time (one 16-bit load = two batch-local indices) so the loads / power /
+      // exp of one overlap the serial transmittance + behind-colour recurrences of the other.
+      {
 #pragma unroll 1
-      for (int c = 0; c < BL_CHUNKS; ++c) {
-        uint32_t m = s_ball[stage][warp][c];
-        // Candidates are taken BG at a time so the loads / power / exp of one overlap the serial
-        // transmittance + behind-colour recurrences and the butterfly reduction of the other.
-        while (m) {
+        for (int i = 0; i < ncand; i += BG) {
+          const uint32_t packed = cand[i >> 1];
           int j[BG];
-          bool has[BG], valid[BG];
+          bool valid[BG];
           float G[BG], alpha[BG], rinv[BG];
           float2 d[BG];
           float4 con_o[BG], cd[BG];
-          int jmax = 0;
 #pragma unroll
-          for (int k = 0; k < BG; ++k) {
-            has[k] = m != 0;
-            j[k] = has[k] ? (c * 32 + __ffs(m) - 1) : j[0];
-            m &= m - 1;
-            jmax = max(jmax, j[k]);
-          }
-          if (batch_first_pos - jmax >= warp_last) continue;  // all of them lie behind this block's last contributor
+          for (int k = 0; k < BG; ++k) j[k] = (int)((packed >> (8 * k)) & 0xffu);
 #pragma unroll
           for (int k = 0; k < BG; ++k) {
             const int pos = batch_first_pos - j[k];  // 0-based list position
@@ -194,7 +181,7 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint2* __re
             G[k] = expf(power);
             alpha[k] = min(0.99f, con_o[k].w * G[k]);
             rinv[k] = __frcp_rn(1.f - alpha[k]);
-            valid[k] = has[k] && (pos < last_contributor) && (power <= 0.0f) && (alpha[k] >= 1.0f / 255.0f);
+            valid[k] = (pos < last_contributor) && (power <= 0.0f) && (alpha[k] >= 1.0f / 255.0f);
           }
 #pragma unroll
           for (int k = 0; k < BG; ++k) {

@@ -26,7 +26,6 @@ namespace tgr {
 
 constexpr int BL_STAGES = 4;  // shared-memory ring depth (how far consumers may drift apart)
 
-constexpr int FG = 4;  // candidates evaluated together by a consumer warp
 
 template <bool EXTRAS>
 __global__ void __launch_bounds__(BL_THREADS) blend_fwd_kernel(const uint32_t* __restrict__ order, uint32_t* __restrict__ queue_counters,
@@ -44,10 +43,10 @@ __global__ void __launch_bounds__(BL_THREADS) blend_fwd_kernel(const uint32_t* _
                                                                const uint32_t* __restrict__ seg_base,
                                                                float4* __restrict__ ckpt, float* __restrict__ ckpt_z,
                                                                float4* __restrict__ final_state, float* __restrict__ final_z) {
-  __shared__ __align__(16) float4 s_xy[BL_STAGES][BL_BATCH];   // x, y, hx, hy
-  __shared__ __align__(16) float4 s_co[BL_STAGES][BL_BATCH];   // conic xx, xy, yy, opacity
-  __shared__ __align__(16) float4 s_cd[BL_STAGES][BL_BATCH];   // r, g, b, depth
-  __shared__ uint32_t s_ball[BL_STAGES][8][BL_CHUNKS];         // [stage][consumer block][chunk of 32]
+  __shared__ __align__(16) float4 s_xy[BL_STAGES][BL_BATCH + 1];   // x, y, hx, hy   (+1: the PAD_ENTRY dummy)
+  __shared__ __align__(16) float4 s_co[BL_STAGES][BL_BATCH + 1];   // conic xx, xy, yy, opacity
+  __shared__ __align__(16) float4 s_cd[BL_STAGES][BL_BATCH + 1];   // r, g, b, depth
+  __shared__ __align__(4) uint8_t s_list[8][LIST_BYTES];            // per consumer warp: candidates of the current batch
   __shared__ __align__(8) uint64_t s_full[BL_STAGES], s_empty[BL_STAGES];
   __shared__ uint32_t s_stop[BL_STAGES];
   __shared__ uint32_t s_done_warps;
@@ -76,39 +75,18 @@ __global__ void __launch_bounds__(BL_THREADS) blend_fwd_kernel(const uint32_t* _
     }
     s_done_warps = 0;
   }
+  if (tid < BL_STAGES) init_pad_record(s_xy[tid], s_co[tid], s_cd[tid]);
   __syncthreads();
 
   if (warp == 8) {
-    // ======================= PRODUCER =======================
-    const float tile_x0 = (float)(tile_bx * TILE), tile_y0 = (float)(tile_by * TILE);
-    const uint32_t* list = point_list + range.x;
-    uint32_t ids[BL_CHUNKS];
-    if (rounds > 0) {
-      prod_load_ids(list, total, 0, false, lane, ids);
-      prod_issue(ids, xy_ext, conic_opacity, rgb_depth, s_xy[0], s_co[0], s_cd[0], nullptr, lane);
-      prod_load_ids(list, total, BL_BATCH, false, lane, ids);
-    }
-    for (int b = 0; b < rounds; ++b) {
-      const int stage = b % BL_STAGES;
-      if (*(volatile uint32_t*)&s_done_warps == 8u) {  // every pixel of the tile has terminated
-        cp_async_wait<0>();
-        if (lane == 0) s_stop[stage] = 1;
-        __syncwarp();
-        mbar_arrive(&s_full[stage]);
-        break;
-      }
-      if (b + 1 < rounds) {  // put the gathers of batch b+1 in flight, prefetch the ids of batch b+2
-        const int nstage = (b + 1) % BL_STAGES;
-        if (b + 1 >= BL_STAGES) mbar_wait(&s_empty[nstage], (((b + 1) / BL_STAGES) - 1) & 1);
-        prod_issue(ids, xy_ext, conic_opacity, rgb_depth, s_xy[nstage], s_co[nstage], s_cd[nstage], nullptr, lane);
-        prod_load_ids(list, total, (b + 2) * BL_BATCH, false, lane, ids);
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
-      }
-      prod_classify(total, b * BL_BATCH, s_xy[stage], s_ball[stage], tile_x0, tile_y0, lane);
-      mbar_arrive(&s_full[stage]);
-    }
+    // ======================= PRODUCER: a pure data mover =======================
+    auto stop = [&](int stage) {
+      if (*(volatile uint32_t*)&s_done_warps != 8u) return false;  // some pixel of the tile is still alive
+      if (lane == 0) s_stop[stage] = 1;
+      return true;
+    };
+    producer_loop<BL_STAGES, false, false>(point_list + range.x, total, rounds, xy_ext, conic_opacity, rgb_depth, s_xy,
+                                              s_co, s_cd, nullptr, s_full, s_empty, lane, stop);
     return;
   }
 
@@ -118,6 +96,8 @@ __global__ void __launch_bounds__(BL_THREADS) blend_fwd_kernel(const uint32_t* _
   const bool inside = px < (uint32_t)W && py < (uint32_t)H;
   const uint32_t pix_id = (uint32_t)W * py + px;
   const float2 pixf = {(float)px, (float)py};
+  const float bx0 = (float)(tile_bx * TILE + (warp & 1) * 8), bx1 = bx0 + 7.f;   // this warp's pixel block
+  const float by0 = (float)(tile_by * TILE + (warp >> 1) * 4), by1 = by0 + 3.f;
 
   bool done = !inside;
   bool warp_done = false;
@@ -145,49 +125,43 @@ __global__ void __launch_bounds__(BL_THREADS) blend_fwd_kernel(const uint32_t* _
     if (*(volatile uint32_t*)&s_stop[stage]) break;
     if (!warp_done) {
       const uint32_t base_pos = (uint32_t)(b * BL_BATCH);
+      const int ncand = cons_classify(0, min(BL_BATCH, total - b * BL_BATCH), s_xy[stage], s_list[warp], bx0, bx1, by0, by1, lane);
+      const uint32_t* cand = reinterpret_cast<const uint32_t*>(s_list[warp]);
+      // Candidates are taken CAND_GROUP at a time (one 32-bit load = four batch-local indices): their loads,
+      // power and exp are independent (ILP), only the transmittance update is a serial chain.  Profiling showed
+      // the kernel bound by the single-warp latency of the heaviest tile, not by SM throughput.
 #pragma unroll 1
-      for (int c = 0; c < BL_CHUNKS; ++c) {
-        uint32_t m = s_ball[stage][warp][c];
-        // Candidates are taken FG at a time: their loads, power and exp are independent (ILP), only the
-        // transmittance update is a serial chain.  Profiling showed the kernel bound by the single-warp
-        // latency of the heaviest tile, not by SM throughput.
-        while (m) {
-          int j[FG];
-          bool ok[FG];
+      for (int i = 0; i < ncand; i += CAND_GROUP) {
+        const uint32_t packed = cand[i >> 2];
+        int j[CAND_GROUP];
+        bool ok[CAND_GROUP];
+        float alpha[CAND_GROUP];
+        float4 cd[CAND_GROUP];
 #pragma unroll
-          for (int k = 0; k < FG; ++k) {
-            ok[k] = m != 0;
-            j[k] = ok[k] ? (c * 32 + __ffs(m) - 1) : j[0];
-            m &= m - 1;
-          }
-          float alpha[FG];
-          float4 cd[FG];
+        for (int k = 0; k < CAND_GROUP; ++k) {
+          j[k] = (int)((packed >> (8 * k)) & 0xffu);
+          const float4 g = s_xy[stage][j[k]];
+          const float4 con_o = s_co[stage][j[k]];
+          cd[k] = s_cd[stage][j[k]];
+          const float2 d = {g.x - pixf.x, g.y - pixf.y};
+          const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
+          alpha[k] = min(0.99f, con_o.w * expf(power));
+          ok[k] = (power <= 0.0f) && (alpha[k] >= 1.0f / 255.0f);
+        }
 #pragma unroll
-          for (int k = 0; k < FG; ++k) {
-            const float4 g = s_xy[stage][j[k]];
-            const float4 con_o = s_co[stage][j[k]];
-            cd[k] = s_cd[stage][j[k]];
-            const float2 d = {g.x - pixf.x, g.y - pixf.y};
-            const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
-            alpha[k] = min(0.99f, con_o.w * expf(power));
-            ok[k] = ok[k] && (power <= 0.0f) && (alpha[k] >= 1.0f / 255.0f);
+        for (int k = 0; k < CAND_GROUP; ++k) {
+          const float test_T = T * (1 - alpha[k]);
+          const bool act = ok[k] && !done;
+          const bool term = act && (test_T < 0.0001f);
+          done = done || term;
+          if (act && !term) {
+            C[0] += cd[k].x * alpha[k] * T;
+            C[1] += cd[k].y * alpha[k] * T;
+            C[2] += cd[k].z * alpha[k] * T;
+            if (EXTRAS) Dz += cd[k].w * alpha[k] * T;
+            T = test_T;
+            last_contributor = base_pos + j[k] + 1;
           }
-#pragma unroll
-          for (int k = 0; k < FG; ++k) {
-            const float test_T = T * (1 - alpha[k]);
-            const bool act = ok[k] && !done;
-            const bool term = act && (test_T < 0.0001f);
-            done = done || term;
-            if (act && !term) {
-              C[0] += cd[k].x * alpha[k] * T;
-              C[1] += cd[k].y * alpha[k] * T;
-              C[2] += cd[k].z * alpha[k] * T;
-              if (EXTRAS) Dz += cd[k].w * alpha[k] * T;
-              T = test_T;
-              last_contributor = base_pos + j[k] + 1;
-            }
-          }
-          if (__all_sync(0xffffffffu, done)) break;
         }
         if (__all_sync(0xffffffffu, done)) break;
       }

@@ -8,7 +8,6 @@ namespace tgr {
 constexpr int BL_BATCH = 128;                // list entries per ring stage
 constexpr int BL_CHUNKS = BL_BATCH / 32;     // 32-entry chunks (one ballot word each)
 constexpr int BL_THREADS = 9 * 32;           // 8 consumer warps + 1 producer warp
-static_assert(8 * BL_CHUNKS == 32, "produce_batch maps one (block, chunk) ballot word to each producer lane");
 
 // ---- SM-affine work queues ------------------------------------------------------------------------------
 // Tiles are sorted heaviest-first (tile_order_kernel).  All non-empty tiles of an avatar view fit in the first
@@ -67,6 +66,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
 }
+// Blocks until the phase with the given parity completes.  The suspend-time hint lets the hardware park the
+// warp instead of returning after a few dozen cycles: with the default limit ncu showed the consumers of cheap
+// pixel blocks re-issuing try_wait ~130 times per wait — a third of all instructions the blend kernels issued.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
   uint32_t ok;
@@ -74,11 +76,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}\n"
         : "=r"(ok)
-        : "r"(a), "r"(parity)
+        : "r"(a), "r"(parity), "r"(0x989680u)
         : "memory");
   } while (!ok);
 }
@@ -95,24 +97,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// 8-bit mask of the warp blocks (bit = 2*row4 + col8) that the footprint [x-hx,x+hx]x[y-hy,y+hy] reaches.
-// Pixel centres are integers (forward.cu:282), so pixel p is inside iff x-hx <= p <= x+hx.
-__device__ __forceinline__ uint32_t block_mask(float x, float y, float hx, float hy, float tile_x0, float tile_y0) {
-  if (!(hx >= 0.f)) return 0u;  // can never reach alpha >= 1/255 (or NaN extents)
-  const float fx0 = ceilf(x - hx) - tile_x0, fx1 = floorf(x + hx) - tile_x0;
-  const float fy0 = ceilf(y - hy) - tile_y0, fy1 = floorf(y + hy) - tile_y0;
-  if (fx1 < 0.f || fy1 < 0.f || fx0 > 15.f || fy0 > 15.f || fx0 > fx1 || fy0 > fy1) return 0u;
-  const int x0 = (int)fmaxf(fx0, 0.f), x1 = (int)fminf(fx1, 15.f);
-  const int y0 = (int)fmaxf(fy0, 0.f), y1 = (int)fminf(fy1, 15.f);
-  const uint32_t colm = ((x0 < 8) ? 1u : 0u) | ((x1 >= 8) ? 2u : 0u);
-  const int r0 = y0 >> 2, r1 = y1 >> 2;
-  uint32_t m = 0;
-#pragma unroll
-  for (int r = 0; r < 4; ++r)
-    if (r >= r0 && r <= r1) m |= colm << (2 * r);
-  return m;
-}
-
 // ---- producer warp ------------------------------------------------------------------------------------
 // Batch entry e maps to list position e (forward) or total-1-e (reverse, for the back-to-front replay).
 // The producer is software-pipelined: ids of batch b+2 are prefetched into registers and the 16-byte
@@ -127,8 +111,15 @@ __device__ __forceinline__ void prod_load_ids(const uint32_t* __restrict__ list,
   }
 }
 
-// Records go global -> shared with cp.async (no register staging); one commit group per batch.
-__device__ __forceinline__ void prod_issue(const uint32_t (&ids)[BL_CHUNKS], const float4* __restrict__ xy_ext,
+// Records go global -> shared with cp.async (no register staging).  The backward also needs the Gaussian id of
+// every entry next to its record; it travels as a 4-byte cp.async from the list itself so that EVERYTHING a
+// consumer reads is covered by the asynchronous arrive on full[] (producer_loop).
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem)
+               : "memory");
+}
+__device__ __forceinline__ void prod_issue(const uint32_t (&ids)[BL_CHUNKS], const uint32_t* __restrict__ list, int total,
+                                           int first, bool reverse, const float4* __restrict__ xy_ext,
                                            const float4* __restrict__ conic_opacity,
                                            const float4* __restrict__ rgb_depth, float4* s_xy, float4* s_co,
                                            float4* s_cd, uint32_t* s_id, int lane) {
@@ -139,30 +130,97 @@ __device__ __forceinline__ void prod_issue(const uint32_t (&ids)[BL_CHUNKS], con
       cp_async16(&s_xy[j], &xy_ext[ids[c]]);
       cp_async16(&s_co[j], &conic_opacity[ids[c]]);
       cp_async16(&s_cd[j], &rgb_depth[ids[c]]);
-      if (s_id) s_id[j] = ids[c];
+      if (s_id) {
+        const int e = first + j;
+        cp_async4(&s_id[j], list + (reverse ? (total - 1 - e) : e));
+      }
     }
   }
-  cp_async_commit();
 }
 
-// Classifies the landed footprints of one batch against the eight warp blocks: s_ball[block][chunk].
-__device__ __forceinline__ void prod_classify(int total, int first, const float4* s_xy, uint32_t (*s_ball)[BL_CHUNKS],
-                                              float tile_x0, float tile_y0, int lane) {
-  uint32_t keep = 0;
+// ---- consumer-side classification -------------------------------------------------------------------
+// Every consumer warp tests the landed footprints of a batch against ITS OWN 8x4 pixel block and compacts the
+// hits into an ordered list of batch-local indices (bytes), padded to a multiple of CAND_GROUP with PAD_ENTRY.
+// PAD_ENTRY indexes a dummy record with opacity 0 (it fails the alpha >= 1/255 test), so the evaluation loop
+// walks full groups without validity bookkeeping: one 32-bit shared load yields four candidates.
+// History (ncu-driven): v1 had the producer warp classify all eight blocks (8 ballots per 32 entries) — it became
+// the serial bottleneck of the ring, a third of all issued instructions were consumers polling full[]; v2 moves
+// the test to the eight consumers (one ballot per 32 entries each, in parallel) and leaves the producer a pure
+// data mover (ids -> cp.async gathers), like a TMA producer.
+// The block test is conservative: pixel centres are integers (forward.cu:282), pixel p can reach alpha >= 1/255
+// only if x-hx <= p <= x+hx, so a block [x0,x1] is skipped when x-hx > x1 or x+hx < x0 (same in y).
+constexpr int CAND_GROUP = 4;
+constexpr int PAD_ENTRY = BL_BATCH;                 // dummy record slot; record arrays hold BL_BATCH + 1 entries
+constexpr int LIST_BYTES = BL_BATCH + CAND_GROUP;   // per consumer warp
+
+// first_excluded: entries >= this batch-local index are ignored (ragged last batch; in the backward also the
+// entries behind the block's last contributor, see blend_bwd.cu).  first_included: entries below are ignored.
+__device__ __forceinline__ int cons_classify(int first_included, int first_excluded, const float4* s_xy, uint8_t* my_list,
+                                             float bx0, float bx1, float by0, float by1, int lane) {
+  uint32_t cnt = 0;
+  const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
   for (int c = 0; c < BL_CHUNKS; ++c) {
-    uint32_t mm = 0;
-    if (first + c * 32 + lane < total) {
-      const float4 g = s_xy[c * 32 + lane];
-      mm = block_mask(g.x, g.y, g.z, g.w, tile_x0, tile_y0);
+    const int e = c * 32 + lane;
+    bool hit = false;
+    if (e >= first_included && e < first_excluded) {
+      const float4 g = s_xy[e];
+      hit = (g.z >= 0.f) && (g.x - g.z <= bx1) && (g.x + g.z >= bx0) && (g.y - g.w <= by1) && (g.y + g.w >= by0);
     }
-#pragma unroll
-    for (int b = 0; b < 8; ++b) {
-      const uint32_t bal = __ballot_sync(0xffffffffu, (mm >> b) & 1u);
-      if (lane == b * BL_CHUNKS + c) keep = bal;  // lane (b,c) holds the word for block b, chunk c
-    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+    if (hit) my_list[cnt + __popc(bal & lt)] = (uint8_t)e;
+    cnt += __popc(bal);
   }
-  if (lane < 8 * BL_CHUNKS) s_ball[lane / BL_CHUNKS][lane % BL_CHUNKS] = keep;
+  const uint32_t padded = (cnt + CAND_GROUP - 1) & ~(uint32_t)(CAND_GROUP - 1);
+  if (cnt + lane < padded) my_list[cnt + lane] = (uint8_t)PAD_ENTRY;
+  __syncwarp();
+  return (int)padded;
+}
+
+// ---- producer loop -----------------------------------------------------------------------------------
+// The producer never waits for its own gathers: after issuing a batch every lane executes
+// cp.async.mbarrier.arrive.noinc on full[slot], so the hardware arrives on the barrier when that lane's copies
+// have landed (the Ampere-era equivalent of a TMA complete_tx).  The only thing the producer blocks on is
+// empty[slot] — the back-pressure of the ring — so up to STAGES batches of gathers are in flight and a landed
+// batch is never held back by the producer being busy elsewhere.  full[] is initialised with 32 expected arrivals.
+// `stop` (forward only) is polled once per batch: when it returns true the producer hands over a stop marker
+// instead of data and leaves.
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+
+template <int STAGES, bool REVERSE, bool WITH_IDS, typename StopFn>
+__device__ __forceinline__ void producer_loop(const uint32_t* __restrict__ list, int total, int rounds,
+                                              const float4* __restrict__ xy_ext, const float4* __restrict__ conic_opacity,
+                                              const float4* __restrict__ rgb_depth, float4 (*s_xy)[BL_BATCH + 1],
+                                              float4 (*s_co)[BL_BATCH + 1], float4 (*s_cd)[BL_BATCH + 1],
+                                              uint32_t (*s_id)[BL_BATCH + 1], uint64_t* s_full, uint64_t* s_empty,
+                                              int lane, StopFn stop) {
+  uint32_t ids[BL_CHUNKS];
+  prod_load_ids(list, total, 0, REVERSE, lane, ids);
+  for (int k = 0; k < rounds; ++k) {
+    const int st = k % STAGES;
+    if (k >= STAGES) mbar_wait(&s_empty[st], ((k / STAGES) - 1) & 1);
+    if (stop(st)) {
+      cp_async_wait<0>();
+      __syncwarp();
+      mbar_arrive(&s_full[st]);
+      return;
+    }
+    prod_issue(ids, list, total, k * BL_BATCH, REVERSE, xy_ext, conic_opacity, rgb_depth, s_xy[st], s_co[st], s_cd[st],
+               WITH_IDS ? s_id[st] : nullptr, lane);
+    cp_async_mbar_arrive(&s_full[st]);
+    prod_load_ids(list, total, (k + 1) * BL_BATCH, REVERSE, lane, ids);
+  }
+  cp_async_wait<0>();  // do not leave with copies in flight
+}
+
+// The dummy record PAD_ENTRY points at (written once per CTA, for every ring stage).
+__device__ __forceinline__ void init_pad_record(float4* s_xy_stage, float4* s_co_stage, float4* s_cd_stage) {
+  s_xy_stage[PAD_ENTRY] = make_float4(0.f, 0.f, 0.f, 0.f);
+  s_co_stage[PAD_ENTRY] = make_float4(0.f, 0.f, 0.f, 0.f);   // opacity 0 -> alpha 0 -> never blended
+  s_cd_stage[PAD_ENTRY] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 }  // namespace tgr
