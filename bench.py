@@ -5,8 +5,11 @@
   (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...)
 
 A *step* = every rank renders V (default 8) different orbit views of the C3 scene — 1 M mesh-bound Gaussians,
-1024x1024, SH degree 3, forward + backward with the depth/alpha extras — accumulating the per-Gaussian
-gradients in one flat buffer, then (N > 1) all-reduces that buffer once.  Prints ONE JSON line on rank 0.
+1024x1024, SH degree 3, forward + backward with the depth/alpha extras — summing the per-Gaussian gradients of
+its views in one flat buffer, then (N > 1) all-reduces that buffer once.  Ours renders the V views as ONE
+multi-view batch (youreditableavatar_b200.multiview: one preprocess / backward-preprocess launch per batch, the
+per-view stages on `--streams` CUDA streams); the reference arm has no such call and loops over views.
+Prints ONE JSON line on rank 0.
 
   value   views/s over all ranks, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e     same metric through the public operator API with HOST buffers: every view's camera + upstream
@@ -43,6 +46,9 @@ def parse():
     ap.add_argument("--config", default="C3")
     ap.add_argument("--views-per-step", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the per-view stages of a batch rotate over")
+    ap.add_argument("--per-view-api", action="store_true",
+                    help="ours: loop over the single-view drop-in calls instead of the multi-view batch")
     return ap.parse_args()
 
 
@@ -204,8 +210,114 @@ class HostFeeder:
         torch.cuda.current_stream().wait_stream(self.s_out)
 
 
+class BatchFeeder:
+    """Host<->device traffic of the e2e leg for the multi-view batch, double-buffered: while step k renders, the
+    cameras and upstream-gradient images of step k+1 are copied from pinned host memory on a side stream (every
+    step consumes its own fresh copy); the rendered images go back to pinned memory on another stream while the
+    backward runs."""
+
+    def __init__(self, host_cams, host_ups, out_pinned):
+        self.cams, self.ups, self.out = host_cams, host_ups, out_pinned   # ups: 3 stacked pinned tensors
+        self.s_in, self.s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        self.pending = None
+        self.keep = []
+        # all cameras of the batch travel as ONE pinned block [V, 38] = view 16 | proj 16 | campos 3 | bg 3
+        self.cam_pack = torch.stack([torch.cat([c["viewmatrix"].flatten(), c["projmatrix"].flatten(),
+                                                c["campos"].flatten(), c["bg"].flatten()]) for c in host_cams]).pin_memory()
+        self.loss_pinned = torch.zeros(2, 1).pin_memory()   # gradient checksum of step k lands here asynchronously
+        self.loss_events = [None, None]
+        self.k = 0
+
+    def _issue(self):
+        with torch.cuda.stream(self.s_in):
+            pack = self.cam_pack.cuda(non_blocking=True)
+            cams = []
+            for v, c in enumerate(self.cams):
+                d = dict(c)
+                d["viewmatrix"], d["projmatrix"] = pack[v, 0:16].view(4, 4), pack[v, 16:32].view(4, 4)
+                d["campos"], d["bg"] = pack[v, 32:35], pack[v, 35:38]
+                cams.append(d)
+            ups = tuple(t.cuda(non_blocking=True) for t in self.ups)
+            ev = torch.cuda.Event(); ev.record(self.s_in)
+        return cams, ups, ev
+
+    def begin_step(self):
+        if self.pending is None:
+            self.pending = self._issue()
+        self.cur = self.pending
+        # inputs of the NEXT step start streaming now; their buffers must not be recycled under this step's kernels
+        self.s_in.wait_stream(torch.cuda.current_stream())
+        self.pending = self._issue()
+        torch.cuda.current_stream().wait_event(self.cur[2])
+        self.keep = [self.cur]
+        return self.cur[0]
+
+    def images_out(self, color, view_events):
+        # view v goes back as soon as ITS forward is done, while the other views still render
+        with torch.cuda.stream(self.s_out):
+            for v, ev in enumerate(view_events):
+                self.s_out.wait_event(ev)
+                self.out[v].copy_(color[v], non_blocking=True)
+        self.keep.append(color)
+
+    def upstream(self):
+        return self.cur[1]
+
+    def end_step(self, result):
+        """Reads the step's result back: an asynchronous copy into pinned memory every step; the host consumes the
+        value one step later (so it never stalls the GPU), and waits for the last one in drain()."""
+        torch.cuda.current_stream().wait_stream(self.s_out)
+        slot = self.k & 1
+        self.loss_pinned[slot].copy_(result, non_blocking=True)
+        ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream())
+        self.loss_events[slot] = ev
+        self.k += 1
+        prev = self.loss_events[slot ^ 1]
+        if prev is not None:
+            prev.synchronize()
+            return float(self.loss_pinned[slot ^ 1])
+        return None
+
+    def drain(self):
+        for ev in self.loss_events:
+            if ev is not None:
+                ev.synchronize()
+        return float(self.loss_pinned[(self.k - 1) & 1]) if self.k else None
+
+
 class OursRunner:
+    """Multi-view batch through youreditableavatar_b200.parallel.render_views_fwd_bwd."""
     name = "ours"
+    n_up = 3
+
+    def __init__(self, P, res, act, extras=True, n_streams=4):
+        from youreditableavatar_b200.parallel import GradBucket
+        self.act, self.extras, self.n_streams = act, extras, n_streams
+        self.bucket = GradBucket(P, 16, "cuda", names=GradBucket.TRAINING)
+
+    def step(self, cams, ups, world, feeder=None):
+        from youreditableavatar_b200.parallel import render_views_fwd_bwd
+        if feeder is not None:
+            cams = feeder.begin_step()
+
+        def upstream(color, depth, alpha, view_events):
+            if feeder is None:
+                return ups if self.extras else (ups[0], None, None)
+            feeder.images_out(color, view_events)
+            u = feeder.upstream()
+            return u if self.extras else (u[0], None, None)
+
+        render_views_fwd_bwd(self.act, cams, 3, upstream, self.bucket, extras=self.extras, n_streams=self.n_streams)
+        self.bucket.all_reduce()
+        if feeder is not None:
+            return feeder.end_step(self.bucket.flat[:1024].sum().view(1))   # D2H read of a gradient checksum
+        return None
+
+
+class OursPerViewRunner:
+    """The single-view drop-in calls in a Python loop with in-kernel gradient accumulation (what a caller that
+    keeps the reference's one-view-per-call structure gets)."""
+    name = "ours-per-view"
     n_up = 3
 
     def __init__(self, P, res, act, extras=True):
@@ -284,13 +396,15 @@ def timed(runner, cams, ups, world, steps, warmup, feeder=None):
     e0.record()
     for _ in range(steps):
         runner.step(cams, ups, world, feeder)
+    if feeder is not None and hasattr(feeder, "drain"):
+        feeder.drain()                       # the last step's result has reached the host
     e1.record()
     barrier(world)
     return max_over_ranks(e0.elapsed_time(e1), world)  # ms
 
 
 # ----------------------------------------------------------------------------------------------------
-def cpu_oracle_baseline(cfg, budget_tiles=160):
+def cpu_oracle_baseline(cfg, budget_tiles=420):
     """float64 oracle (oracle/oracle.py) on a bounded sample of the same workload: the full per-Gaussian
     preprocess + fwd+bwd blending of `budget_tiles` non-empty tiles, extrapolated by list entries."""
     import numpy as np
@@ -351,42 +465,84 @@ def main():
             return
 
     P, res, act, cams, up_host, up_dev = build_workload(cfg, V, rank, world)
-    runner = OursRunner(P, res, act) if args.impl == "ours" else RefRunner(P, res, act)
     from youreditableavatar_b200 import _lib
     L = _lib.lib()
+    batched = args.impl == "ours" and not args.per_view_api
+    if batched:
+        # the multi-view batch takes stacked tensors: dL/dcolor [V,3,H,W], dL/ddepth [V,1,H,W], dL/dalpha [V,1,H,W]
+        up_stack_host = tuple(torch.stack([u[k] for u in up_host]).pin_memory() for k in range(3))
+        up_stack_dev = tuple(t.cuda() for t in up_stack_host)
+        runner = OursRunner(P, res, act, n_streams=args.streams)
+        ups_for_runner = up_stack_dev
+    else:
+        runner = OursPerViewRunner(P, res, act) if args.impl == "ours" else RefRunner(P, res, act)
+        ups_for_runner = up_dev
 
-    # ---- device-resident throughput (value) with per-stage events + clock sampling -------------------
+    # ---- device-resident throughput (value) + clock sampling --------------------------------------------
     for _ in range(max(args.warmup, 3)):
-        runner.step(cams, up_dev, world)
+        runner.step(cams, ups_for_runner, world)
     sampler = ClockSampler(local)
     launches0 = L.tgr_kernel_launches()
     if args.impl == "ours":
         L.tgr_profile_enable(1)
     sampler.start()
-    ms = timed(runner, cams, up_dev, world, args.steps, 0)
+    ms = timed(runner, cams, ups_for_runner, world, args.steps, 0)
     clocks = sampler.stop()
     launches = L.tgr_kernel_launches() - launches0
-    stage = {}
-    if args.impl == "ours":
+
+    def collect_stages():
         sums = (C.c_float * _lib.NUM_STAGES)()
         cnts = (C.c_int32 * _lib.NUM_STAGES)()
         L.tgr_profile_collect(sums, cnts)
+        return {n: {"ms_avg": (sums[i] / cnts[i]) if cnts[i] else None, "launches": int(cnts[i])}
+                for i, n in enumerate(_lib.STAGE_NAMES)}
+
+    stage, stage_overlapped = {}, {}
+    if args.impl == "ours":
+        # events of the timed region: with several streams the kernels of different views share the SMs, so these
+        # durations are NOT properties of the kernels (reported as stages_overlapped)
+        stage_overlapped = collect_stages()
+        if batched and args.streams > 1:
+            # same batch on ONE stream, untimed: per-kernel durations without interference (used by `roofline`)
+            serial = OursRunner(P, res, act, n_streams=1)
+            serial.bucket = runner.bucket
+            serial.step(cams, ups_for_runner, world)
+            torch.cuda.synchronize()
+            collect_stages()
+            for _ in range(2):
+                serial.step(cams, ups_for_runner, world)
+            torch.cuda.synchronize()
+            stage = collect_stages()
+        else:
+            stage = stage_overlapped
         L.tgr_profile_enable(0)
-        stage = {n: {"ms_avg": (sums[i] / cnts[i]) if cnts[i] else None, "launches": int(cnts[i])}
-                 for i, n in enumerate(_lib.STAGE_NAMES)}
     views = V * world * args.steps
     value = views / (ms / 1000.0)
 
     # ---- end to end through the operator API with host buffers ------------------------------------------
     host_cams = [cam_to_host(c) for c in cams]
-    out_pinned = [torch.empty(3, res, res).pin_memory() for _ in range(V)]
-    feeder = HostFeeder(host_cams, up_host, out_pinned, runner.n_up)
-    ms_e2e = timed(runner, cams, up_dev, world, args.steps, max(1, args.warmup // 2), feeder)
+    n_up = runner.n_up
+    if batched:
+        out_pinned = torch.empty(V, 3, res, res).pin_memory()
+        feeder = BatchFeeder(host_cams, up_stack_host, out_pinned)
+    else:
+        out_pinned = [torch.empty(3, res, res).pin_memory() for _ in range(V)]
+        feeder = HostFeeder(host_cams, up_host, out_pinned, n_up)
+    ms_e2e = timed(runner, cams, ups_for_runner, world, args.steps, max(args.warmup, 3), feeder)
     e2e_value = views / (ms_e2e / 1000.0)
     cam_bytes = sum(v.numel() * 4 for v in host_cams[0].values() if isinstance(v, torch.Tensor))
-    n_up = runner.n_up
     h2d = V * (cam_bytes + sum(t.numel() * 4 for t in up_host[0][:n_up]))
     d2h = V * (3 * res * res * 4) + 4
+
+    # ---- ours through the single-view drop-in calls (the API the reference's callers use today) ---------
+    per_view = None
+    if batched:
+        pv = OursPerViewRunner(P, res, act)
+        pv.bucket = runner.bucket
+        k = max(2, args.steps // 4)
+        ms_pv = timed(pv, cams, up_dev, world, k, 2)
+        per_view = {"value": V * world * k / (ms_pv / 1000.0), "unit": UNIT,
+                    "note": "same workload through GaussianRasterizer-style single-view calls in a loop, one stream"}
 
     if rank != 0:
         return
@@ -398,6 +554,8 @@ def main():
                                "1024x1024, SH degree 3, fwd+bwd with depth/alpha outputs" % cfg,
                    "views_per_step_per_gpu": V, "global_views_per_step": V * world,
                    "parallelism": "dp%d over views, 1 all-reduce of the flat gradient buffer per step" % world,
+                   "api": ("multi-view batch (MultiViewRasterizer / tgr_*_batch), %d streams" % args.streams) if batched
+                          else "single-view calls in a loop",
                    "cache": "inputs (236 MB of parameters + 8 different cameras) exceed the 126 MB L2; no flush"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
@@ -411,7 +569,6 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         # dominant kernel: blend_bwd.  Algorithmic bytes per launch: N*20 + R*40 + P*48
-        fo_R = []
         from youreditableavatar_b200 import rasterizer as rz
         e = torch.Tensor([])
         cam = cams[0]
@@ -421,10 +578,24 @@ def main():
         alg = res * res * 20 + R0 * 40 + P * 48
         dom = stage.get("blend_bwd", {}).get("ms_avg") or float("nan")
         ach = alg / (dom * 1e-3) / 1e9
+        traffic = None
+        try:  # dram bytes of one launch from the committed `ncu --set full` capture (profiles/)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "blend_bwd_dram_traffic.json")))["bytes_per_launch"]
+        except Exception:
+            pass
         out["roofline"] = {"bound": "hbm", "kernel": "blend_bwd_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
-                           "frac": ach / peak, "traffic": None, "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback",
+                           "frac": ach / peak, "traffic": traffic,
+                           "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback",
                            "algorithmic_bytes_per_launch": alg, "ms_per_launch": dom,
-                           "note": "blend_bwd is issue/latency bound (FP32 + shuffle), not HBM bound: see profiles/"}
+                           "timing": "CUDA events around every launch of the kernel, batch issued on one stream "
+                                     "(stages); the timed region runs the views on %d streams, where kernel durations "
+                                     "include interference (stages_overlapped)" % args.streams,
+                           "note": "blend_bwd is issue/latency bound (FP32 + SFU pipes, reduction traffic to L2), not HBM "
+                                   "bound: see profiles/ for pipe utilisation and stall reasons"}
+        if stage_overlapped is not stage:
+            out["stages_overlapped"] = stage_overlapped
+        if per_view is not None:
+            out["per_view_api"] = per_view
         out["stages"] = stage
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_oracle_baseline(cfg)

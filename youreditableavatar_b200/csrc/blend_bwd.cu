@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint2* __re
   __shared__ __align__(16) float4 s_xy[BL_STAGES][BL_BATCH + 1];   // +1: the PAD_ENTRY dummy record
   __shared__ __align__(16) float4 s_co[BL_STAGES][BL_BATCH + 1];
   __shared__ __align__(16) float4 s_cd[BL_STAGES][BL_BATCH + 1];
-  __shared__ __align__(4) uint8_t s_list[8][LIST_BYTES];            // per consumer warp: candidates of the current batch
+  __shared__ __align__(4) uint8_t s_list[8][SUB_GROUPS * LIST_BYTES];  // per consumer warp and lane group: candidates of the current batch
   __shared__ __align__(8) uint64_t s_full[BL_STAGES], s_empty[BL_STAGES];
 
   // ---- work unit = (tile, segment): list positions [seg*SEG, min((seg+1)*SEG, total)) of one tile -------
@@ -97,14 +97,16 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint2* __re
   }
 
   // ========================= CONSUMERS =========================
-  const uint32_t px = tile_bx * TILE + (warp & 1) * 8 + (lane & 7);
-  const uint32_t py = tile_by * TILE + (warp >> 1) * 4 + (lane >> 3);
+  int lx, ly, group;
+  lane_pixel(warp, lane, lx, ly, group);
+  const uint32_t px = tile_bx * TILE + lx;
+  const uint32_t py = tile_by * TILE + ly;
   const bool inside = px < (uint32_t)W && py < (uint32_t)H;
   const uint32_t pix_id = (uint32_t)W * py + px;
   const float2 pixf = {(float)px, (float)py};
   const int pix_in_tile = warp * 32 + lane;
-  const float bx0 = (float)(tile_bx * TILE + (warp & 1) * 8), bx1 = bx0 + 7.f;   // this warp's pixel block
-  const float by0 = (float)(tile_by * TILE + (warp >> 1) * 4), by1 = by0 + 3.f;
+  const float bx0 = (float)(tile_bx * TILE + (warp & 1) * 8);   // origin of this warp's 8x4 pixel block
+  const float by0 = (float)(tile_by * TILE + (warp >> 1) * 4);
 
   const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
   const int warp_last = __reduce_max_sync(0xffffffffu, last_contributor);
@@ -153,15 +155,16 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint2* __re
     if (batch_first_pos - (BL_BATCH - 1) < warp_last) {  // else: whole batch lies behind this block's last contributor
       // entries at list positions >= warp_last lie behind this block's last contributor: batch entry e sits at
       // position batch_first_pos - e, so only e > batch_first_pos - warp_last can matter
+      int longest;
       const int ncand = cons_classify(max(0, batch_first_pos - warp_last + 1), min(BL_BATCH, count - b * BL_BATCH),
-                                      s_xy[stage], s_list[warp], bx0, bx1, by0, by1, lane);
-      const uint16_t* cand = reinterpret_cast<const uint16_t*>(s_list[warp]);
+                                      s_xy[stage], s_list[warp], bx0, by0, lane, longest);
+      const uint16_t* cand = reinterpret_cast<const uint16_t*>(s_list[warp] + group * LIST_BYTES);
       // Candidates are taken BG at a time (one 16-bit load = two batch-local indices) so the loads / power /
       // exp of one overlap the serial transmittance + behind-colour recurrences of the other.
       {
 #pragma unroll 1
-        for (int i = 0; i < ncand; i += BG) {
-          const uint32_t packed = cand[i >> 1];
+        for (int i = 0; i < longest; i += BG) {
+          const uint32_t packed = i < ncand ? (uint32_t)cand[i >> 1] : (PAD_WORD & 0xffffu);
           int j[BG];
           bool valid[BG];
           float G[BG], alpha[BG], rinv[BG];

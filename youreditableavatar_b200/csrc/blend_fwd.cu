@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(BL_THREADS) blend_fwd_kernel(const uint32_t* _
   __shared__ __align__(16) float4 s_xy[BL_STAGES][BL_BATCH + 1];   // x, y, hx, hy   (+1: the PAD_ENTRY dummy)
   __shared__ __align__(16) float4 s_co[BL_STAGES][BL_BATCH + 1];   // conic xx, xy, yy, opacity
   __shared__ __align__(16) float4 s_cd[BL_STAGES][BL_BATCH + 1];   // r, g, b, depth
-  __shared__ __align__(4) uint8_t s_list[8][LIST_BYTES];            // per consumer warp: candidates of the current batch
+  __shared__ __align__(4) uint8_t s_list[8][SUB_GROUPS * LIST_BYTES];  // per consumer warp and lane group: candidates of the current batch
   __shared__ __align__(8) uint64_t s_full[BL_STAGES], s_empty[BL_STAGES];
   __shared__ uint32_t s_stop[BL_STAGES];
   __shared__ uint32_t s_done_warps;
@@ -91,13 +91,15 @@ __global__ void __launch_bounds__(BL_THREADS) blend_fwd_kernel(const uint32_t* _
   }
 
   // ========================= CONSUMERS =========================
-  const uint32_t px = tile_bx * TILE + (warp & 1) * 8 + (lane & 7);
-  const uint32_t py = tile_by * TILE + (warp >> 1) * 4 + (lane >> 3);
+  int lx, ly, group;
+  lane_pixel(warp, lane, lx, ly, group);
+  const uint32_t px = tile_bx * TILE + lx;
+  const uint32_t py = tile_by * TILE + ly;
   const bool inside = px < (uint32_t)W && py < (uint32_t)H;
   const uint32_t pix_id = (uint32_t)W * py + px;
   const float2 pixf = {(float)px, (float)py};
-  const float bx0 = (float)(tile_bx * TILE + (warp & 1) * 8), bx1 = bx0 + 7.f;   // this warp's pixel block
-  const float by0 = (float)(tile_by * TILE + (warp >> 1) * 4), by1 = by0 + 3.f;
+  const float bx0 = (float)(tile_bx * TILE + (warp & 1) * 8);   // origin of this warp's 8x4 pixel block
+  const float by0 = (float)(tile_by * TILE + (warp >> 1) * 4);
 
   bool done = !inside;
   bool warp_done = false;
@@ -125,14 +127,15 @@ __global__ void __launch_bounds__(BL_THREADS) blend_fwd_kernel(const uint32_t* _
     if (*(volatile uint32_t*)&s_stop[stage]) break;
     if (!warp_done) {
       const uint32_t base_pos = (uint32_t)(b * BL_BATCH);
-      const int ncand = cons_classify(0, min(BL_BATCH, total - b * BL_BATCH), s_xy[stage], s_list[warp], bx0, bx1, by0, by1, lane);
-      const uint32_t* cand = reinterpret_cast<const uint32_t*>(s_list[warp]);
+      int longest;
+      const int ncand = cons_classify(0, min(BL_BATCH, total - b * BL_BATCH), s_xy[stage], s_list[warp], bx0, by0, lane, longest);
+      const uint32_t* cand = reinterpret_cast<const uint32_t*>(s_list[warp] + group * LIST_BYTES);
       // Candidates are taken CAND_GROUP at a time (one 32-bit load = four batch-local indices): their loads,
       // power and exp are independent (ILP), only the transmittance update is a serial chain.  Profiling showed
       // the kernel bound by the single-warp latency of the heaviest tile, not by SM throughput.
 #pragma unroll 1
-      for (int i = 0; i < ncand; i += CAND_GROUP) {
-        const uint32_t packed = cand[i >> 2];
+      for (int i = 0; i < longest; i += CAND_GROUP) {
+        const uint32_t packed = i < ncand ? cand[i >> 2] : PAD_WORD;
         int j[CAND_GROUP];
         bool ok[CAND_GROUP];
         float alpha[CAND_GROUP];

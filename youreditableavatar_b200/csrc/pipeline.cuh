@@ -153,29 +153,67 @@ constexpr int CAND_GROUP = 4;
 constexpr int PAD_ENTRY = BL_BATCH;                 // dummy record slot; record arrays hold BL_BATCH + 1 entries
 constexpr int LIST_BYTES = BL_BATCH + CAND_GROUP;   // per consumer warp
 
+// Sub-blocks.  The splats of an avatar are tiny: ncu showed the blend instructions of the forward running with 5
+// of 32 lanes active on average, i.e. a candidate of an 8x4 block touches ~3-5 of its pixels.  A warp therefore
+// splits into SUB_GROUPS lane groups, each owning a SUB_W x SUB_H sub-block of the warp's 8x4 block and walking
+// ITS OWN candidate list: in one warp instruction up to SUB_GROUPS different Gaussians are evaluated, each only
+// on the pixels of a sub-block it can reach.  The warp iterates to the longest of its group lists; shorter lists
+// read PAD_ENTRY.
+constexpr int SUB_GROUPS = 4;
+constexpr int SUB_W = 4, SUB_H = 2;
+constexpr int SUB_GX = 8 / SUB_W;                 // sub-blocks across the warp's 8x4 block
+constexpr int SUB_LANES = 32 / SUB_GROUPS;
+static_assert(SUB_W * SUB_H == SUB_LANES && (8 % SUB_W) == 0 && (4 % SUB_H) == 0, "sub-block geometry");
+
+// pixel (relative to the tile origin) owned by `lane` of consumer warp `warp`; shared by forward and backward
+__device__ __forceinline__ void lane_pixel(int warp, int lane, int& x, int& y, int& group) {
+  group = lane / SUB_LANES;
+  const int t = lane % SUB_LANES;
+  x = (warp & 1) * 8 + (group % SUB_GX) * SUB_W + (t % SUB_W);
+  y = (warp >> 1) * 4 + (group / SUB_GX) * SUB_H + (t / SUB_W);
+}
+
 // first_excluded: entries >= this batch-local index are ignored (ragged last batch; in the backward also the
 // entries behind the block's last contributor, see blend_bwd.cu).  first_included: entries below are ignored.
-__device__ __forceinline__ int cons_classify(int first_included, int first_excluded, const float4* s_xy, uint8_t* my_list,
-                                             float bx0, float bx1, float by0, float by1, int lane) {
-  uint32_t cnt = 0;
+// (bx0, by0) is the pixel origin of the warp's 8x4 block.  Writes SUB_GROUPS lists (lists[g*LIST_BYTES ...]) and
+// returns, per lane, the padded length of ITS group's list; `longest` is the warp-wide maximum.
+__device__ __forceinline__ int cons_classify(int first_included, int first_excluded, const float4* s_xy, uint8_t* lists,
+                                             float bx0, float by0, int lane, int& longest) {
+  uint32_t cnt[SUB_GROUPS];
+#pragma unroll
+  for (int g = 0; g < SUB_GROUPS; ++g) cnt[g] = 0;
   const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
   for (int c = 0; c < BL_CHUNKS; ++c) {
     const int e = c * 32 + lane;
-    bool hit = false;
+    float x_lo = 1e30f, x_hi = -1e30f, y_lo = 1e30f, y_hi = -1e30f;  // empty interval: hits nothing
     if (e >= first_included && e < first_excluded) {
-      const float4 g = s_xy[e];
-      hit = (g.z >= 0.f) && (g.x - g.z <= bx1) && (g.x + g.z >= bx0) && (g.y - g.w <= by1) && (g.y + g.w >= by0);
+      const float4 q = s_xy[e];
+      if (q.z >= 0.f) { x_lo = q.x - q.z - bx0; x_hi = q.x + q.z - bx0; y_lo = q.y - q.w - by0; y_hi = q.y + q.w - by0; }
     }
-    const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-    if (hit) my_list[cnt + __popc(bal & lt)] = (uint8_t)e;
-    cnt += __popc(bal);
+#pragma unroll
+    for (int g = 0; g < SUB_GROUPS; ++g) {
+      const float sx0 = (float)((g % SUB_GX) * SUB_W), sy0 = (float)((g / SUB_GX) * SUB_H);
+      const bool hit = (x_lo <= sx0 + (float)(SUB_W - 1)) && (x_hi >= sx0) && (y_lo <= sy0 + (float)(SUB_H - 1)) && (y_hi >= sy0);
+      const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+      if (hit) lists[g * LIST_BYTES + cnt[g] + __popc(bal & lt)] = (uint8_t)e;
+      cnt[g] += __popc(bal);
+    }
   }
-  const uint32_t padded = (cnt + CAND_GROUP - 1) & ~(uint32_t)(CAND_GROUP - 1);
-  if (cnt + lane < padded) my_list[cnt + lane] = (uint8_t)PAD_ENTRY;
+  int mine = 0;
+  longest = 0;
+#pragma unroll
+  for (int g = 0; g < SUB_GROUPS; ++g) {
+    const uint32_t padded = (cnt[g] + CAND_GROUP - 1) & ~(uint32_t)(CAND_GROUP - 1);
+    if (cnt[g] + lane < padded) lists[g * LIST_BYTES + cnt[g] + lane] = (uint8_t)PAD_ENTRY;
+    if (lane / SUB_LANES == g) mine = (int)padded;
+    longest = max(longest, (int)padded);
+  }
   __syncwarp();
-  return (int)padded;
+  return mine;
 }
+
+constexpr uint32_t PAD_WORD = 0x01010101u * (uint32_t)PAD_ENTRY;  // four PAD_ENTRY indices
 
 // ---- producer loop -----------------------------------------------------------------------------------
 // The producer never waits for its own gathers: after issuing a batch every lane executes

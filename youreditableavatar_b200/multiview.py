@@ -63,6 +63,7 @@ class ViewBatchState:
         self.extras = False
         self.n_streams = 1
         self.binding = None
+        self.view_events = []   # one CUDA event per view, recorded when its forward outputs are complete
 
 
 def _align(x: int, a: int = 256) -> int:
@@ -152,6 +153,7 @@ def c_rasterize_views(settings: Sequence, means3D, colors, opacity, scales, rota
         fork = torch.cuda.Event()
         fork.record(main)
         binnings = []
+        view_events = []
         for v in range(V):
             p = params[v]
             binning = torch.empty(L.tgr_binning_bytes(P, counts[v], W, H), **u8)
@@ -162,11 +164,15 @@ def c_rasterize_views(settings: Sequence, means3D, colors, opacity, scales, rota
                 s.wait_event(fork)
             check(L.tgr_forward_depth_sort(C.byref(p), s.cuda_stream), "tgr_forward_depth_sort")
             check(L.tgr_forward_render(C.byref(p), counts[v], s.cuda_stream), "tgr_forward_render")
+            ev = torch.cuda.Event()
+            ev.record(s)
+            view_events.append(ev)   # view v's images are complete: lets callers drain them while later views render
         if S > 1:
             for s in streams:
                 main.wait_stream(s)
 
     state.params, state.counts, state.n_streams = params, counts, S
+    state.view_events = view_events
     state.tensors = (means3D, colors, opacity, scales, rotations, cov3D_precomp, sh, cams, geom, img, binnings, radii)
     return (state, color, radii) + ((depth, alpha) if extras else ())
 

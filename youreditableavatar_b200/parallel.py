@@ -115,8 +115,10 @@ def render_views_fwd_bwd(inp: Dict[str, torch.Tensor], cams: Sequence[Dict[str, 
     """Batched forward + backward of this rank's views (youreditableavatar_b200.multiview): one preprocess launch
     for all views, per-view binning / blending on `n_streams` streams, one backward-preprocess launch that writes
     the summed gradients into `bucket` (overwrite, or add with accumulate=True).
-    `upstream(color[V,3,H,W], depth[V,1,H,W] | None, alpha | None)` -> (dL_dcolor[V,3,H,W], dL_ddepth | None,
-    dL_dalpha | None).  Returns the rendered images."""
+    `upstream(color[V,3,H,W], depth[V,1,H,W] | None, alpha | None[, view_events])` -> (dL_dcolor[V,3,H,W],
+    dL_ddepth | None, dL_dalpha | None); `view_events[v]` fires when view v's images are complete (the forward has
+    already been joined on the current stream when `upstream` runs, the events only matter to side streams).
+    Returns the rendered images."""
     from . import multiview as mv
     e = torch.Tensor([])
     g = lambda k: inp[k] if inp.get(k) is not None else e
@@ -125,7 +127,11 @@ def render_views_fwd_bwd(inp: Dict[str, torch.Tensor], cams: Sequence[Dict[str, 
                                g("cov3D_precomp"), g("shs"), extras=extras, n_streams=n_streams)
     state, color = res[0], res[1]
     depth, alpha = (res[3], res[4]) if extras else (None, None)
-    dLc, dLd, dLa = upstream(color, depth, alpha)
+    import inspect
+    if len(inspect.signature(upstream).parameters) >= 4:
+        dLc, dLd, dLa = upstream(color, depth, alpha, state.view_events)
+    else:
+        dLc, dLd, dLa = upstream(color, depth, alpha)
     kw = dict(accumulate_into=bucket.views) if accumulate else dict(out=bucket.views)
     mv.c_rasterize_views_backward(state, dLc, dL_dout_depth=dLd, dL_dout_alpha=dLa, **kw)
     return color
