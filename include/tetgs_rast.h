@@ -153,15 +153,19 @@ int tgr_backward(const tgr_params* p, const tgr_binding* bind, uint64_t num_rend
  *   for v: tgr_forward_depth_sort(&views[v], s_v); tgr_forward_render(&views[v], cap_v, s_v)
  *   ... upstream gradients ...
  *   for v: tgr_backward_blend(&views[v], cap_v, s_v)       2-D gradients of view v (blend stage only)
- *   tgr_backward_preprocess_batch(views, caps, n, bind, s0) after all s_v joined s0: chain rule to the
+ *   tgr_backward_preprocess_batch(views, caps, n, bind, 0, 0, s0)
+ *                                                          after all s_v joined s0: chain rule to the
  *                                                          parameters, summed over the batch; outputs and the
  *                                                          accumulate flag are taken from views[0]
  * tgr_forward_preprocess == preprocess_batch of one view + depth sort; tgr_backward == blend + batch of one. */
 int tgr_forward_preprocess_batch(const tgr_params* views, int32_t n_views, const tgr_binding* bind, void* stream);
 int tgr_forward_depth_sort(const tgr_params* p, void* stream);
 int tgr_backward_blend(const tgr_params* p, uint64_t num_rendered_capacity, void* stream);
+/* gaussian_first / gaussian_count restrict the launch to a range of Gaussians (first a multiple of 256;
+ * count <= 0 = all): a data-parallel caller splits the backward into ranges and all-reduces the gradients of one
+ * range while the next range is being computed. */
 int tgr_backward_preprocess_batch(const tgr_params* views, const uint64_t* num_rendered_capacities, int32_t n_views,
-                                  const tgr_binding* bind, void* stream);
+                                  const tgr_binding* bind, int32_t gaussian_first, int32_t gaussian_count, void* stream);
 
 /* Synchronously reads {num_rendered, overflow, num_visible, reserved} from a geom buffer header. */
 int tgr_read_header(const void* geom_buffer, uint32_t out[4], void* stream);

@@ -374,6 +374,14 @@ def test_multiview_batch_matches_per_view_calls(V, n_streams):
         ref_sum = [x.clone() for x in go] if ref_sum is None else [a + b for a, b in zip(ref_sum, go)]
     for name, a, b in zip(["m2D", "col", "op", "m3D", "cov", "sh", "sc", "rot"], grads, ref_sum):
         assert rel_l2(a, b) <= 2e-6, (name, rel_l2(a, b))
+    # the Gaussian-range variant (ranges of the final kernel, used to overlap the all-reduce) gives the same sums
+    # (not the same bits: the blend stage's floating-point reductions are re-run in a different order)
+    seen = []
+    grads_r = mv.c_rasterize_views_backward(state, dLc, dL_dout_depth=dLd, dL_dout_alpha=dLa, chunks=3,
+                                            on_chunk=lambda first, count: seen.append((first, count)))
+    assert sum(c for _, c in seen) == P and all(f % 256 == 0 for f, _ in seen) and len(seen) == 3
+    for a, b in zip(grads_r, grads):
+        assert rel_l2(a, b) <= 2e-6
     # accumulate=True adds a second batch on top
     grads2 = mv.c_rasterize_views_backward(state, dLc, dL_dout_depth=dLd, dL_dout_alpha=dLa, accumulate_into=grads)
     for a, b in zip(grads2, ref_sum):

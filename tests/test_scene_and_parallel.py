@@ -87,6 +87,8 @@ def test_grad_bucket_layout():
         assert v.data_ptr() % 16 == 0
     b.views[5].fill_(2.0)
     assert float(b.flat.sum()) == 2.0 * 10 * 16 * 3
+    # SH rows sit last in memory: everything else is one contiguous slice in front of them
+    assert b.sh_offset == b.flat.numel() - 10 * 16 * 3 and b.views[5].data_ptr() == b.flat[b.sh_offset:].data_ptr()
     t = GradBucket(10, 16, "cpu", names=GradBucket.TRAINING)
     assert [n for n, v in zip(GRAD_NAMES, t.views) if v is not None] == list(GradBucket.TRAINING)
     assert t.flat.numel() < b.flat.numel()
@@ -108,9 +110,17 @@ def _worker(rank, world, port, q):
                 t.copy_(contrib)
             else:
                 t.add_(contrib)
+    ref = bucket.flat.clone()
     bucket.all_reduce()
     want = sum(v + 1 for v in range(n_views))
     ok = all(torch.allclose(t, torch.full_like(t, float(want) * (k + 1))) for k, t in enumerate(bucket.views) if t is not None)
+    # overlapped variant: SH rows in ranges (as the chunked backward hands them over), then the rest
+    summed = bucket.flat.clone()
+    bucket.flat.copy_(ref)
+    for first in range(0, P, 16):
+        bucket.all_reduce_sh_rows_async(first, min(16, P - first))
+    bucket.all_reduce_rest_and_wait()
+    ok = ok and torch.equal(bucket.flat, summed) and bucket._pending == []
     q.put((rank, ok, mine))
     dist.destroy_process_group()
 

@@ -168,6 +168,8 @@ static int preprocess_views(const tgr_params* views, int32_t n, const tgr_bindin
   for (int32_t v0 = 0; v0 < n; v0 += MAX_BATCH) {
     ViewBatch vb{};
     vb.V = std::min<int32_t>(MAX_BATCH, n - v0);
+    vb.first = 0;
+    vb.end = p0->P;
     for (int32_t k = 0; k < vb.V; ++k) {
       GeomView g = carve_geom(views[v0 + k].geom_buffer, p0->P);
       cudaMemsetAsync(g.header, 0, sizeof(GeomHeader), s);
@@ -274,6 +276,8 @@ int tgr_backward(const tgr_params* p, const tgr_binding* bind, uint64_t cap, voi
   if (int rc = backward_blend(p, cap, s)) return rc;
   ViewBatch vb{};
   vb.V = 1;
+  vb.first = 0;
+  vb.end = p->P;
   vb.v[0] = make_view_desc(*p, carve_geom(p->geom_buffer, p->P), carve_bin(p->binning_buffer, p->P, cap, p->W, p->H).grad_acc);
   prof_begin(TGR_STAGE_PREPROCESS_BWD, s);
   if (int rc = launch_preprocess_bwd(*p, bind, vb, s)) return rc;
@@ -290,9 +294,14 @@ int tgr_backward_blend(const tgr_params* p, uint64_t cap, void* stream) {
 }
 
 int tgr_backward_preprocess_batch(const tgr_params* views, const uint64_t* caps, int32_t n_views, const tgr_binding* bind,
-                                  void* stream) {
+                                  int32_t gaussian_first, int32_t gaussian_count, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!views || !caps || n_views <= 0) { set_error("batch: no views"); return 1; }
+  if (gaussian_count <= 0) { gaussian_first = 0; gaussian_count = views[0].P; }
+  if (gaussian_first < 0 || (gaussian_first % 256) != 0 || gaussian_first + (int64_t)gaussian_count > views[0].P) {
+    set_error("batch: Gaussian range [%d, +%d) must start at a multiple of 256 and lie inside [0, P)", gaussian_first, gaussian_count);
+    return 1;
+  }
   for (int32_t v = 0; v < n_views; ++v) {
     if (int rc = validate(&views[v], true, caps[v])) return rc;
     if (v && check_same_gaussians(&views[0], &views[v])) return 1;
@@ -302,6 +311,8 @@ int tgr_backward_preprocess_batch(const tgr_params* views, const uint64_t* caps,
   for (int32_t v0 = 0; v0 < n_views; v0 += MAX_BATCH) {
     ViewBatch vb{};
     vb.V = std::min<int32_t>(MAX_BATCH, n_views - v0);
+    vb.first = gaussian_first;
+    vb.end = gaussian_first + gaussian_count;
     for (int32_t k = 0; k < vb.V; ++k) {
       const tgr_params& pv = views[v0 + k];
       vb.v[k] = make_view_desc(pv, carve_geom(pv.geom_buffer, pv.P),

@@ -196,6 +196,8 @@ struct ViewDesc {
 
 struct ViewBatch {
   int32_t V;
+  int32_t first;   // backward: first Gaussian of the range this launch covers (multiple of 256); forward: 0
+  int32_t end;     // backward: one past the last Gaussian of the range; forward: P
   int32_t pad;
   ViewDesc v[MAX_BATCH];
 };

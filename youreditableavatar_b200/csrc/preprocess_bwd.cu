@@ -49,9 +49,11 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
                                                              const __grid_constant__ ViewBatch vb) {
   extern __shared__ float s_rows[];
   __shared__ float s_cam[MAX_BATCH][CAM_FLOATS];
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int block_first = blockIdx.x * blockDim.x;
-  const int nrows = min((int)blockDim.x, p.P - block_first);
+  // the launch covers Gaussians [vb.first, vb.end): a caller may split a batch's backward into ranges so that the
+  // all-reduce of one range's gradients overlaps the next range's kernel (parallel.py)
+  const int block_first = vb.first + blockIdx.x * blockDim.x;
+  const int idx = block_first + threadIdx.x;
+  const int nrows = min((int)blockDim.x, vb.end - block_first);
   const int V = MULTI ? vb.V : 1;
   for (int e = threadIdx.x; e < V * CAM_FLOATS; e += blockDim.x) {
     const int v = e / CAM_FLOATS, k = e % CAM_FLOATS;
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
 
   float o_m2[2] = {0.f, 0.f}, o_col[3] = {0.f, 0.f, 0.f}, o_op = 0.f, o_mean[3] = {0.f, 0.f, 0.f};
   float o_cov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, o_sc[3] = {0.f, 0.f, 0.f}, o_rot[4] = {0.f, 0.f, 0.f, 0.f};
-  if (idx < p.P) {
+  if (idx < vb.end) {
   const size_t i = (size_t)idx;
   const int M = p.M;
   const bool has_sh = (p.shs != nullptr && p.colors_precomp == nullptr && M > 0);
@@ -439,8 +441,8 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
 // `p` carries the Gaussians and the output gradient tensors (shared by the batch); cameras, radii, clamp flags
 // and the packed 2-D gradient rows of every view come from `vb`.
 int launch_preprocess_bwd(const tgr_params& p, const tgr_binding* bind, const ViewBatch& vb, cudaStream_t s) {
-  const int blocks = (p.P + 255) / 256;
-  if (blocks == 0 || vb.V <= 0) return 0;
+  const int blocks = (vb.end - vb.first + 255) / 256;
+  if (blocks <= 0 || vb.V <= 0) return 0;
   const bool has_sh = (p.shs != nullptr && p.colors_precomp == nullptr && p.M > 0);
   const bool staged = has_sh && p.M == 16 && p.D >= 2 && p.dL_dsh != nullptr &&
                       (reinterpret_cast<uintptr_t>(p.shs) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.dL_dsh) & 15) == 0;

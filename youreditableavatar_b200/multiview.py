@@ -178,7 +178,7 @@ def c_rasterize_views(settings: Sequence, means3D, colors, opacity, scales, rota
 
 
 def c_rasterize_views_backward(state: ViewBatchState, dL_dout_color, dL_dout_depth=None, dL_dout_alpha=None,
-                               accumulate_into=None, out=None):
+                               accumulate_into=None, out=None, chunks: int = 1, on_chunk=None):
     """Backward of a batch: dL_dout_color[V,3,H,W] (+ depth / alpha gradients [V,1,H,W]) -> the 8-tuple of
     `_C.rasterize_gaussians_backward` (rasterize_points.cu:117-196), summed over the V views.  `out` /
     `accumulate_into` as in `c_rasterize_gaussians_backward`."""
@@ -243,7 +243,16 @@ def c_rasterize_views_backward(state: ViewBatchState, dL_dout_color, dL_dout_dep
                 main.wait_stream(s)
         caps = (C.c_uint64 * V)(*state.counts)
         bptr = C.byref(state.binding) if state.binding is not None else None
-        check(L.tgr_backward_preprocess_batch(params, caps, V, bptr, main.cuda_stream), "tgr_backward_preprocess_batch")
+        nch = max(1, min(int(chunks), (P + 255) // 256))
+        per = ((P + nch - 1) // nch + 255) // 256 * 256          # range starts must be multiples of 256
+        first = 0
+        while first < P:
+            count = min(per, P - first)
+            check(L.tgr_backward_preprocess_batch(params, caps, V, bptr, first, count, main.cuda_stream),
+                  "tgr_backward_preprocess_batch")
+            if on_chunk is not None:
+                on_chunk(first, count)
+            first += count
         state.keep_bwd = (dL_dout_color, dL_dout_depth, dL_dout_alpha)
     return grads
 

@@ -28,9 +28,11 @@ def grad_shapes(P: int, M: int) -> Tuple[Tuple[int, ...], ...]:
 
 
 class GradBucket:
-    """One flat fp32 buffer laid out [means2D | colors | opacity | means3D | cov3D | sh | scales | rotations];
-    `.views` are the eight gradient tensors aliasing it.  Offsets are multiples of 4 floats (16-byte vector
-    stores in the kernels need the SH / rotation views 16-byte aligned)."""
+    """One flat fp32 buffer holding the gradient tensors back to back; `.views` are the eight gradient tensors (in
+    the order `_C.rasterize_gaussians_backward` returns them) aliasing it.  Memory order: the small tensors first,
+    dL_dsh (81 % of the bytes at SH degree 3) LAST, so that "everything but SH" is one contiguous slice and SH rows
+    of a range of Gaussians are another — the two shapes the overlapped all-reduce sends.  Offsets are multiples of
+    4 floats (16-byte vector stores in the kernels need the SH / rotation views 16-byte aligned)."""
 
     # what an optimizer over (means/delta, opacity, SH, scales, rotations) consumes; the other three exist in the
     # reference's return tuple only because its kernels produce them on the way
@@ -40,19 +42,21 @@ class GradBucket:
         self.P, self.M = P, M
         self.shapes = grad_shapes(P, M)
         self.names = tuple(GRAD_NAMES if names is None else names)
-        offs, total = [], 0
-        for name, shp in zip(GRAD_NAMES, self.shapes):
-            if name not in self.names:
-                offs.append(None)
+        offs, total = [None] * len(GRAD_NAMES), 0
+        order = [i for i, n in enumerate(GRAD_NAMES) if n != "dL_dsh"] + [GRAD_NAMES.index("dL_dsh")]
+        for i in order:
+            if GRAD_NAMES[i] not in self.names:
                 continue
-            offs.append(total)
+            offs[i] = total
             n = 1
-            for d in shp:
+            for d in self.shapes[i]:
                 n *= d
             total += (n + 3) // 4 * 4
         self.offsets = offs
         self.flat = torch.zeros(max(total, 1), dtype=torch.float32, device=device)
         self.views = tuple(None if o is None else self._view(o, shp) for o, shp in zip(offs, self.shapes))
+        self.sh_offset = offs[GRAD_NAMES.index("dL_dsh")]   # None when SH gradients are not in the bucket
+        self._pending = []
 
     def _view(self, off, shp):
         n = 1
@@ -63,11 +67,39 @@ class GradBucket:
     def named(self) -> Dict[str, torch.Tensor]:
         return dict(zip(GRAD_NAMES, self.views))
 
-    def all_reduce(self, group=None):
-        """Sum over ranks — the only collective of a step."""
+    @staticmethod
+    def _distributed(group=None) -> bool:
         import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+    def all_reduce(self, group=None):
+        """Sum over ranks in one call — the only collective of a step."""
+        import torch.distributed as dist
+        if self._distributed(group):
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        return self
+
+    # -- overlapped variant: ranges of SH rows leave while the backward still computes the next range ---------
+    def all_reduce_sh_rows_async(self, first: int, count: int, group=None):
+        """Starts the all-reduce of dL_dsh[first:first+count] (contiguous in `flat`).  Stream-ordered after the work
+        already queued on the current stream, runs on the process group's own stream."""
+        import torch.distributed as dist
+        if self.sh_offset is None or not self._distributed(group):
+            return
+        row = self.M * 3
+        sl = self.flat[self.sh_offset + first * row: self.sh_offset + (first + count) * row]
+        self._pending.append(dist.all_reduce(sl, op=dist.ReduceOp.SUM, group=group, async_op=True))
+
+    def all_reduce_rest_and_wait(self, group=None):
+        """All-reduces everything that is not SH (one contiguous slice) and joins the pending SH ranges."""
+        import torch.distributed as dist
+        if self._distributed(group):
+            end = self.sh_offset if self.sh_offset is not None else self.flat.numel()
+            if end > 0:
+                self._pending.append(dist.all_reduce(self.flat[:end], op=dist.ReduceOp.SUM, group=group, async_op=True))
+            for w in self._pending:
+                w.wait()
+        self._pending = []
         return self
 
 
@@ -111,13 +143,17 @@ def settings_from_cam(cam: Dict[str, object], degree: int):
 
 
 def render_views_fwd_bwd(inp: Dict[str, torch.Tensor], cams: Sequence[Dict[str, object]], degree: int, upstream,
-                         bucket: GradBucket, extras: bool = False, n_streams: int = 4, accumulate: bool = False):
+                         bucket: GradBucket, extras: bool = False, n_streams: int = 4, accumulate: bool = False,
+                         all_reduce: bool = False, comm_chunks: int = 4, group=None):
     """Batched forward + backward of this rank's views (youreditableavatar_b200.multiview): one preprocess launch
     for all views, per-view binning / blending on `n_streams` streams, one backward-preprocess launch that writes
     the summed gradients into `bucket` (overwrite, or add with accumulate=True).
     `upstream(color[V,3,H,W], depth[V,1,H,W] | None, alpha | None[, view_events])` -> (dL_dcolor[V,3,H,W],
     dL_ddepth | None, dL_dalpha | None); `view_events[v]` fires when view v's images are complete (the forward has
     already been joined on the current stream when `upstream` runs, the events only matter to side streams).
+    all_reduce=True also sums `bucket` over the ranks, overlapped with the backward: the per-Gaussian kernel runs
+    over `comm_chunks` ranges of Gaussians and each range's SH gradient rows are all-reduced (NCCL, on the process
+    group's stream) while the next range is computed; the small tensors follow in one slice at the end.
     Returns the rendered images."""
     from . import multiview as mv
     e = torch.Tensor([])
@@ -133,5 +169,11 @@ def render_views_fwd_bwd(inp: Dict[str, torch.Tensor], cams: Sequence[Dict[str, 
     else:
         dLc, dLd, dLa = upstream(color, depth, alpha)
     kw = dict(accumulate_into=bucket.views) if accumulate else dict(out=bucket.views)
-    mv.c_rasterize_views_backward(state, dLc, dL_dout_depth=dLd, dL_dout_alpha=dLa, **kw)
+    if all_reduce and GradBucket._distributed(group):
+        mv.c_rasterize_views_backward(state, dLc, dL_dout_depth=dLd, dL_dout_alpha=dLa, chunks=comm_chunks,
+                                      on_chunk=lambda first, count: bucket.all_reduce_sh_rows_async(first, count, group),
+                                      **kw)
+        bucket.all_reduce_rest_and_wait(group)
+    else:
+        mv.c_rasterize_views_backward(state, dLc, dL_dout_depth=dLd, dL_dout_alpha=dLa, **kw)
     return color
