@@ -46,7 +46,9 @@ def parse():
     ap.add_argument("--config", default="C3")
     ap.add_argument("--views-per-step", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the per-view stages of a batch rotate over")
+    ap.add_argument("--streams", type=int, default=0,
+                    help="0 (default): fused schedule, every per-view stage is one launch for the whole batch; "
+                         "n >= 1: per-view launches round-robin on n CUDA streams")
     ap.add_argument("--comm-chunks", type=int, default=4,
                     help="N > 1: Gaussian ranges the backward is split into so the all-reduce overlaps it")
     ap.add_argument("--per-view-api", action="store_true",
@@ -295,7 +297,7 @@ class OursRunner:
     name = "ours"
     n_up = 3
 
-    def __init__(self, P, res, act, extras=True, n_streams=4, comm_chunks=4):
+    def __init__(self, P, res, act, extras=True, n_streams=0, comm_chunks=4):
         from youreditableavatar_b200.parallel import GradBucket
         self.act, self.extras, self.n_streams, self.comm_chunks = act, extras, n_streams, comm_chunks
         self.bucket = GradBucket(P, 16, "cuda", names=GradBucket.TRAINING)
@@ -561,7 +563,8 @@ def main():
                    "views_per_step_per_gpu": V, "global_views_per_step": V * world,
                    "parallelism": "dp%d over views, flat gradient buffer all-reduced once per step%s" % (
                        world, (" in %d ranges overlapped with the backward" % args.comm_chunks) if (batched and world > 1) else ""),
-                   "api": ("multi-view batch (MultiViewRasterizer / tgr_*_batch), %d streams" % args.streams) if batched
+                   "api": ("multi-view batch (MultiViewRasterizer / tgr_*_batch), " +
+                           ("fused per-stage launches" if args.streams == 0 else "%d streams" % args.streams)) if batched
                           else "single-view calls in a loop",
                    "cache": "inputs (236 MB of parameters + 8 different cameras) exceed the 126 MB L2; no flush"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -575,14 +578,16 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        # dominant kernel: blend_bwd.  Algorithmic bytes per launch: N*20 + R*40 + P*48
-        from youreditableavatar_b200 import rasterizer as rz
+        # dominant kernel: blend_bwd.  Algorithmic bytes per view: N*20 + R*40 + P*48; a launch of the
+        # fused schedule serves all V views of the batch, a per-view launch one
+        from youreditableavatar_b200 import multiview as mv
+        from youreditableavatar_b200.parallel import settings_from_cam
         e = torch.Tensor([])
-        cam = cams[0]
-        R0 = rz.c_rasterize_gaussians(cam["bg"], act["means3D"], e, act["opacities"], act["scales"], act["rotations"], 1.0,
-                                      e, cam["viewmatrix"], cam["projmatrix"], cam["tanfovx"], cam["tanfovy"], res, res,
-                                      act["shs"], 3, cam["campos"], False, False)[0]
-        alg = res * res * 20 + R0 * 40 + P * 48
+        st = mv.c_rasterize_views([settings_from_cam(c, 3) for c in cams], act["means3D"], e, act["opacities"],
+                                  act["scales"], act["rotations"], e, act["shs"], extras=True)[0]
+        Rs = list(st.counts)
+        per_launch_views = V if (batched and args.streams == 0) else 1
+        alg = (res * res * 20 + P * 48) * per_launch_views + 40 * (sum(Rs) if per_launch_views == V else Rs[0])
         dom = stage.get("blend_bwd", {}).get("ms_avg") or float("nan")
         ach = alg / (dom * 1e-3) / 1e9
         traffic = None
@@ -593,10 +598,13 @@ def main():
         out["roofline"] = {"bound": "hbm", "kernel": "blend_bwd_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
                            "frac": ach / peak, "traffic": traffic,
                            "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback",
-                           "algorithmic_bytes_per_launch": alg, "ms_per_launch": dom,
-                           "timing": "CUDA events around every launch of the kernel, batch issued on one stream "
-                                     "(stages); the timed region runs the views on %d streams, where kernel durations "
-                                     "include interference (stages_overlapped)" % args.streams,
+                           "algorithmic_bytes_per_launch": alg, "ms_per_launch": dom, "views_per_launch": per_launch_views,
+                           "num_rendered_per_view": Rs,
+                           "timing": ("CUDA events around every launch of the kernel inside the timed region, on the "
+                                      "launching stream") if args.streams <= 1 else
+                                     ("CUDA events around every launch of the kernel, batch issued on one stream (stages); "
+                                      "the timed region runs the views on %d streams, where kernel durations include "
+                                      "interference (stages_overlapped)" % args.streams),
                            "note": "blend_bwd is issue/latency bound (FP32 + SFU pipes, reduction traffic to L2), not HBM "
                                    "bound: see profiles/ for pipe utilisation and stall reasons"}
         if stage_overlapped is not stage:

@@ -161,6 +161,17 @@ int tgr_backward(const tgr_params* p, const tgr_binding* bind, uint64_t num_rend
 int tgr_forward_preprocess_batch(const tgr_params* views, int32_t n_views, const tgr_binding* bind, void* stream);
 int tgr_forward_depth_sort(const tgr_params* p, void* stream);
 int tgr_backward_blend(const tgr_params* p, uint64_t num_rendered_capacity, void* stream);
+/* Fused schedule: every per-view stage (depth sort, emission, tile sort, ranges, blending / blend backward) is
+ * ONE launch for up to TGR_MAX_BATCH views (blockIdx.y or the work queue selects the view), on one stream:
+ *   tgr_forward_render_batch  == for v: tgr_forward_depth_sort + tgr_forward_render
+ *   tgr_backward_blend_batch  == for v: tgr_backward_blend
+ * with identical per-view results.  A single 1 M-Gaussian view cannot fill 148 SMs in its sorts and scans and ends
+ * its blending in a single-tile tail; eight views in one launch can, and the heaviest tiles of ALL views are
+ * scheduled first. */
+int tgr_forward_render_batch(const tgr_params* views, const uint64_t* num_rendered_capacities, int32_t n_views,
+                             void* stream);
+int tgr_backward_blend_batch(const tgr_params* views, const uint64_t* num_rendered_capacities, int32_t n_views,
+                             void* stream);
 /* gaussian_first / gaussian_count restrict the launch to a range of Gaussians (first a multiple of 256;
  * count <= 0 = all): a data-parallel caller splits the backward into ranges and all-reduces the gradients of one
  * range while the next range is being computed. */

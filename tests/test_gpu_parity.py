@@ -345,7 +345,7 @@ def test_work_queue_covers_every_tile_many_sizes():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n_streams", [1, 3])
+@pytest.mark.parametrize("n_streams", [0, 1, 3])
 @pytest.mark.parametrize("V", [1, 3, 11])
 def test_multiview_batch_matches_per_view_calls(V, n_streams):
     """tgr_*_batch: per-view forward results are bit-identical to single-view calls; the summed gradients agree

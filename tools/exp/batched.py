@@ -31,7 +31,7 @@ for S in [int(x) for x in sys.argv[1:]] or [1, 2, 4]:
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     line = "batched V=%d streams %d: %.3f ms/step  %.1f views/s" % (V, S, ms / K, V * K / ms * 1000)
-    if S == 1:
+    if S <= 1:
         L.tgr_profile_enable(1)
         step(); torch.cuda.synchronize()
         sums = (C.c_float * _lib.NUM_STAGES)(); cnts = (C.c_int32 * _lib.NUM_STAGES)()

@@ -63,6 +63,8 @@ SYMBOLS = {
     "tgr_forward_preprocess_batch": (C.c_int, [C.POINTER(TgrParams), C.c_int32, C.POINTER(TgrBinding), C.c_void_p]),
     "tgr_forward_depth_sort": (C.c_int, [C.POINTER(TgrParams), C.c_void_p]),
     "tgr_backward_blend": (C.c_int, [C.POINTER(TgrParams), C.c_uint64, C.c_void_p]),
+    "tgr_forward_render_batch": (C.c_int, [C.POINTER(TgrParams), C.POINTER(C.c_uint64), C.c_int32, C.c_void_p]),
+    "tgr_backward_blend_batch": (C.c_int, [C.POINTER(TgrParams), C.POINTER(C.c_uint64), C.c_int32, C.c_void_p]),
     "tgr_backward_preprocess_batch": (C.c_int, [C.POINTER(TgrParams), C.POINTER(C.c_uint64), C.c_int32,
                                                 C.POINTER(TgrBinding), C.c_int32, C.c_int32, C.c_void_p]),
     "tgr_read_header": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32 * 4), C.c_void_p]),

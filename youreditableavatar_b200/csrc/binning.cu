@@ -25,11 +25,18 @@ __device__ __forceinline__ void stv(uint32_t* p, uint32_t v) {
   asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(EMIT_THREADS) emit_kernel(int P, const uint32_t* __restrict__ order,
-                                                            const ushort4* __restrict__ rect, uint32_t grid_w,
-                                                            uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                                                            uint32_t cap, GeomHeader* __restrict__ header,
-                                                            uint32_t* __restrict__ scan_state) {
+__global__ void __launch_bounds__(EMIT_THREADS) emit_kernel(const __grid_constant__ RenderBatch rb) {
+  const RenderView& rv = rb.v[blockIdx.y];
+  const int P = rv.P;
+  if ((uint32_t)blockIdx.x * EMIT_TILE >= (uint32_t)P) return;   // the grid is sized for the largest view
+  const uint32_t* __restrict__ order = rv.order;
+  const ushort4* __restrict__ rect = rv.rect;
+  const uint32_t grid_w = (rv.W + TILE - 1) / TILE;
+  uint32_t* __restrict__ keys = rv.key_a;
+  uint32_t* __restrict__ vals = rv.val_a;
+  const uint32_t cap = rv.cap;
+  GeomHeader* __restrict__ header = rv.header;
+  uint32_t* __restrict__ scan_state = rv.scan_state;
   __shared__ uint32_t s_tile, s_prefix;
   __shared__ uint32_t s_warp[EMIT_THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -136,20 +143,26 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_kernel(int P, const uint32_
   }
 }
 
-int launch_emit(const tgr_params& p, const GeomView& g, const BinView& b, uint64_t cap, cudaStream_t s) {
-  const int ntiles = (p.P + EMIT_TILE - 1) / EMIT_TILE;
+int launch_emit(const RenderBatch& rb, cudaStream_t s) {
+  int ntiles = 0;
+  for (int v = 0; v < rb.V; ++v) {
+    const int nt = (rb.v[v].P + EMIT_TILE - 1) / EMIT_TILE;
+    if (nt > 0) cudaMemsetAsync(rb.v[v].scan_state, 0, (size_t)(nt + 1) * 4, s);
+    ntiles = std::max(ntiles, nt);
+  }
   if (ntiles == 0) return 0;
-  cudaMemsetAsync(g.scan_state, 0, (size_t)(ntiles + 1) * 4, s);
-  const uint32_t gw = (p.W + TILE - 1) / TILE;
-  emit_kernel<<<ntiles, EMIT_THREADS, 0, s>>>(p.P, g.order, g.rect, gw, b.key_a, b.val_a,
-                                              (uint32_t)std::min<uint64_t>(cap, 0xffffffffull), g.header, g.scan_state);
+  emit_kernel<<<dim3(ntiles, rb.V), EMIT_THREADS, 0, s>>>(rb);
   count_launch();
-  return check_launch("emit", p.debug != 0, s);
+  return check_launch("emit", false, s);
 }
 
 // per-tile [start,end) in the tile-sorted instance list; ranges must be zero-initialised
-__global__ void __launch_bounds__(256) ranges_kernel(const uint32_t* __restrict__ keys, uint32_t cap,
-                                                     const GeomHeader* __restrict__ header, uint2* __restrict__ ranges) {
+__global__ void __launch_bounds__(256) ranges_kernel(const __grid_constant__ RenderBatch rb) {
+  const RenderView& rv = rb.v[blockIdx.y];
+  const uint32_t* __restrict__ keys = rv.sorted_keys;
+  const uint32_t cap = rv.cap;
+  const GeomHeader* __restrict__ header = rv.header;
+  uint2* __restrict__ ranges = rv.ranges;
   const uint32_t L = min(header->num_rendered, cap);
   if (header->overflow) return;
   const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -167,15 +180,16 @@ __global__ void __launch_bounds__(256) ranges_kernel(const uint32_t* __restrict_
   if (idx == L - 1) ranges[cur].y = L;
 }
 
-int launch_ranges(const tgr_params& p, const GeomView& g, const uint32_t* sorted_keys, const ImageView& im,
-                  uint64_t cap, cudaStream_t s) {
-  const uint32_t T = ((p.W + TILE - 1) / TILE) * ((p.H + TILE - 1) / TILE);
-  cudaMemsetAsync(im.ranges, 0, (size_t)T * sizeof(uint2), s);
-  if (cap == 0) return 0;
-  const unsigned blocks = (unsigned)((cap + 255) / 256);
-  ranges_kernel<<<blocks, 256, 0, s>>>(sorted_keys, (uint32_t)cap, g.header, im.ranges);
+int launch_ranges(const RenderBatch& rb, cudaStream_t s) {
+  uint32_t cap_max = 0;
+  for (int v = 0; v < rb.V; ++v) {
+    cudaMemsetAsync(rb.v[v].ranges, 0, (size_t)rb.v[v].T * sizeof(uint2), s);
+    cap_max = std::max(cap_max, rb.v[v].cap);
+  }
+  if (cap_max == 0) return 0;
+  ranges_kernel<<<dim3((cap_max + 255) / 256, rb.V), 256, 0, s>>>(rb);
   count_launch();
-  return check_launch("ranges", p.debug != 0, s);
+  return check_launch("ranges", false, s);
 }
 
 // Heaviest-first tile order.  The block scheduler hands consecutive CTAs to different SMs, so rendering tiles
@@ -183,16 +197,19 @@ int launch_ranges(const tgr_params& p, const GeomView& g, const uint32_t* sorted
 // only ~15-20% of the tiles; with row-major order ncu showed SMs idle ~48% of the blend kernels).
 // One CTA, bucketed counting sort on weight/8 (4096 buckets, exact order inside a bucket is irrelevant).
 constexpr int TO_BUCKETS = 4096;
-__global__ void __launch_bounds__(1024) tile_order_kernel(const uint2* __restrict__ ranges,
-                                                          const uint32_t* __restrict__ tile_last, uint32_t T,
-                                                          uint32_t* __restrict__ order,
-                                                          uint32_t* __restrict__ queue_counters,
-                                                          uint32_t* __restrict__ seg_base) {
+__global__ void __launch_bounds__(1024) tile_order_kernel(const __grid_constant__ RenderBatch rb) {
+  const RenderView& rv = rb.v[blockIdx.x];   // one CTA per view
+  const uint2* __restrict__ ranges = rv.ranges;
+  const uint32_t* tile_last = nullptr;
+  const uint32_t T = rv.T;
+  uint32_t* __restrict__ order = rv.order_fwd;
+  uint32_t* __restrict__ queue_counters = blockIdx.x == 0 ? rb.queue_counters : nullptr;
+  uint32_t* __restrict__ seg_base = rv.seg_base;
   __shared__ uint32_t s_cnt[TO_BUCKETS];
   __shared__ uint32_t s_warp[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < TO_BUCKETS; i += 1024) s_cnt[i] = 0;
-  if (tid < MAX_QUEUES) queue_counters[tid] = 0;
+  if (queue_counters != nullptr && tid < MAX_QUEUES) queue_counters[tid] = 0;
   __syncthreads();
   auto bucket_of = [&](uint32_t t) {
     const uint2 r = ranges[t];
@@ -262,10 +279,14 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const uint2* __restric
 }
 
 // Backward work units: tile t contributes ceil(min(tile_last_t, len_t) / SEG) units (tile, segment).
-__global__ void __launch_bounds__(1024) unit_build_kernel(const uint2* __restrict__ ranges,
-                                                          const uint32_t* __restrict__ tile_last, uint32_t T,
-                                                          uint2* __restrict__ units, uint32_t units_cap,
-                                                          uint32_t* __restrict__ unit_count) {
+__global__ void __launch_bounds__(1024) unit_build_kernel(const __grid_constant__ RenderBatch rb) {
+  const RenderView& rv = rb.v[blockIdx.x];   // one CTA per view
+  const uint2* __restrict__ ranges = rv.ranges;
+  const uint32_t* __restrict__ tile_last = rv.tile_last;
+  const uint32_t T = rv.T;
+  uint2* __restrict__ units = rv.units;
+  const uint32_t units_cap = rv.units_cap;
+  uint32_t* __restrict__ unit_count = rv.unit_count;
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -298,9 +319,8 @@ __global__ void __launch_bounds__(1024) unit_build_kernel(const uint2* __restric
   if (tid == 0) *unit_count = min(s_carry, units_cap);
 }
 
-int launch_unit_build(const uint2* ranges, const uint32_t* tile_last, uint32_t T, uint2* units, uint32_t units_cap,
-                      uint32_t* unit_count, cudaStream_t s) {
-  unit_build_kernel<<<1, 1024, 0, s>>>(ranges, tile_last, T, units, units_cap, unit_count);
+int launch_unit_build(const RenderBatch& rb, cudaStream_t s) {
+  unit_build_kernel<<<rb.V, 1024, 0, s>>>(rb);
   count_launch();
   return check_launch("unit_build", false, s);
 }
@@ -319,9 +339,8 @@ uint32_t num_queues() {
   return cached;
 }
 
-int launch_tile_order(const uint2* ranges, const uint32_t* tile_last, uint32_t T, uint32_t* order,
-                      uint32_t* queue_counters, uint32_t* seg_base, cudaStream_t s) {
-  tile_order_kernel<<<1, 1024, 0, s>>>(ranges, tile_last, T, order, queue_counters, seg_base);
+int launch_tile_order(const RenderBatch& rb, cudaStream_t s) {
+  tile_order_kernel<<<rb.V, 1024, 0, s>>>(rb);
   count_launch();
   return check_launch("tile_order", false, s);
 }

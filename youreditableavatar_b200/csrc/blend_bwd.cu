@@ -23,7 +23,7 @@
 
 namespace tgr {
 
-constexpr int BL_STAGES = 3;  // shared-memory ring depth (how far consumers may drift apart)
+constexpr int BL_STAGES = 4;  // shared-memory ring depth (how far consumers may drift apart)
 
 constexpr int BG = 2;  // candidates evaluated together by a consumer warp
 
@@ -35,31 +35,33 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 }
 
 template <bool EXTRAS>
-__global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint2* __restrict__ units,
-                                                               const uint32_t* __restrict__ unit_count,
-                                                               const uint2* __restrict__ ranges,
-                                                               const uint32_t* __restrict__ point_list, int W, int H,
-                                                               const float* __restrict__ bg,
-                                                               const float4* __restrict__ xy_ext,
-                                                               const float4* __restrict__ conic_opacity,
-                                                               const float4* __restrict__ rgb_depth,
-                                                               const float4* __restrict__ final_state,
-                                                               const float* __restrict__ final_depth,
-                                                               const uint32_t* __restrict__ n_contrib,
-                                                               const uint32_t* __restrict__ tile_last,
-                                                               const uint32_t* __restrict__ seg_base,
-                                                               const float4* __restrict__ ckpt,
-                                                               const float* __restrict__ ckpt_z,
-                                                               const float* __restrict__ dL_dpix,
-                                                               const float* __restrict__ dL_ddepth,
-                                                               const float* __restrict__ dL_dalpha_img,
-                                                               float* __restrict__ grad_acc) {
+__global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const __grid_constant__ RenderBatch rb) {
+  const RenderView& rv = rb.v[blockIdx.y];   // one launch serves every view of the batch
+  const uint2* __restrict__ units = rv.units;
+  const uint32_t* __restrict__ unit_count = rv.unit_count;
+  const uint2* __restrict__ ranges = rv.ranges;
+  const uint32_t* __restrict__ point_list = rv.point_list;
+  const int W = rv.W, H = rv.H;
+  const float* __restrict__ bg = rv.bg;
+  const float4* __restrict__ xy_ext = rv.xy_ext;
+  const float4* __restrict__ conic_opacity = rv.conic_opacity;
+  const float4* __restrict__ rgb_depth = rv.rgb_depth;
+  const float4* __restrict__ final_state = rv.final_state;
+  const float* __restrict__ final_depth = rv.final_z;
+  const uint32_t* __restrict__ n_contrib = rv.n_contrib;
+  const uint32_t* __restrict__ tile_last = rv.tile_last;
+  const uint32_t* __restrict__ seg_base = rv.seg_base;
+  const float4* __restrict__ ckpt = rv.ckpt;
+  const float* __restrict__ ckpt_z = rv.ckpt_z;
+  const float* __restrict__ dL_dpix = rv.dL_dpix;
+  const float* __restrict__ dL_ddepth = rv.dL_ddepth;
+  const float* __restrict__ dL_dalpha_img = rv.dL_dalpha;
+  float* __restrict__ grad_acc = rv.grad_acc;
   __shared__ uint32_t s_id[BL_STAGES][BL_BATCH + 1];
   __shared__ __align__(16) float4 s_xy[BL_STAGES][BL_BATCH + 1];   // +1: the PAD_ENTRY dummy record
   __shared__ __align__(16) float4 s_co[BL_STAGES][BL_BATCH + 1];
   __shared__ __align__(16) float4 s_cd[BL_STAGES][BL_BATCH + 1];
   __shared__ __align__(4) uint8_t s_list[8][SUB_GROUPS * LIST_BYTES];  // per consumer warp and lane group: candidates of the current batch
-  __shared__ __align__(8) uint64_t s_full[BL_STAGES], s_empty[BL_STAGES];
 
   // ---- work unit = (tile, segment): list positions [seg*SEG, min((seg+1)*SEG, total)) of one tile -------
   if (blockIdx.x >= *unit_count) return;
@@ -76,10 +78,11 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint2* __re
   if (count <= 0) return;
   const int rounds = (count + BL_BATCH - 1) / BL_BATCH;
 
+  __shared__ __align__(8) uint64_t s_full[BL_STAGES], s_empty[BL_STAGES];
   if (tid == 0) {
     for (int s = 0; s < BL_STAGES; ++s) {
-      mbar_init(&s_full[s], 32);
-      mbar_init(&s_empty[s], 8);
+      mbar_init(&s_full[s], 32);   // every producer lane's copies arrive (cp.async.mbarrier.arrive)
+      mbar_init(&s_empty[s], 8);   // one arrival per consumer warp
     }
   }
   if (tid < BL_STAGES) {
@@ -232,28 +235,17 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const uint2* __re
   }
 }
 
-int launch_blend_bwd(const tgr_params& p, const GeomView& g, const uint32_t* point_list, const ImageView& im,
-                     const BinView& b, cudaStream_t s) {
-  const uint32_t T = (uint32_t)((p.W + TILE - 1) / TILE) * ((p.H + TILE - 1) / TILE);
-  const uint32_t ucap = (uint32_t)std::min<uint64_t>(b.units_cap, 0x7fffffffull);
-  if (int rc = launch_unit_build(im.ranges, im.tile_last, T, b.units, ucap, im.unit_count, s)) return rc;
-  // one CTA per work unit; the grid is sized for the capacity, surplus CTAs exit on the device-side count
-  const dim3 grid(ucap, 1, 1);
-  const bool ex = p.extras && (p.dL_dout_depth || p.dL_dout_alpha);
-  if (ex)
-    blend_bwd_kernel<true><<<grid, BL_THREADS, 0, s>>>(b.units, im.unit_count, im.ranges, point_list, p.W, p.H,
-                                                       p.background, g.xy_ext, g.conic_opacity, g.rgb_depth,
-                                                       im.final_state, im.final_z, im.n_contrib, im.tile_last,
-                                                       im.seg_base, b.ckpt, b.ckpt_z, p.dL_dout_color, p.dL_dout_depth,
-                                                       p.dL_dout_alpha, b.grad_acc);
-  else
-    blend_bwd_kernel<false><<<grid, BL_THREADS, 0, s>>>(b.units, im.unit_count, im.ranges, point_list, p.W, p.H,
-                                                        p.background, g.xy_ext, g.conic_opacity, g.rgb_depth,
-                                                        im.final_state, nullptr, im.n_contrib, im.tile_last,
-                                                        im.seg_base, b.ckpt, b.ckpt_z, p.dL_dout_color, nullptr, nullptr,
-                                                        b.grad_acc);
+int launch_blend_bwd(const RenderBatch& rb, bool extras, bool debug, cudaStream_t s) {
+  if (int rc = launch_unit_build(rb, s)) return rc;
+  // one CTA per work unit; the grid is sized for the largest capacity, surplus CTAs exit on the device-side count
+  uint32_t ucap = 0;
+  for (int v = 0; v < rb.V; ++v) ucap = std::max(ucap, rb.v[v].units_cap);
+  if (ucap == 0) return 0;
+  const dim3 grid(ucap, rb.V, 1);
+  if (extras) blend_bwd_kernel<true><<<grid, BL_THREADS, 0, s>>>(rb);
+  else blend_bwd_kernel<false><<<grid, BL_THREADS, 0, s>>>(rb);
   count_launch();
-  return check_launch("blend_bwd", p.debug != 0, s);
+  return check_launch("blend_bwd", debug, s);
 }
 
 }  // namespace tgr

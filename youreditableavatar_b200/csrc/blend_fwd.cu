@@ -28,21 +28,7 @@ constexpr int BL_STAGES = 4;  // shared-memory ring depth (how far consumers may
 
 
 template <bool EXTRAS>
-__global__ void __launch_bounds__(BL_THREADS) blend_fwd_kernel(const uint32_t* __restrict__ order, uint32_t* __restrict__ queue_counters,
-                                                               uint32_t num_tiles, uint32_t num_queues,
-                                                               const uint2* __restrict__ ranges,
-                                                               const uint32_t* __restrict__ point_list, int W, int H,
-                                                               const float4* __restrict__ xy_ext,
-                                                               const float4* __restrict__ conic_opacity,
-                                                               const float4* __restrict__ rgb_depth,
-                                                               const float* __restrict__ bg, float* __restrict__ final_T,
-                                                               uint32_t* __restrict__ n_contrib,
-                                                               uint32_t* __restrict__ tile_last,
-                                                               float* __restrict__ out_color, float* __restrict__ out_depth,
-                                                               float* __restrict__ out_alpha,
-                                                               const uint32_t* __restrict__ seg_base,
-                                                               float4* __restrict__ ckpt, float* __restrict__ ckpt_z,
-                                                               float4* __restrict__ final_state, float* __restrict__ final_z) {
+__global__ void __launch_bounds__(BL_THREADS) blend_fwd_kernel(const __grid_constant__ RenderBatch rb, uint32_t num_queues) {
   __shared__ __align__(16) float4 s_xy[BL_STAGES][BL_BATCH + 1];   // x, y, hx, hy   (+1: the PAD_ENTRY dummy)
   __shared__ __align__(16) float4 s_co[BL_STAGES][BL_BATCH + 1];   // conic xx, xy, yy, opacity
   __shared__ __align__(16) float4 s_cd[BL_STAGES][BL_BATCH + 1];   // r, g, b, depth
@@ -53,15 +39,41 @@ __global__ void __launch_bounds__(BL_THREADS) blend_fwd_kernel(const uint32_t* _
   __shared__ uint32_t s_last[8];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t tiles_x = (W + TILE - 1) / TILE;
+  // Work item = one tile of one view.  Global rank r of the batch's queue -> view r % V, rank r / V in that view's
+  // heaviest-first tile order, so the heaviest tiles of every view start first and one launch balances all views.
   __shared__ uint32_t s_rank;
   if (warp == 0) {
-    const uint32_t r = fetch_tile_rank(queue_counters, num_tiles, num_queues, lane);
+    const uint32_t V = (uint32_t)rb.V;
+    uint32_t r;
+    while (true) {
+      r = fetch_tile_rank(rb.queue_counters, V * rb.T_max, num_queues, lane);
+      if (r == NO_TILE || r / V < rb.v[r % V].T) break;   // ranks beyond a smaller view's tile count are skipped
+    }
     if (lane == 0) s_rank = r;
   }
   __syncthreads();
   if (s_rank == NO_TILE) return;
-  const uint32_t tile_id = order[s_rank];
+  const RenderView& rv = rb.v[s_rank % (uint32_t)rb.V];
+  const int W = rv.W, H = rv.H;
+  const uint2* __restrict__ ranges = rv.ranges;
+  const uint32_t* __restrict__ point_list = rv.point_list;
+  const float4* __restrict__ xy_ext = rv.xy_ext;
+  const float4* __restrict__ conic_opacity = rv.conic_opacity;
+  const float4* __restrict__ rgb_depth = rv.rgb_depth;
+  const float* __restrict__ bg = rv.bg;
+  float* __restrict__ final_T = rv.final_T;
+  uint32_t* __restrict__ n_contrib = rv.n_contrib;
+  uint32_t* __restrict__ tile_last = rv.tile_last;
+  float* __restrict__ out_color = rv.out_color;
+  float* __restrict__ out_depth = rv.out_depth;
+  float* __restrict__ out_alpha = rv.out_alpha;
+  const uint32_t* __restrict__ seg_base = rv.seg_base;
+  float4* __restrict__ ckpt = rv.ckpt;
+  float* __restrict__ ckpt_z = rv.ckpt_z;
+  float4* __restrict__ final_state = rv.final_state;
+  float* __restrict__ final_z = rv.final_z;
+  const uint32_t tiles_x = (W + TILE - 1) / TILE;
+  const uint32_t tile_id = rv.order_fwd[s_rank / (uint32_t)rb.V];
   const uint32_t tile_bx = tile_id % tiles_x, tile_by = tile_id / tiles_x;
   const uint2 range = ranges[tile_id];
   const int total = (int)(range.y - range.x);
@@ -69,7 +81,7 @@ __global__ void __launch_bounds__(BL_THREADS) blend_fwd_kernel(const uint32_t* _
 
   if (tid == 0) {
     for (int s = 0; s < BL_STAGES; ++s) {
-      mbar_init(&s_full[s], 32);   // every producer lane arrives after its stores
+      mbar_init(&s_full[s], 32);   // every producer lane's copies arrive (cp.async.mbarrier.arrive)
       mbar_init(&s_empty[s], 8);   // one arrival per consumer warp
       s_stop[s] = 0;
     }
@@ -190,7 +202,7 @@ __global__ void __launch_bounds__(BL_THREADS) blend_fwd_kernel(const uint32_t* _
   // tile-wide maximum of last_contributor: lets the backward start at the last useful list entry
   const uint32_t wl = __reduce_max_sync(0xffffffffu, inside ? last_contributor : 0u);
   if (lane == 0) s_last[warp] = wl;
-  bar_sync_named(1, 256);  // the eight consumer warps only (the producer has left)
+  bar_sync_named(BAR_EPILOGUE, 256);  // the eight consumer warps only (the producer has left)
   if (tid == 0) {
     uint32_t m = 0;
 #pragma unroll
@@ -199,23 +211,14 @@ __global__ void __launch_bounds__(BL_THREADS) blend_fwd_kernel(const uint32_t* _
   }
 }
 
-int launch_blend_fwd(const tgr_params& p, const GeomView& g, const uint32_t* point_list, const ImageView& im,
-                     const BinView& b, cudaStream_t s) {
-  const uint32_t T = (uint32_t)((p.W + TILE - 1) / TILE) * ((p.H + TILE - 1) / TILE);
-  if (int rc = launch_tile_order(im.ranges, nullptr, T, im.order_fwd, im.queue_counters, im.seg_base, s)) return rc;
-  const dim3 grid(T, 1, 1);
-  if (p.extras && p.out_depth && p.out_alpha)
-    blend_fwd_kernel<true><<<grid, BL_THREADS, 0, s>>>(im.order_fwd, im.queue_counters, T, num_queues(), im.ranges, point_list, p.W, p.H, g.xy_ext, g.conic_opacity,
-                                                       g.rgb_depth, p.background, im.final_T, im.n_contrib,
-                                                       im.tile_last, p.out_color, p.out_depth, p.out_alpha, im.seg_base, b.ckpt, b.ckpt_z,
-                                                       im.final_state, im.final_z);
-  else
-    blend_fwd_kernel<false><<<grid, BL_THREADS, 0, s>>>(im.order_fwd, im.queue_counters, T, num_queues(), im.ranges, point_list, p.W, p.H, g.xy_ext, g.conic_opacity,
-                                                        g.rgb_depth, p.background, im.final_T, im.n_contrib,
-                                                        im.tile_last, p.out_color, nullptr, nullptr, im.seg_base, b.ckpt, b.ckpt_z,
-                                                        im.final_state, im.final_z);
+int launch_blend_fwd(const RenderBatch& rb, bool extras, bool debug, cudaStream_t s) {
+  if (int rc = launch_tile_order(rb, s)) return rc;
+  // one CTA per (view, tile); the device-side queue hands out the work
+  const dim3 grid(rb.T_max * (uint32_t)rb.V, 1, 1);
+  if (extras) blend_fwd_kernel<true><<<grid, BL_THREADS, 0, s>>>(rb, num_queues());
+  else blend_fwd_kernel<false><<<grid, BL_THREADS, 0, s>>>(rb, num_queues());
   count_launch();
-  return check_launch("blend_fwd", p.debug != 0, s);
+  return check_launch("blend_fwd", debug, s);
 }
 
 }  // namespace tgr

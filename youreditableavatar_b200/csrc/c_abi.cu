@@ -141,16 +141,110 @@ static int check_same_gaussians(const tgr_params* a, const tgr_params* b) {
   return 0;
 }
 
-static int depth_sort(const tgr_params* p, const GeomView& g, cudaStream_t s) {
-  // (depth bits, id) order of the Gaussians: positive floats compare like their bit patterns; bit 31 is 0
-  bool in_b = false;
-  prof_begin(TGR_STAGE_DEPTH_SORT, s);
-  if (int rc = launch_sort_pairs((uint64_t)p->P, nullptr, g.depth_key, g.order, g.key_alt, g.val_alt, true, 0, 32,
-                                 g.sort_temp, s, &in_b)) return rc;
-  prof_end(TGR_STAGE_DEPTH_SORT, s);
-  if (in_b) { set_error("internal: depth sort must end in buffer A"); return 3; }
+// (depth bits, id) order of the Gaussians of every view: positive floats compare like their bit patterns (bit 31
+// is 0).  One batched launch sequence for all views.
+static int depth_sort_views(const tgr_params* views, int32_t n, cudaStream_t s) {
+  for (int32_t v0 = 0; v0 < n; v0 += MAX_BATCH) {
+    SortBatch sb{};
+    sb.V = std::min<int32_t>(MAX_BATCH, n - v0);
+    for (int32_t k = 0; k < sb.V; ++k) {
+      const tgr_params& p = views[v0 + k];
+      GeomView g = carve_geom(p.geom_buffer, p.P);
+      sb.s[k] = SortSeg{g.depth_key, g.order, g.key_alt, g.val_alt, g.sort_temp, nullptr, (uint32_t)p.P};
+    }
+    bool in_b = false;
+    prof_begin(TGR_STAGE_DEPTH_SORT, s);
+    if (int rc = launch_sort_pairs_batch(sb, true, 0, 32, s, &in_b)) return rc;
+    prof_end(TGR_STAGE_DEPTH_SORT, s);
+    if (in_b) { set_error("internal: depth sort must end in buffer A"); return 3; }
+  }
   return 0;
 }
+
+static RenderView make_render_view(const tgr_params& p, uint64_t cap, bool tile_sorted_in_b) {
+  GeomView g = carve_geom(p.geom_buffer, p.P);
+  BinView b = carve_bin(p.binning_buffer, p.P, cap, p.W, p.H);
+  ImageView im = carve_image(p.image_buffer, p.W, p.H);
+  RenderView r{};
+  r.P = p.P; r.W = p.W; r.H = p.H;
+  r.T = (uint32_t)((p.W + TILE - 1) / TILE) * ((p.H + TILE - 1) / TILE);
+  r.cap = (uint32_t)std::min<uint64_t>(cap, 0xffffffffull);
+  r.units_cap = (uint32_t)std::min<uint64_t>(b.units_cap, 0x7fffffffull);
+  r.header = g.header; r.order = g.order; r.rect = g.rect;
+  r.xy_ext = g.xy_ext; r.conic_opacity = g.conic_opacity; r.rgb_depth = g.rgb_depth; r.scan_state = g.scan_state;
+  r.key_a = b.key_a; r.val_a = b.val_a;
+  r.sorted_keys = tile_sorted_in_b ? b.key_b : b.key_a;
+  r.point_list = tile_sorted_in_b ? b.val_b : b.val_a;
+  r.grad_acc = b.grad_acc; r.ckpt = b.ckpt; r.ckpt_z = b.ckpt_z; r.units = b.units;
+  r.ranges = im.ranges; r.tile_last = im.tile_last; r.order_fwd = im.order_fwd; r.seg_base = im.seg_base;
+  r.unit_count = im.unit_count; r.final_T = im.final_T; r.n_contrib = im.n_contrib; r.final_state = im.final_state;
+  r.final_z = im.final_z;
+  r.bg = p.background; r.out_color = p.out_color; r.out_depth = p.out_depth; r.out_alpha = p.out_alpha;
+  r.dL_dpix = p.dL_dout_color; r.dL_ddepth = p.dL_dout_depth; r.dL_dalpha = p.dL_dout_alpha;
+  return r;
+}
+
+// The tile sort of a batch must use one bit range; views whose tile counts need a different number of bits are
+// rendered in separate groups (square same-size batches — the normal case — form one group).
+static bool same_group(const tgr_params& a, const tgr_params& b) {
+  auto tb = [](const tgr_params& p) { return tile_bits((uint32_t)((p.W + TILE - 1) / TILE) * ((p.H + TILE - 1) / TILE)); };
+  const bool ea = a.extras && a.out_depth && a.out_alpha, eb = b.extras && b.out_depth && b.out_alpha;
+  return tb(a) == tb(b) && ea == eb;
+}
+
+// emit -> tile sort -> ranges -> blend for a group of <= MAX_BATCH views, every stage ONE launch for the group
+static int render_group(const tgr_params* views, const uint64_t* caps, int32_t n, cudaStream_t s) {
+  const tgr_params& p0 = views[0];
+  const uint32_t T0 = (uint32_t)((p0.W + TILE - 1) / TILE) * ((p0.H + TILE - 1) / TILE);
+  SortPlan plan = make_sort_plan(0, tile_bits(T0));
+  const bool in_b = (plan.npasses & 1) != 0;
+  RenderBatch rb{};
+  rb.V = n;
+  bool any = false;
+  for (int32_t k = 0; k < n; ++k) {
+    rb.v[k] = make_render_view(views[k], caps[k], in_b);
+    rb.T_max = std::max(rb.T_max, rb.v[k].T);
+    any = any || (views[k].P > 0 && caps[k] > 0);
+  }
+  rb.queue_counters = carve_image(p0.image_buffer, p0.W, p0.H).queue_counters;
+  if (any) {
+    prof_begin(TGR_STAGE_EMIT, s);
+    if (int rc = launch_emit(rb, s)) return rc;
+    prof_end(TGR_STAGE_EMIT, s);
+    SortBatch sb{};
+    sb.V = n;
+    for (int32_t k = 0; k < n; ++k) {
+      BinView b = carve_bin(views[k].binning_buffer, views[k].P, caps[k], views[k].W, views[k].H);
+      GeomView g = carve_geom(views[k].geom_buffer, views[k].P);
+      sb.s[k] = SortSeg{b.key_a, b.val_a, b.key_b, b.val_b, b.sort_temp, &g.header->num_rendered, rb.v[k].cap};
+    }
+    prof_begin(TGR_STAGE_TILE_SORT, s);
+    if (int rc = launch_sort_pairs_batch(sb, false, 0, tile_bits(T0), s, nullptr)) return rc;
+    prof_end(TGR_STAGE_TILE_SORT, s);
+  }
+  prof_begin(TGR_STAGE_RANGES, s);
+  if (int rc = launch_ranges(rb, s)) return rc;
+  prof_end(TGR_STAGE_RANGES, s);
+  const bool extras = p0.extras && p0.out_depth && p0.out_alpha;
+  prof_begin(TGR_STAGE_BLEND_FWD, s);
+  if (int rc = launch_blend_fwd(rb, extras, p0.debug != 0, s)) return rc;
+  prof_end(TGR_STAGE_BLEND_FWD, s);
+  return 0;
+}
+
+extern "C++" {
+template <typename GroupFn>
+static int for_each_group(const tgr_params* views, const uint64_t* caps, int32_t n, GroupFn fn) {
+  int32_t v0 = 0;
+  while (v0 < n) {
+    int32_t v1 = v0 + 1;
+    while (v1 < n && v1 - v0 < MAX_BATCH && same_group(views[v0], views[v1])) ++v1;
+    if (int rc = fn(views + v0, caps + v0, v1 - v0)) return rc;
+    v0 = v1;
+  }
+  return 0;
+}
+}  // extern "C++"
 
 // One preprocess launch per chunk of <= TGR_MAX_BATCH views; instance counts go to each view's pinned slot.
 static int preprocess_views(const tgr_params* views, int32_t n, const tgr_binding* bind, cudaStream_t s) {
@@ -195,7 +289,7 @@ int tgr_forward_preprocess(const tgr_params* p, const tgr_binding* bind, void* s
   if (!p) { set_error("null params"); return 1; }
   if (int rc = preprocess_views(p, 1, bind, s)) return rc;
   if (p->P == 0) return 0;
-  if (int rc = depth_sort(p, carve_geom(p->geom_buffer, p->P), s)) return rc;
+  if (int rc = depth_sort_views(p, 1, s)) return rc;
   return check_launch("forward_preprocess", p->debug != 0, s);
 }
 
@@ -210,7 +304,7 @@ int tgr_forward_depth_sort(const tgr_params* p, void* stream) {
   if (int rc = validate(p, false, 0)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (p->P == 0) return 0;
-  if (int rc = depth_sort(p, carve_geom(p->geom_buffer, p->P), s)) return rc;
+  if (int rc = depth_sort_views(p, 1, s)) return rc;
   return check_launch("forward_depth_sort", p->debug != 0, s);
 }
 
@@ -231,40 +325,40 @@ static const uint32_t* sorted_vals(const tgr_params* p, const BinView& b, bool* 
 int tgr_forward_render(const tgr_params* p, uint64_t cap, void* stream) {
   if (int rc = validate(p, true, cap)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  GeomView g = carve_geom(p->geom_buffer, p->P);
-  BinView b = carve_bin(p->binning_buffer, p->P, cap, p->W, p->H);
-  ImageView im = carve_image(p->image_buffer, p->W, p->H);
-  const uint32_t T = (uint32_t)((p->W + TILE - 1) / TILE) * ((p->H + TILE - 1) / TILE);
-  if (p->P > 0 && cap > 0) {
-    prof_begin(TGR_STAGE_EMIT, s);
-    if (int rc = launch_emit(*p, g, b, cap, s)) return rc;
-    prof_end(TGR_STAGE_EMIT, s);
-    bool in_b = false;
-    prof_begin(TGR_STAGE_TILE_SORT, s);
-    if (int rc = launch_sort_pairs(cap, &g.header->num_rendered, b.key_a, b.val_a, b.key_b, b.val_b, false, 0,
-                                   tile_bits(T), b.sort_temp, s, &in_b)) return rc;
-    prof_end(TGR_STAGE_TILE_SORT, s);
-    prof_begin(TGR_STAGE_RANGES, s);
-    if (int rc = launch_ranges(*p, g, in_b ? b.key_b : b.key_a, im, cap, s)) return rc;
-    prof_end(TGR_STAGE_RANGES, s);
-  } else {
-    cudaMemsetAsync(im.ranges, 0, (size_t)T * sizeof(uint2), s);
-  }
-  const uint32_t* plist = sorted_vals(p, b);
-  prof_begin(TGR_STAGE_BLEND_FWD, s);
-  if (int rc = launch_blend_fwd(*p, g, plist, im, b, s)) return rc;
-  prof_end(TGR_STAGE_BLEND_FWD, s);
+  if (int rc = render_group(p, &cap, 1, s)) return rc;
   return check_launch("forward_render", p->debug != 0, s);
 }
 
-static int backward_blend(const tgr_params* p, uint64_t cap, cudaStream_t s) {
-  if (!p->dL_dout_color) { set_error("dL_dout_color missing"); return 1; }
-  GeomView g = carve_geom(p->geom_buffer, p->P);
-  BinView b = carve_bin(p->binning_buffer, p->P, cap, p->W, p->H);
-  ImageView im = carve_image(p->image_buffer, p->W, p->H);
-  cudaMemsetAsync(b.grad_acc, 0, (size_t)p->P * GRAD_ACC * sizeof(float), s);
+int tgr_forward_render_batch(const tgr_params* views, const uint64_t* caps, int32_t n_views, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!views || !caps || n_views <= 0) { set_error("batch: no views"); return 1; }
+  for (int32_t v = 0; v < n_views; ++v)
+    if (int rc = validate(&views[v], true, caps[v])) return rc;
+  if (views[0].P > 0)
+    if (int rc = depth_sort_views(views, n_views, s)) return rc;
+  if (int rc = for_each_group(views, caps, n_views,
+                              [&](const tgr_params* g, const uint64_t* c, int32_t n) { return render_group(g, c, n, s); }))
+    return rc;
+  return check_launch("forward_render_batch", views[0].debug != 0, s);
+}
+
+// memset of the packed 2-D gradient rows + unit build + blend backward for a group of views (one launch each)
+static int backward_blend_group(const tgr_params* views, const uint64_t* caps, int32_t n, cudaStream_t s) {
+  const tgr_params& p0 = views[0];
+  const uint32_t T0 = (uint32_t)((p0.W + TILE - 1) / TILE) * ((p0.H + TILE - 1) / TILE);
+  const bool in_b = (make_sort_plan(0, tile_bits(T0)).npasses & 1) != 0;
+  RenderBatch rb{};
+  rb.V = n;
+  bool extras = false;
+  for (int32_t k = 0; k < n; ++k) {
+    if (!views[k].dL_dout_color) { set_error("dL_dout_color missing"); return 1; }
+    rb.v[k] = make_render_view(views[k], caps[k], in_b);
+    rb.T_max = std::max(rb.T_max, rb.v[k].T);
+    cudaMemsetAsync(rb.v[k].grad_acc, 0, (size_t)views[k].P * GRAD_ACC * sizeof(float), s);
+    extras = extras || (views[k].extras && (views[k].dL_dout_depth || views[k].dL_dout_alpha));
+  }
   prof_begin(TGR_STAGE_BLEND_BWD, s);
-  if (int rc = launch_blend_bwd(*p, g, sorted_vals(p, b), im, b, s)) return rc;
+  if (int rc = launch_blend_bwd(rb, extras, p0.debug != 0, s)) return rc;
   prof_end(TGR_STAGE_BLEND_BWD, s);
   return 0;
 }
@@ -273,7 +367,7 @@ int tgr_backward(const tgr_params* p, const tgr_binding* bind, uint64_t cap, voi
   if (int rc = validate(p, true, cap)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (p->P == 0) return 0;
-  if (int rc = backward_blend(p, cap, s)) return rc;
+  if (int rc = backward_blend_group(p, &cap, 1, s)) return rc;
   ViewBatch vb{};
   vb.V = 1;
   vb.first = 0;
@@ -289,8 +383,21 @@ int tgr_backward_blend(const tgr_params* p, uint64_t cap, void* stream) {
   if (int rc = validate(p, true, cap)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (p->P == 0) return 0;
-  if (int rc = backward_blend(p, cap, s)) return rc;
+  if (int rc = backward_blend_group(p, &cap, 1, s)) return rc;
   return check_launch("backward_blend", p->debug != 0, s);
+}
+
+int tgr_backward_blend_batch(const tgr_params* views, const uint64_t* caps, int32_t n_views, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!views || !caps || n_views <= 0) { set_error("batch: no views"); return 1; }
+  for (int32_t v = 0; v < n_views; ++v)
+    if (int rc = validate(&views[v], true, caps[v])) return rc;
+  if (views[0].P == 0) return 0;
+  if (int rc = for_each_group(views, caps, n_views, [&](const tgr_params* g, const uint64_t* c, int32_t n) {
+        return backward_blend_group(g, c, n, s);
+      }))
+    return rc;
+  return check_launch("backward_blend_batch", views[0].debug != 0, s);
 }
 
 int tgr_backward_preprocess_batch(const tgr_params* views, const uint64_t* caps, int32_t n_views, const tgr_binding* bind,

@@ -202,6 +202,73 @@ struct ViewBatch {
   ViewDesc v[MAX_BATCH];
 };
 
+// Everything the binning and blend kernels need to know about one view of a batch.  Those kernels take the whole
+// table as a __grid_constant__ parameter and pick their view from blockIdx.y (or from the work item), so ONE launch
+// serves every view of the batch: the per-view launches of a 1 M-Gaussian view are individually too small to fill
+// 148 SMs (sorts, scans) or end in a long single-tile tail (blending).
+struct RenderView {
+  int32_t P, W, H;
+  uint32_t T;               // tiles of this view
+  uint32_t cap;             // instance capacity of the binning buffer
+  uint32_t units_cap;
+  // geometry records
+  GeomHeader* header;
+  const uint32_t* order;    // Gaussian ids in (depth, id) order
+  const ushort4* rect;
+  const float4* xy_ext;
+  const float4* conic_opacity;
+  const float4* rgb_depth;
+  uint32_t* scan_state;
+  // binning
+  uint32_t* key_a;
+  uint32_t* val_a;
+  const uint32_t* sorted_keys;   // tile ids after the tile sort
+  const uint32_t* point_list;    // Gaussian ids after the tile sort
+  float* grad_acc;
+  float4* ckpt;
+  float* ckpt_z;
+  uint2* units;
+  // image state
+  uint2* ranges;
+  uint32_t* tile_last;
+  uint32_t* order_fwd;
+  uint32_t* seg_base;
+  uint32_t* unit_count;
+  float* final_T;
+  uint32_t* n_contrib;
+  float4* final_state;
+  float* final_z;
+  // user tensors
+  const float* bg;
+  float* out_color;
+  float* out_depth;
+  float* out_alpha;
+  const float* dL_dpix;
+  const float* dL_ddepth;
+  const float* dL_dalpha;
+};
+struct RenderBatch {
+  int32_t V;
+  uint32_t T_max;            // largest tile count of the batch
+  uint32_t* queue_counters;  // [MAX_QUEUES] per-SM work-queue cursors shared by the batch (zeroed by tile_order)
+  RenderView v[MAX_BATCH];
+};
+
+// A batch of independent radix sorts (sort.cu): one segment per view.
+struct SortSeg {
+  uint32_t* keys_a;
+  uint32_t* vals_a;
+  uint32_t* keys_b;
+  uint32_t* vals_b;
+  uint32_t* temp;          // sort_temp_bytes(n_host)
+  const uint32_t* n_dev;   // optional device-side element count (min'ed with n_host)
+  uint32_t n_host;
+};
+struct SortBatch {
+  int32_t V;
+  SortSeg s[MAX_BATCH];
+};
+
 // camera block staged in shared memory by the batched kernels: [view 16 | proj 16 | campos 3 | pad] per view
 constexpr int CAM_FLOATS = 36;
 
@@ -326,18 +393,15 @@ int launch_preprocess(const tgr_params& p, const tgr_binding* bind, const ViewBa
 int launch_sort_pairs(uint64_t n_host, const uint32_t* n_dev, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b,
                       uint32_t* vals_b, bool iota_vals, int begin_bit, int end_bit, uint32_t* temp, cudaStream_t s,
                       bool* result_in_b);
-int launch_emit(const tgr_params& p, const GeomView& g, const BinView& b, uint64_t cap, cudaStream_t s);
-int launch_tile_order(const uint2* ranges, const uint32_t* tile_last, uint32_t T, uint32_t* order,
-                      uint32_t* queue_counters, uint32_t* seg_base, cudaStream_t s);
-int launch_unit_build(const uint2* ranges, const uint32_t* tile_last, uint32_t T, uint2* units, uint32_t units_cap,
-                      uint32_t* unit_count, cudaStream_t s);
+int launch_sort_pairs_batch(const SortBatch& sb, bool iota_vals, int begin_bit, int end_bit, cudaStream_t s,
+                            bool* result_in_b);
+int launch_emit(const RenderBatch& rb, cudaStream_t s);
+int launch_ranges(const RenderBatch& rb, cudaStream_t s);
+int launch_tile_order(const RenderBatch& rb, cudaStream_t s);
+int launch_unit_build(const RenderBatch& rb, cudaStream_t s);
 uint32_t num_queues();  // number of SMs of the current device (one work queue per SM)
-int launch_ranges(const tgr_params& p, const GeomView& g, const uint32_t* sorted_keys, const ImageView& im,
-                  uint64_t cap, cudaStream_t s);
-int launch_blend_fwd(const tgr_params& p, const GeomView& g, const uint32_t* point_list, const ImageView& im,
-                     const BinView& b, cudaStream_t s);
-int launch_blend_bwd(const tgr_params& p, const GeomView& g, const uint32_t* point_list, const ImageView& im,
-                     const BinView& b, cudaStream_t s);
+int launch_blend_fwd(const RenderBatch& rb, bool extras, bool debug, cudaStream_t s);
+int launch_blend_bwd(const RenderBatch& rb, bool extras, bool debug, cudaStream_t s);
 int launch_preprocess_bwd(const tgr_params& p, const tgr_binding* bind, const ViewBatch& vb, cudaStream_t s);
 int launch_mark_visible(int32_t P, const float* means3D, const float* view, const float* proj, uint8_t* present,
                         cudaStream_t s);

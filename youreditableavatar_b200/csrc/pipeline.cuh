@@ -66,23 +66,33 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
 }
-// Blocks until the phase with the given parity completes.  The suspend-time hint lets the hardware park the
-// warp instead of returning after a few dozen cycles: with the default limit ncu showed the consumers of cheap
-// pixel blocks re-issuing try_wait ~130 times per wait — a third of all instructions the blend kernels issued.
+// Blocks until the phase with the given parity completes.  try_wait parks the warp only for a few dozen cycles
+// (whatever the suspend hint says), so a waiting warp re-issues it: ncu attributed 26 % of all instructions the
+// forward issued to these polling loops once the fused multi-view launches had made the kernel issue-bound.
+// Failed tries therefore back off with nanosleep (doubling, capped): a warp that waits long polls rarely, and the
+// ring's slack of several batches hides the coarser wake-up.
+__device__ __forceinline__ bool mbar_try(uint32_t a, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(a), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(ok)
-        : "r"(a), "r"(parity), "r"(0x989680u)
-        : "memory");
-  } while (!ok);
+  if (mbar_try(a, parity)) return;
+  uint32_t ns = 64;
+  while (true) {
+    __nanosleep(ns);
+    if (mbar_try(a, parity)) return;
+    if (ns < 512) ns *= 2;
+  }
 }
 __device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -221,12 +231,16 @@ constexpr uint32_t PAD_WORD = 0x01010101u * (uint32_t)PAD_ENTRY;  // four PAD_EN
 // have landed (the Ampere-era equivalent of a TMA complete_tx).  The only thing the producer blocks on is
 // empty[slot] — the back-pressure of the ring — so up to STAGES batches of gathers are in flight and a landed
 // batch is never held back by the producer being busy elsewhere.  full[] is initialised with 32 expected arrivals.
+// (Tried and measured slower: hardware named barriers, bar.arrive / bar.sync.  They do not poll, but the producer
+// then has to wait for its copies itself and can only signal a landed batch between two blocking waits, which
+// couples the fast consumers to the slowest one: forward 1.36 -> 1.62 ms per 8-view batch.)
 // `stop` (forward only) is polled once per batch: when it returns true the producer hands over a stop marker
 // instead of data and leaves.
 __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar))
                : "memory");
 }
+constexpr int BAR_EPILOGUE = 1;
 
 template <int STAGES, bool REVERSE, bool WITH_IDS, typename StopFn>
 __device__ __forceinline__ void producer_loop(const uint32_t* __restrict__ list, int total, int rounds,

@@ -30,9 +30,15 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
 }
 
 // ---- upfront digit histograms for every pass -------------------------------------------------
-__global__ void __launch_bounds__(256) radix_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n_host,
-                                                         const uint32_t* __restrict__ n_dev, SortPlan plan,
-                                                         uint32_t* __restrict__ ghist) {
+// Both kernels serve a BATCH of independent sorts (blockIdx.y = segment): the sorts of a multi-view batch are
+// each ~1 M pairs — alone they fill the GPU for a few microseconds per pass and are bound by launch + look-back
+// latency; eight of them in one launch stream at HBM speed.
+__global__ void __launch_bounds__(256) radix_hist_kernel(const __grid_constant__ SortBatch sb, SortPlan plan) {
+  const SortSeg& seg = sb.s[blockIdx.y];
+  const uint32_t* __restrict__ keys = seg.keys_a;
+  const uint32_t n_host = seg.n_host;
+  const uint32_t* __restrict__ n_dev = seg.n_dev;
+  uint32_t* __restrict__ ghist = seg.temp;
   __shared__ uint32_t sh[RS_MAX_PASSES * RS_BINS];
   for (int i = threadIdx.x; i < RS_MAX_PASSES * RS_BINS; i += blockDim.x) sh[i] = 0;
   __syncthreads();
@@ -62,10 +68,19 @@ __global__ void __launch_bounds__(256) radix_hist_kernel(const uint32_t* __restr
 
 // ---- one digit pass ------------------------------------------------------------------------------
 template <bool IOTA>
-__global__ void __launch_bounds__(RS_THREADS, 3) radix_pass_kernel(
-    const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
-    uint32_t* __restrict__ vals_out, uint32_t n_host, const uint32_t* __restrict__ n_dev, int begin_bit, int nbits,
-    const uint32_t* __restrict__ ghist, uint32_t* __restrict__ ticket, uint32_t* __restrict__ lookback) {
+__global__ void __launch_bounds__(RS_THREADS, 3) radix_pass_kernel(const __grid_constant__ SortBatch sb, int pass, int flip,
+                                                                   int begin_bit, int nbits, uint32_t ntiles_max) {
+  // per-segment buffers: pass `pass` reads A (flip = 0) or B (flip = 1) and writes the other
+  const SortSeg& seg = sb.s[blockIdx.y];
+  const uint32_t* __restrict__ keys_in = flip ? seg.keys_b : seg.keys_a;
+  const uint32_t* __restrict__ vals_in = flip ? seg.vals_b : seg.vals_a;
+  uint32_t* __restrict__ keys_out = flip ? seg.keys_a : seg.keys_b;
+  uint32_t* __restrict__ vals_out = flip ? seg.vals_a : seg.vals_b;
+  const uint32_t n_host = seg.n_host;
+  const uint32_t* __restrict__ n_dev = seg.n_dev;
+  const uint32_t* __restrict__ ghist = seg.temp + pass * RS_BINS;
+  uint32_t* __restrict__ ticket = seg.temp + RS_MAX_PASSES * RS_BINS + pass;
+  uint32_t* __restrict__ lookback = seg.temp + RS_MAX_PASSES * RS_BINS + 32 + (uint64_t)pass * sort_ntiles(n_host) * RS_BINS;
   extern __shared__ uint32_t smem[];
   uint32_t* s_keys = smem;                          // [RS_TILE]
   uint32_t* s_vals = s_keys + RS_TILE;              // [RS_TILE]
@@ -226,44 +241,52 @@ __global__ void __launch_bounds__(RS_THREADS, 3) radix_pass_kernel(
 
 constexpr size_t RS_SMEM = (size_t)(2 * RS_TILE + (RS_THREADS / 32) * RS_BINS + 2 * RS_BINS + 16) * 4;
 
-int launch_sort_pairs(uint64_t n_host, const uint32_t* n_dev, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b,
-                      uint32_t* vals_b, bool iota_vals, int begin_bit, int end_bit, uint32_t* temp, cudaStream_t s,
-                      bool* result_in_b) {
+// Sorts every segment of `sb` (same bit range for all).  Results land in the B buffers when the plan has an odd
+// number of passes (*result_in_b), else in A.
+int launch_sort_pairs_batch(const SortBatch& sb, bool iota_vals, int begin_bit, int end_bit, cudaStream_t s,
+                            bool* result_in_b) {
   SortPlan plan = make_sort_plan(begin_bit, end_bit);
   if (result_in_b) *result_in_b = (plan.npasses & 1) != 0;
-  if (n_host == 0 || plan.npasses == 0) return 0;
-  if (n_host >= (1ull << 30)) { set_error("sort: n=%llu exceeds 2^30", (unsigned long long)n_host); return 1; }
+  uint64_t n_max = 0;
+  for (int i = 0; i < sb.V; ++i) n_max = std::max<uint64_t>(n_max, sb.s[i].n_host);
+  if (sb.V <= 0 || n_max == 0 || plan.npasses == 0) return 0;
+  if (n_max >= (1ull << 30)) { set_error("sort: n=%llu exceeds 2^30", (unsigned long long)n_max); return 1; }
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(radix_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM);
     cudaFuncSetAttribute(radix_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM);
     attr_set = true;
   }
-  const uint64_t ntiles = sort_ntiles(n_host);
-  uint32_t* ghist = temp;
-  uint32_t* tickets = temp + RS_MAX_PASSES * RS_BINS;
-  uint32_t* lookback = tickets + 32;
-  const size_t zero_bytes = ((size_t)RS_MAX_PASSES * RS_BINS + 32 + (size_t)plan.npasses * ntiles * RS_BINS) * 4;
-  cudaMemsetAsync(temp, 0, zero_bytes, s);
-  int hist_blocks = (int)std::min<uint64_t>((n_host + 256 * 16 - 1) / (256 * 16), (uint64_t)NUM_SM * 8);
-  radix_hist_kernel<<<hist_blocks, 256, 0, s>>>(keys_a, (uint32_t)n_host, n_dev, plan, ghist);
+  const uint64_t ntiles = sort_ntiles(n_max);
+  for (int i = 0; i < sb.V; ++i) {
+    if (sb.s[i].n_host == 0) continue;
+    const size_t zero_bytes =
+        ((size_t)RS_MAX_PASSES * RS_BINS + 32 + (size_t)plan.npasses * sort_ntiles(sb.s[i].n_host) * RS_BINS) * 4;
+    cudaMemsetAsync(sb.s[i].temp, 0, zero_bytes, s);
+  }
+  const int hist_blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>((n_max + 256 * 16 - 1) / (256 * 16),
+                                                                         (uint64_t)NUM_SM * 8 / sb.V));
+  radix_hist_kernel<<<dim3(hist_blocks, sb.V), 256, 0, s>>>(sb, plan);
   count_launch();
-  const uint32_t* kin = keys_a; const uint32_t* vin = vals_a;
-  uint32_t* kout = keys_b; uint32_t* vout = vals_b;
   for (int ps = 0; ps < plan.npasses; ++ps) {
-    uint32_t* lb = lookback + (uint64_t)ps * ntiles * RS_BINS;
+    const dim3 grid((unsigned)ntiles, sb.V);
     if (ps == 0 && iota_vals)
-      radix_pass_kernel<true><<<(unsigned)ntiles, RS_THREADS, RS_SMEM, s>>>(
-          kin, vin, kout, vout, (uint32_t)n_host, n_dev, plan.begin[ps], plan.bits[ps], ghist + ps * RS_BINS, tickets + ps, lb);
+      radix_pass_kernel<true><<<grid, RS_THREADS, RS_SMEM, s>>>(sb, ps, ps & 1, plan.begin[ps], plan.bits[ps], (uint32_t)ntiles);
     else
-      radix_pass_kernel<false><<<(unsigned)ntiles, RS_THREADS, RS_SMEM, s>>>(
-          kin, vin, kout, vout, (uint32_t)n_host, n_dev, plan.begin[ps], plan.bits[ps], ghist + ps * RS_BINS, tickets + ps, lb);
+      radix_pass_kernel<false><<<grid, RS_THREADS, RS_SMEM, s>>>(sb, ps, ps & 1, plan.begin[ps], plan.bits[ps], (uint32_t)ntiles);
     count_launch();
-    const uint32_t* tk = kin; const uint32_t* tv = vin;
-    kin = kout; vin = vout;
-    kout = const_cast<uint32_t*>(tk); vout = const_cast<uint32_t*>(tv);
   }
   return check_launch("radix_sort", false, s);
+}
+
+int launch_sort_pairs(uint64_t n_host, const uint32_t* n_dev, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b,
+                      uint32_t* vals_b, bool iota_vals, int begin_bit, int end_bit, uint32_t* temp, cudaStream_t s,
+                      bool* result_in_b) {
+  SortBatch sb{};
+  sb.V = 1;
+  sb.s[0] = SortSeg{keys_a, vals_a, keys_b, vals_b, temp, n_dev, (uint32_t)std::min<uint64_t>(n_host, 0xffffffffull)};
+  if (n_host >= (1ull << 30)) { set_error("sort: n=%llu exceeds 2^30", (unsigned long long)n_host); return 1; }
+  return launch_sort_pairs_batch(sb, iota_vals, begin_bit, end_bit, s, result_in_b);
 }
 
 }  // namespace tgr

@@ -71,10 +71,13 @@ def _align(x: int, a: int = 256) -> int:
 
 
 def c_rasterize_views(settings: Sequence, means3D, colors, opacity, scales, rotations, cov3D_precomp, sh,
-                      extras: bool = False, n_streams: int = 4, binding=None):
+                      extras: bool = False, n_streams: int = 0, binding=None):
     """Forward of V views.  `settings` is a sequence of GaussianRasterizationSettings (same image size, SH degree
     and scale_modifier; cameras differ).  Returns (state, color[V,3,H,W], radii[V,P] int32[, depth[V,1,H,W],
-    alpha[V,1,H,W]]).  The per-view results are bit-identical to V single-view `c_rasterize_gaussians` calls."""
+    alpha[V,1,H,W]]).  The per-view results are bit-identical to V single-view `c_rasterize_gaussians` calls.
+    n_streams = 0 (default): fused schedule — every per-view stage is one launch for the whole batch
+    (tgr_forward_render_batch); n_streams >= 1: the per-view stages are issued view by view, round-robin on that
+    many CUDA streams."""
     V = len(settings)
     if V == 0:
         raise RuntimeError("rasterize_views: empty batch")
@@ -148,28 +151,36 @@ def c_rasterize_views(settings: Sequence, means3D, colors, opacity, scales, rota
         check(L.tgr_wait_num_rendered(), "tgr_wait_num_rendered")
         counts = [int(x) for x in slots.tolist()]
 
-        S = max(1, min(int(n_streams), V))
-        streams = _side_streams(device, S) if S > 1 else [main]
-        fork = torch.cuda.Event()
-        fork.record(main)
         binnings = []
         view_events = []
         for v in range(V):
-            p = params[v]
             binning = torch.empty(L.tgr_binning_bytes(P, counts[v], W, H), **u8)
             binnings.append(binning)
-            p.binning_buffer, p.binning_bytes = binning.data_ptr(), binning.numel()
-            s = streams[v % S]
-            if S > 1 and v < S:
-                s.wait_event(fork)
-            check(L.tgr_forward_depth_sort(C.byref(p), s.cuda_stream), "tgr_forward_depth_sort")
-            check(L.tgr_forward_render(C.byref(p), counts[v], s.cuda_stream), "tgr_forward_render")
+            params[v].binning_buffer, params[v].binning_bytes = binning.data_ptr(), binning.numel()
+        S = max(0, min(int(n_streams), V))
+        if S == 0:
+            caps = (C.c_uint64 * V)(*counts)
+            check(L.tgr_forward_render_batch(params, caps, V, main.cuda_stream), "tgr_forward_render_batch")
             ev = torch.cuda.Event()
-            ev.record(s)
-            view_events.append(ev)   # view v's images are complete: lets callers drain them while later views render
-        if S > 1:
-            for s in streams:
-                main.wait_stream(s)
+            ev.record(main)
+            view_events = [ev] * V
+        else:
+            streams = _side_streams(device, S) if S > 1 else [main]
+            fork = torch.cuda.Event()
+            fork.record(main)
+            for v in range(V):
+                p = params[v]
+                s = streams[v % S]
+                if S > 1 and v < S:
+                    s.wait_event(fork)
+                check(L.tgr_forward_depth_sort(C.byref(p), s.cuda_stream), "tgr_forward_depth_sort")
+                check(L.tgr_forward_render(C.byref(p), counts[v], s.cuda_stream), "tgr_forward_render")
+                ev = torch.cuda.Event()
+                ev.record(s)
+                view_events.append(ev)   # view v's images are complete: lets callers drain them while later views render
+            if S > 1:
+                for s in streams:
+                    main.wait_stream(s)
 
     state.params, state.counts, state.n_streams = params, counts, S
     state.view_events = view_events
@@ -229,18 +240,22 @@ def c_rasterize_views_backward(state: ViewBatchState, dL_dout_color, dL_dout_dep
 
         main = torch.cuda.current_stream(device)
         S = state.n_streams
-        streams = _side_streams(device, S) if S > 1 else [main]
-        if S > 1:
-            fork = torch.cuda.Event()
-            fork.record(main)
-        for v in range(V):
-            s = streams[v % S]
-            if S > 1 and v < S:
-                s.wait_event(fork)
-            check(L.tgr_backward_blend(C.byref(params[v]), state.counts[v], s.cuda_stream), "tgr_backward_blend")
-        if S > 1:
-            for s in streams:
-                main.wait_stream(s)
+        caps = (C.c_uint64 * V)(*state.counts)
+        if S == 0:
+            check(L.tgr_backward_blend_batch(params, caps, V, main.cuda_stream), "tgr_backward_blend_batch")
+        else:
+            streams = _side_streams(device, S) if S > 1 else [main]
+            if S > 1:
+                fork = torch.cuda.Event()
+                fork.record(main)
+            for v in range(V):
+                s = streams[v % S]
+                if S > 1 and v < S:
+                    s.wait_event(fork)
+                check(L.tgr_backward_blend(C.byref(params[v]), state.counts[v], s.cuda_stream), "tgr_backward_blend")
+            if S > 1:
+                for s in streams:
+                    main.wait_stream(s)
         caps = (C.c_uint64 * V)(*state.counts)
         bptr = C.byref(state.binding) if state.binding is not None else None
         nch = max(1, min(int(chunks), (P + 255) // 256))
@@ -281,7 +296,7 @@ class _RasterizeViews(torch.autograd.Function):
 
 
 def rasterize_views(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, settings,
-                    extras=False, n_streams=4):
+                    extras=False, n_streams=0):
     return _RasterizeViews.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                                  list(settings), extras, n_streams)
 
@@ -291,7 +306,7 @@ class MultiViewRasterizer(torch.nn.Module):
     (diff_gaussian_rasterization/__init__.py:186-220) and returns (color[V,3,H,W], radii[V,P]) — plus
     depth[V,1,H,W], alpha[V,1,H,W] with extra_outputs=True."""
 
-    def __init__(self, raster_settings: Sequence, extra_outputs: bool = False, n_streams: int = 4):
+    def __init__(self, raster_settings: Sequence, extra_outputs: bool = False, n_streams: int = 0):
         super().__init__()
         self.raster_settings = list(raster_settings)
         self.extra_outputs = extra_outputs

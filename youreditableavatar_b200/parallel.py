@@ -143,11 +143,11 @@ def settings_from_cam(cam: Dict[str, object], degree: int):
 
 
 def render_views_fwd_bwd(inp: Dict[str, torch.Tensor], cams: Sequence[Dict[str, object]], degree: int, upstream,
-                         bucket: GradBucket, extras: bool = False, n_streams: int = 4, accumulate: bool = False,
+                         bucket: GradBucket, extras: bool = False, n_streams: int = 0, accumulate: bool = False,
                          all_reduce: bool = False, comm_chunks: int = 4, group=None):
     """Batched forward + backward of this rank's views (youreditableavatar_b200.multiview): one preprocess launch
-    for all views, per-view binning / blending on `n_streams` streams, one backward-preprocess launch that writes
-    the summed gradients into `bucket` (overwrite, or add with accumulate=True).
+    for all views, binning / blending fused per stage (n_streams = 0) or per view on `n_streams` streams, one
+    backward-preprocess launch that writes the summed gradients into `bucket` (overwrite, or add with accumulate=True).
     `upstream(color[V,3,H,W], depth[V,1,H,W] | None, alpha | None[, view_events])` -> (dL_dcolor[V,3,H,W],
     dL_ddepth | None, dL_dalpha | None); `view_events[v]` fires when view v's images are complete (the forward has
     already been joined on the current stream when `upstream` runs, the events only matter to side streams).
