@@ -28,7 +28,7 @@ constexpr int BL_STAGES = 4;  // shared-memory ring depth (how far consumers may
 
 
 template <bool EXTRAS>
-__global__ void __launch_bounds__(BL_THREADS) blend_fwd_kernel(const __grid_constant__ RenderBatch rb, uint32_t num_queues) {
+__global__ void __launch_bounds__(BL_THREADS, 4) blend_fwd_kernel(const __grid_constant__ RenderBatch rb, uint32_t num_queues) {
   __shared__ __align__(16) float4 s_xy[BL_STAGES][BL_BATCH + 1];   // x, y, hx, hy   (+1: the PAD_ENTRY dummy)
   __shared__ __align__(16) float4 s_co[BL_STAGES][BL_BATCH + 1];   // conic xx, xy, yy, opacity
   __shared__ __align__(16) float4 s_cd[BL_STAGES][BL_BATCH + 1];   // r, g, b, depth
