@@ -53,6 +53,8 @@ class TgrBinding(C.Structure):
 SYMBOLS = {
     "tgr_abi_version": (C.c_int, []),
     "tgr_last_error": (C.c_char_p, []),
+    "tgr_set_pair_factor": (C.c_int, [C.c_int]),
+    "tgr_get_pair_factor": (C.c_int, []),
     "tgr_geom_bytes": (C.c_uint64, [C.c_int32]),
     "tgr_image_bytes": (C.c_uint64, [C.c_int32, C.c_int32]),
     "tgr_binning_bytes": (C.c_uint64, [C.c_int32, C.c_uint64, C.c_int32, C.c_int32]),
