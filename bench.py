@@ -12,10 +12,10 @@ per-view stages on `--streams` CUDA streams); the reference arm has no such call
 Prints ONE JSON line on rank 0.
 
   value   views/s over all ranks, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e     same metric through the public operator API with HOST buffers: every view's camera + upstream
-          gradients are copied from pinned host memory and the rendered image + a gradient checksum are read
-          back inside the timed region (Gaussian parameters are model state and stay resident, as in the
-          reference's training loops)
+  e2e     same metric as a training step through the public operator API with HOST buffers: every view's camera
+          and uint8 target image come from pinned host memory, the image loss and its upstream gradients are
+          formed on the device from the rendered outputs, and the step's loss is read back, all inside the timed
+          region (Gaussian parameters are model state and stay resident, as in the reference's training loops)
   roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md.
 `--impl reference` times the UNMODIFIED reference CUDA rasterizer (oracle/_ref, built by oracle/build_ref.py)
 on the same scene through its own `_C` entry points; if that build is absent it falls back to the CPU oracle.
@@ -161,7 +161,54 @@ def build_workload(cfg, V, rank, world):
         da = (torch.randn(1, res, res, generator=gen) / N).pin_memory()
         up_host.append((dc, dd, da))
     up_dev = [tuple(t.cuda() for t in u) for u in up_host]
-    return P, res, act, cams, up_host, up_dev
+    # e2e leg: the step's host-side inputs are uint8 target images (what a dataset holds), one per view
+    targets_host = torch.randint(0, 256, (V, 3, res, res), generator=gen, dtype=torch.uint8).pin_memory()
+    return P, res, act, cams, up_host, up_dev, targets_host
+
+
+def image_loss(color, depth, alpha, target_u8):
+    """Loss of the e2e leg, formed on the device from the rendered outputs (plain torch elementwise ops — the
+    reference's L1+SSIM loss is out of scope): mean squared colour error against the uint8 target,
+    plus small depth / coverage terms when the extras are rendered.  Returns (dL_dcolor, dL_ddepth, dL_dalpha, loss);
+    works on one view [3,H,W] or a batch [V,3,H,W]."""
+    diff = color - target_u8.to(torch.float32).mul_(1.0 / 255.0)
+    loss = (diff * diff).mean()
+    dLc = diff * (2.0 / diff.numel())
+    dLd = dLa = None
+    if depth is not None:
+        cov = alpha - 1.0
+        loss = loss + 5e-4 * (depth * depth).mean() + 0.5 * (cov * cov).mean()
+        dLd = depth * (1e-3 / depth.numel())
+        dLa = cov * (1.0 / alpha.numel())
+    return dLc, dLd, dLa, loss
+
+
+class ResultReader:
+    """Device->host read of the step's result: an asynchronous copy into pinned memory every step; the host
+    consumes the value one step later (so it never stalls the GPU) and waits for the last one in drain()."""
+
+    def __init__(self):
+        self.pinned = torch.zeros(2, 1).pin_memory()
+        self.events = [None, None]
+        self.k = 0
+
+    def push(self, result):
+        slot = self.k & 1
+        self.pinned[slot].copy_(result.detach().reshape(1), non_blocking=True)
+        ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream())
+        self.events[slot] = ev
+        self.k += 1
+        prev = self.events[slot ^ 1]
+        if prev is not None:
+            prev.synchronize()
+            return float(self.pinned[slot ^ 1])
+        return None
+
+    def drain(self):
+        for ev in self.events:
+            if ev is not None:
+                ev.synchronize()
+        return float(self.pinned[(self.k - 1) & 1]) if self.k else None
 
 
 def cam_to_host(cam):
@@ -173,17 +220,19 @@ def cam_to_dev(cam):
 
 
 class HostFeeder:
-    """Per-view host<->device traffic of the e2e leg, overlapped with rendering on two side streams: the camera
-    and upstream gradients of view i+1 are copied from pinned memory while view i renders; rendered images go
-    back to pinned memory on a third stream.  The same feeder serves both arms."""
+    """Per-view host->device traffic of the e2e leg for the arms that render one view per call: the camera and
+    the uint8 target image of view i+1 are copied from pinned memory on a side stream while view i renders.  The
+    same feeder (and the same device-side loss) serves the reference arm and ours-per-view."""
 
-    def __init__(self, host_cams, host_ups, out_pinned, n_up):
-        self.cams, self.ups, self.out, self.n_up = host_cams, host_ups, out_pinned, n_up
-        self.s_in, self.s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    def __init__(self, host_cams, targets_host):
+        self.cams, self.targets = host_cams, targets_host
+        self.s_in = torch.cuda.Stream()
         self.keep = []
         self.slot = {}
+        self.reader = ResultReader()
 
     def begin_step(self):
+        self.s_in.wait_stream(torch.cuda.current_stream())   # recycled input buffers are no longer in use
         self.keep.clear()
         self.slot.clear()
         self._prefetch(0)
@@ -193,47 +242,39 @@ class HostFeeder:
             return
         with torch.cuda.stream(self.s_in):
             cam = {k: (v.cuda(non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in self.cams[i].items()}
-            ups = tuple(t.cuda(non_blocking=True) for t in self.ups[i][:self.n_up])
+            tgt = self.targets[i].cuda(non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.s_in)
-        self.slot[i] = (cam, ups, ev)
+        self.slot[i] = (cam, tgt, ev)
 
     def view(self, i):
-        cam, ups, ev = self.slot[i]
+        cam, tgt, ev = self.slot[i]
         torch.cuda.current_stream().wait_event(ev)
-        self.keep.append((cam, ups))
+        self.keep.append((cam, tgt))
         self._prefetch(i + 1)
-        return cam, ups
+        return cam, tgt
 
-    def image_out(self, i, color):
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream())
-        with torch.cuda.stream(self.s_out):
-            self.s_out.wait_event(ev)
-            self.out[i].copy_(color, non_blocking=True)
-        self.keep.append(color)
+    def end_step(self, result):
+        return self.reader.push(result)
 
-    def end_step(self):
-        torch.cuda.current_stream().wait_stream(self.s_out)
+    def drain(self):
+        return self.reader.drain()
 
 
 class BatchFeeder:
-    """Host<->device traffic of the e2e leg for the multi-view batch, double-buffered: while step k renders, the
-    cameras and upstream-gradient images of step k+1 are copied from pinned host memory on a side stream (every
-    step consumes its own fresh copy); the rendered images go back to pinned memory on another stream while the
-    backward runs."""
+    """Host->device traffic of the e2e leg for the multi-view batch, double-buffered: while step k renders, the
+    cameras (one packed block) and the uint8 target images of step k+1 are copied from pinned host memory on a side
+    stream; every step consumes its own fresh copy."""
 
-    def __init__(self, host_cams, host_ups, out_pinned):
-        self.cams, self.ups, self.out = host_cams, host_ups, out_pinned   # ups: 3 stacked pinned tensors
-        self.s_in, self.s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    def __init__(self, host_cams, targets_host):
+        self.cams, self.targets = host_cams, targets_host
+        self.s_in = torch.cuda.Stream()
         self.pending = None
         self.keep = []
         # all cameras of the batch travel as ONE pinned block [V, 38] = view 16 | proj 16 | campos 3 | bg 3
         self.cam_pack = torch.stack([torch.cat([c["viewmatrix"].flatten(), c["projmatrix"].flatten(),
                                                 c["campos"].flatten(), c["bg"].flatten()]) for c in host_cams]).pin_memory()
-        self.loss_pinned = torch.zeros(2, 1).pin_memory()   # gradient checksum of step k lands here asynchronously
-        self.loss_events = [None, None]
-        self.k = 0
+        self.reader = ResultReader()
 
     def _issue(self):
         with torch.cuda.stream(self.s_in):
@@ -244,9 +285,9 @@ class BatchFeeder:
                 d["viewmatrix"], d["projmatrix"] = pack[v, 0:16].view(4, 4), pack[v, 16:32].view(4, 4)
                 d["campos"], d["bg"] = pack[v, 32:35], pack[v, 35:38]
                 cams.append(d)
-            ups = tuple(t.cuda(non_blocking=True) for t in self.ups)
+            tgt = self.targets.cuda(non_blocking=True)
             ev = torch.cuda.Event(); ev.record(self.s_in)
-        return cams, ups, ev
+        return cams, tgt, ev
 
     def begin_step(self):
         if self.pending is None:
@@ -259,37 +300,14 @@ class BatchFeeder:
         self.keep = [self.cur]
         return self.cur[0]
 
-    def images_out(self, color, view_events):
-        # view v goes back as soon as ITS forward is done, while the other views still render
-        with torch.cuda.stream(self.s_out):
-            for v, ev in enumerate(view_events):
-                self.s_out.wait_event(ev)
-                self.out[v].copy_(color[v], non_blocking=True)
-        self.keep.append(color)
-
-    def upstream(self):
+    def targets_dev(self):
         return self.cur[1]
 
     def end_step(self, result):
-        """Reads the step's result back: an asynchronous copy into pinned memory every step; the host consumes the
-        value one step later (so it never stalls the GPU), and waits for the last one in drain()."""
-        torch.cuda.current_stream().wait_stream(self.s_out)
-        slot = self.k & 1
-        self.loss_pinned[slot].copy_(result, non_blocking=True)
-        ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream())
-        self.loss_events[slot] = ev
-        self.k += 1
-        prev = self.loss_events[slot ^ 1]
-        if prev is not None:
-            prev.synchronize()
-            return float(self.loss_pinned[slot ^ 1])
-        return None
+        return self.reader.push(result)
 
     def drain(self):
-        for ev in self.loss_events:
-            if ev is not None:
-                ev.synchronize()
-        return float(self.loss_pinned[(self.k - 1) & 1]) if self.k else None
+        return self.reader.drain()
 
 
 class OursRunner:
@@ -307,18 +325,19 @@ class OursRunner:
         if feeder is not None:
             cams = feeder.begin_step()
 
-        def upstream(color, depth, alpha, view_events):
+        box = {}
+
+        def upstream(color, depth, alpha):
             if feeder is None:
                 return ups if self.extras else (ups[0], None, None)
-            feeder.images_out(color, view_events)
-            u = feeder.upstream()
-            return u if self.extras else (u[0], None, None)
+            dLc, dLd, dLa, box["loss"] = image_loss(color, depth, alpha, feeder.targets_dev())
+            return dLc, dLd, dLa
 
         # the all-reduce of the gradient buffer is issued range by range from inside the backward (overlapped)
         render_views_fwd_bwd(self.act, cams, 3, upstream, self.bucket, extras=self.extras, n_streams=self.n_streams,
                              all_reduce=True, comm_chunks=self.comm_chunks)
         if feeder is not None:
-            return feeder.end_step(self.bucket.flat[:1024].sum().view(1))   # D2H read of a gradient checksum
+            return feeder.end_step(box["loss"])   # D2H read of the step's loss
         return None
 
 
@@ -326,7 +345,6 @@ class OursPerViewRunner:
     """The single-view drop-in calls in a Python loop with in-kernel gradient accumulation (what a caller that
     keeps the reference's one-view-per-call structure gets)."""
     name = "ours-per-view"
-    n_up = 3
 
     def __init__(self, P, res, act, extras=True):
         from youreditableavatar_b200.parallel import GradBucket
@@ -337,34 +355,36 @@ class OursPerViewRunner:
         from youreditableavatar_b200 import rasterizer as rz
         e = torch.Tensor([])
         act = self.act
+        loss = None
         if feeder is not None:
             feeder.begin_step()
         for i in range(len(cams)):
-            cam, up = (cams[i], ups[i]) if feeder is None else feeder.view(i)
+            cam, tgt = (cams[i], None) if feeder is None else feeder.view(i)
             fwd = rz.c_rasterize_gaussians(cam["bg"], act["means3D"], e, act["opacities"], act["scales"], act["rotations"],
                                            1.0, e, cam["viewmatrix"], cam["projmatrix"], cam["tanfovx"], cam["tanfovy"],
                                            cam["image_height"], cam["image_width"], act["shs"], 3, cam["campos"], False,
                                            False, extras=self.extras)
             R, color, radii, geom, binning, img = fwd[:6]
-            if feeder is not None:
-                feeder.image_out(i, color)
+            if feeder is None:
+                up = ups[i] if self.extras else (ups[i][0], None, None)
+            else:
+                dLc, dLd, dLa, l = image_loss(color, fwd[6] if self.extras else None, fwd[7] if self.extras else None, tgt)
+                up = (dLc, dLd, dLa)
+                loss = l if loss is None else loss + l
             kw = dict(accumulate_into=self.bucket.views) if i > 0 else dict(out=self.bucket.views)
             rz.c_rasterize_gaussians_backward(cam["bg"], act["means3D"], radii, e, act["scales"], act["rotations"], 1.0, e,
                                               cam["viewmatrix"], cam["projmatrix"], cam["tanfovx"], cam["tanfovy"], up[0],
                                               act["shs"], 3, cam["campos"], geom, R, binning, img, False,
-                                              dL_dout_depth=up[1] if self.extras else None,
-                                              dL_dout_alpha=up[2] if self.extras else None, **kw)
+                                              dL_dout_depth=up[1], dL_dout_alpha=up[2], **kw)
         self.bucket.all_reduce()
         if feeder is not None:
-            feeder.end_step()
-            return float(self.bucket.flat[:1024].sum().item())           # D2H read of a gradient checksum
+            return feeder.end_step(loss)           # D2H read of the step's loss
         return None
 
 
 class RefRunner:
     """The reference's own CUDA rasterizer (unmodified sources compiled into oracle/_ref)."""
     name = "reference"
-    n_up = 1  # it has no depth/alpha outputs to back-propagate
 
     def __init__(self, P, res, act):
         from oracle import ref_cuda
@@ -372,14 +392,18 @@ class RefRunner:
         self.acc = None
 
     def step(self, cams, ups, world, feeder=None):
+        loss = None
         if feeder is not None:
             feeder.begin_step()
         for i in range(len(cams)):
-            cam, up = (cams[i], ups[i]) if feeder is None else feeder.view(i)
+            cam, tgt = (cams[i], None) if feeder is None else feeder.view(i)
             fwd = self.ref.forward(self.act, cam, 3)
-            if feeder is not None:
-                feeder.image_out(i, fwd[1])
-            grads = self.ref.backward(self.act, cam, 3, fwd, up[0])
+            if feeder is None:
+                dLc = ups[i][0]
+            else:
+                dLc, _, _, l = image_loss(fwd[1], None, None, tgt)   # it has no depth/alpha outputs
+                loss = l if loss is None else loss + l
+            grads = self.ref.backward(self.act, cam, 3, fwd, dLc)
             need = (2, 3, 5, 6, 7)  # opacity, means3D, sh, scales, rotations — what ours accumulates too
             if i == 0:
                 self.acc = [grads[k] for k in need]   # first view: adopt the freshly zero-filled tensors
@@ -391,8 +415,7 @@ class RefRunner:
             for a in self.acc:
                 dist.all_reduce(a)
         if feeder is not None:
-            feeder.end_step()
-            return float(self.acc[0].flatten()[:1024].sum().item())
+            return feeder.end_step(loss)           # D2H read of the step's loss
         return None
 
 
@@ -404,7 +427,7 @@ def timed(runner, cams, ups, world, steps, warmup, feeder=None):
     e0.record()
     for _ in range(steps):
         runner.step(cams, ups, world, feeder)
-    if feeder is not None and hasattr(feeder, "drain"):
+    if feeder is not None:
         feeder.drain()                       # the last step's result has reached the host
     e1.record()
     barrier(world)
@@ -472,7 +495,7 @@ def main():
                                   "note": "reference CUDA build (oracle/_ref) absent: CPU oracle port timed instead"}))
             return
 
-    P, res, act, cams, up_host, up_dev = build_workload(cfg, V, rank, world)
+    P, res, act, cams, up_host, up_dev, targets_host = build_workload(cfg, V, rank, world)
     from youreditableavatar_b200 import _lib
     L = _lib.lib()
     batched = args.impl == "ours" and not args.per_view_api
@@ -529,18 +552,12 @@ def main():
 
     # ---- end to end through the operator API with host buffers ------------------------------------------
     host_cams = [cam_to_host(c) for c in cams]
-    n_up = runner.n_up
-    if batched:
-        out_pinned = torch.empty(V, 3, res, res).pin_memory()
-        feeder = BatchFeeder(host_cams, up_stack_host, out_pinned)
-    else:
-        out_pinned = [torch.empty(3, res, res).pin_memory() for _ in range(V)]
-        feeder = HostFeeder(host_cams, up_host, out_pinned, n_up)
+    feeder = BatchFeeder(host_cams, targets_host) if batched else HostFeeder(host_cams, targets_host)
     ms_e2e = timed(runner, cams, ups_for_runner, world, args.steps, max(args.warmup, 3), feeder)
     e2e_value = views / (ms_e2e / 1000.0)
     cam_bytes = sum(v.numel() * 4 for v in host_cams[0].values() if isinstance(v, torch.Tensor))
-    h2d = V * (cam_bytes + sum(t.numel() * 4 for t in up_host[0][:n_up]))
-    d2h = V * (3 * res * res * 4) + 4
+    h2d = V * cam_bytes + targets_host.numel()     # cameras (fp32) + uint8 target images
+    d2h = 4                                        # the step's loss
 
     # ---- ours through the single-view drop-in calls (the API the reference's callers use today) ---------
     per_view = None

@@ -121,6 +121,12 @@ def _worker(rank, world, port, q):
         bucket.all_reduce_sh_rows_async(first, min(16, P - first))
     bucket.all_reduce_rest_and_wait()
     ok = ok and torch.equal(bucket.flat, summed) and bucket._pending == []
+    # all rows of a range in one (coalesced where the backend can) launch
+    bucket.flat.copy_(ref)
+    for first in range(0, P, 16):
+        bucket.all_reduce_rows_async(first, min(16, P - first))
+    bucket.wait()
+    ok = ok and torch.equal(bucket.flat, summed) and bucket._pending == []
     q.put((rank, ok, mine))
     dist.destroy_process_group()
 

@@ -8,7 +8,7 @@ torch.cuda.set_device(local)
 opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
 V = 8
-P, res, act, cams, up_host, up_dev = bench.build_workload("C3", V, rank, world)
+P, res, act, cams, up_host, up_dev, _tg = bench.build_workload("C3", V, rank, world)
 ups = tuple(torch.stack([u[k] for u in up_host]).cuda() for k in range(3))
 from youreditableavatar_b200.parallel import GradBucket, render_views_fwd_bwd
 bucket = GradBucket(P, 16, "cuda", names=GradBucket.TRAINING)
@@ -25,9 +25,10 @@ def run(name, fn, K=15):
     if rank == 0: print(name, " ".join("%.3f" % x.item() for x in g), "ms/step per rank", flush=True)
 
 up = lambda c, d, a: ups
-run("compute only      ", lambda: render_views_fwd_bwd(act, cams, 3, up, bucket, extras=True, n_streams=4))
+run("compute only      ", lambda: render_views_fwd_bwd(act, cams, 3, up, bucket, extras=True, n_streams=0))
 run("allreduce only    ", lambda: bucket.all_reduce())
-run("compute + ar      ", lambda: (render_views_fwd_bwd(act, cams, 3, up, bucket, extras=True, n_streams=4), bucket.all_reduce()))
-for c in (2, 4, 8, 16):
-    run("overlapped chunks %2d" % c, lambda: render_views_fwd_bwd(act, cams, 3, up, bucket, extras=True, n_streams=4, all_reduce=True, comm_chunks=c))
+run("compute + ar      ", lambda: (render_views_fwd_bwd(act, cams, 3, up, bucket, extras=True, n_streams=0), bucket.all_reduce()))
+for mode in ("sh", "rows"):
+    for c in (4, 8):
+        run("overlapped %-4s chunks %2d" % (mode, c), lambda: render_views_fwd_bwd(act, cams, 3, up, bucket, extras=True, all_reduce=True, comm_chunks=c, comm_mode=mode))
 dist.destroy_process_group()

@@ -90,6 +90,29 @@ class GradBucket:
         sl = self.flat[self.sh_offset + first * row: self.sh_offset + (first + count) * row]
         self._pending.append(dist.all_reduce(sl, op=dist.ReduceOp.SUM, group=group, async_op=True))
 
+    def all_reduce_rows_async(self, first: int, count: int, group=None):
+        """Starts the all-reduce of rows [first, first+count) of EVERY gradient tensor in the bucket (one coalesced
+        NCCL launch for the up-to-eight slices).  With this variant nothing but the last range is left for the end
+        of the backward; `wait()` joins."""
+        import torch.distributed as dist
+        if not self._distributed(group):
+            return
+        slices = [t[first:first + count] for t in self.views if t is not None]
+        if dist.get_backend(group) == "nccl" and hasattr(dist, "_coalescing_manager"):
+            with dist._coalescing_manager(group=group, device=self.flat.device, async_ops=True) as cm:
+                for sl in slices:
+                    dist.all_reduce(sl, op=dist.ReduceOp.SUM, group=group)
+            self._pending.append(cm)
+        else:                                               # e.g. gloo in the CPU tests: one op per slice
+            for sl in slices:
+                self._pending.append(dist.all_reduce(sl, op=dist.ReduceOp.SUM, group=group, async_op=True))
+
+    def wait(self):
+        for w in self._pending:
+            w.wait()
+        self._pending = []
+        return self
+
     def all_reduce_rest_and_wait(self, group=None):
         """All-reduces everything that is not SH (one contiguous slice) and joins the pending SH ranges."""
         import torch.distributed as dist
@@ -144,7 +167,7 @@ def settings_from_cam(cam: Dict[str, object], degree: int):
 
 def render_views_fwd_bwd(inp: Dict[str, torch.Tensor], cams: Sequence[Dict[str, object]], degree: int, upstream,
                          bucket: GradBucket, extras: bool = False, n_streams: int = 0, accumulate: bool = False,
-                         all_reduce: bool = False, comm_chunks: int = 4, group=None):
+                         all_reduce: bool = False, comm_chunks: int = 4, group=None, comm_mode: str = "rows"):
     """Batched forward + backward of this rank's views (youreditableavatar_b200.multiview): one preprocess launch
     for all views, binning / blending fused per stage (n_streams = 0) or per view on `n_streams` streams, one
     backward-preprocess launch that writes the summed gradients into `bucket` (overwrite, or add with accumulate=True).
@@ -152,8 +175,9 @@ def render_views_fwd_bwd(inp: Dict[str, torch.Tensor], cams: Sequence[Dict[str, 
     dL_ddepth | None, dL_dalpha | None); `view_events[v]` fires when view v's images are complete (the forward has
     already been joined on the current stream when `upstream` runs, the events only matter to side streams).
     all_reduce=True also sums `bucket` over the ranks, overlapped with the backward: the per-Gaussian kernel runs
-    over `comm_chunks` ranges of Gaussians and each range's SH gradient rows are all-reduced (NCCL, on the process
-    group's stream) while the next range is computed; the small tensors follow in one slice at the end.
+    over `comm_chunks` ranges of Gaussians and each range's gradient rows are all-reduced (NCCL, on the process
+    group's stream; comm_mode "rows": all tensors' rows of the range in one coalesced launch, "sh": the SH rows
+    per range and the small tensors at the end, "flat": no overlap) while the next range is computed.
     Returns the rendered images."""
     from . import multiview as mv
     e = torch.Tensor([])
@@ -170,10 +194,19 @@ def render_views_fwd_bwd(inp: Dict[str, torch.Tensor], cams: Sequence[Dict[str, 
         dLc, dLd, dLa = upstream(color, depth, alpha)
     kw = dict(accumulate_into=bucket.views) if accumulate else dict(out=bucket.views)
     if all_reduce and GradBucket._distributed(group):
-        mv.c_rasterize_views_backward(state, dLc, dL_dout_depth=dLd, dL_dout_alpha=dLa, chunks=comm_chunks,
-                                      on_chunk=lambda first, count: bucket.all_reduce_sh_rows_async(first, count, group),
-                                      **kw)
-        bucket.all_reduce_rest_and_wait(group)
+        if comm_mode == "rows":     # every range carries all its gradient rows: only the last range is exposed
+            mv.c_rasterize_views_backward(state, dLc, dL_dout_depth=dLd, dL_dout_alpha=dLa, chunks=comm_chunks,
+                                          on_chunk=lambda first, count: bucket.all_reduce_rows_async(first, count, group),
+                                          **kw)
+            bucket.wait()
+        elif comm_mode == "sh":     # SH rows per range, the small tensors in one slice at the end
+            mv.c_rasterize_views_backward(state, dLc, dL_dout_depth=dLd, dL_dout_alpha=dLa, chunks=comm_chunks,
+                                          on_chunk=lambda first, count: bucket.all_reduce_sh_rows_async(first, count, group),
+                                          **kw)
+            bucket.all_reduce_rest_and_wait(group)
+        else:                       # "flat": one all-reduce of the whole buffer after the backward
+            mv.c_rasterize_views_backward(state, dLc, dL_dout_depth=dLd, dL_dout_alpha=dLa, **kw)
+            bucket.all_reduce(group)
     else:
         mv.c_rasterize_views_backward(state, dLc, dL_dout_depth=dLd, dL_dout_alpha=dLa, **kw)
     return color
