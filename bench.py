@@ -49,8 +49,10 @@ def parse():
     ap.add_argument("--streams", type=int, default=0,
                     help="0 (default): fused schedule, every per-view stage is one launch for the whole batch; "
                          "n >= 1: per-view launches round-robin on n CUDA streams")
-    ap.add_argument("--comm-chunks", type=int, default=4,
-                    help="N > 1: Gaussian ranges the backward is split into so the all-reduce overlaps it")
+    ap.add_argument("--comm", default="nvls", choices=["nvls", "nccl", "rows", "sh"],
+                    help="N > 1, gradient exchange: nvls = own in-switch all-reduce kernel on a symmetric-memory buffer "
+                         "(default), nccl = one NCCL all-reduce, rows / sh = NCCL per Gaussian range overlapped with the backward")
+    ap.add_argument("--comm-chunks", type=int, default=4, help="Gaussian ranges for --comm rows / sh")
     ap.add_argument("--per-view-api", action="store_true",
                     help="ours: loop over the single-view drop-in calls instead of the multi-view batch")
     return ap.parse_args()
@@ -315,10 +317,14 @@ class OursRunner:
     name = "ours"
     n_up = 3
 
-    def __init__(self, P, res, act, extras=True, n_streams=0, comm_chunks=4):
-        from youreditableavatar_b200.parallel import GradBucket
-        self.act, self.extras, self.n_streams, self.comm_chunks = act, extras, n_streams, comm_chunks
-        self.bucket = GradBucket(P, 16, "cuda", names=GradBucket.TRAINING)
+    def __init__(self, P, res, act, extras=True, n_streams=0, comm="nvls", comm_chunks=4, bucket=None):
+        from youreditableavatar_b200.parallel import GradBucket, SymmGradBucket
+        self.act, self.extras, self.n_streams, self.comm, self.comm_chunks = act, extras, n_streams, comm, comm_chunks
+        # "nvls": the gradient buffer lives in symmetric memory and is summed by this library's own in-switch
+        # all-reduce kernel (falls back to NCCL without multicast support); "nccl": one NCCL all-reduce;
+        # "rows" / "sh": NCCL all-reduces of Gaussian ranges overlapped with the backward
+        self.bucket = bucket if bucket is not None else \
+            (SymmGradBucket if comm == "nvls" else GradBucket)(P, 16, "cuda", names=GradBucket.TRAINING)
 
     def step(self, cams, ups, world, feeder=None):
         from youreditableavatar_b200.parallel import render_views_fwd_bwd
@@ -333,9 +339,12 @@ class OursRunner:
             dLc, dLd, dLa, box["loss"] = image_loss(color, depth, alpha, feeder.targets_dev())
             return dLc, dLd, dLa
 
-        # the all-reduce of the gradient buffer is issued range by range from inside the backward (overlapped)
-        render_views_fwd_bwd(self.act, cams, 3, upstream, self.bucket, extras=self.extras, n_streams=self.n_streams,
-                             all_reduce=True, comm_chunks=self.comm_chunks)
+        if self.comm in ("rows", "sh"):   # NCCL all-reduces issued range by range from inside the backward
+            render_views_fwd_bwd(self.act, cams, 3, upstream, self.bucket, extras=self.extras, n_streams=self.n_streams,
+                                 all_reduce=True, comm_chunks=self.comm_chunks, comm_mode=self.comm)
+        else:
+            render_views_fwd_bwd(self.act, cams, 3, upstream, self.bucket, extras=self.extras, n_streams=self.n_streams)
+            self.bucket.all_reduce()
         if feeder is not None:
             return feeder.end_step(box["loss"])   # D2H read of the step's loss
         return None
@@ -346,10 +355,10 @@ class OursPerViewRunner:
     keeps the reference's one-view-per-call structure gets)."""
     name = "ours-per-view"
 
-    def __init__(self, P, res, act, extras=True):
+    def __init__(self, P, res, act, extras=True, bucket=None):
         from youreditableavatar_b200.parallel import GradBucket
         self.act, self.extras = act, extras
-        self.bucket = GradBucket(P, 16, "cuda", names=GradBucket.TRAINING)
+        self.bucket = bucket if bucket is not None else GradBucket(P, 16, "cuda", names=GradBucket.TRAINING)
 
     def step(self, cams, ups, world, feeder=None):
         from youreditableavatar_b200 import rasterizer as rz
@@ -503,7 +512,7 @@ def main():
         # the multi-view batch takes stacked tensors: dL/dcolor [V,3,H,W], dL/ddepth [V,1,H,W], dL/dalpha [V,1,H,W]
         up_stack_host = tuple(torch.stack([u[k] for u in up_host]).pin_memory() for k in range(3))
         up_stack_dev = tuple(t.cuda() for t in up_stack_host)
-        runner = OursRunner(P, res, act, n_streams=args.streams, comm_chunks=args.comm_chunks)
+        runner = OursRunner(P, res, act, n_streams=args.streams, comm=args.comm, comm_chunks=args.comm_chunks)
         ups_for_runner = up_stack_dev
     else:
         runner = OursPerViewRunner(P, res, act) if args.impl == "ours" else RefRunner(P, res, act)
@@ -535,8 +544,7 @@ def main():
         stage_overlapped = collect_stages()
         if batched and args.streams > 1:
             # same batch on ONE stream, untimed: per-kernel durations without interference (used by `roofline`)
-            serial = OursRunner(P, res, act, n_streams=1)
-            serial.bucket = runner.bucket
+            serial = OursRunner(P, res, act, n_streams=1, comm=args.comm, bucket=runner.bucket)
             serial.step(cams, ups_for_runner, world)
             torch.cuda.synchronize()
             collect_stages()
@@ -562,8 +570,7 @@ def main():
     # ---- ours through the single-view drop-in calls (the API the reference's callers use today) ---------
     per_view = None
     if batched:
-        pv = OursPerViewRunner(P, res, act)
-        pv.bucket = runner.bucket
+        pv = OursPerViewRunner(P, res, act, bucket=runner.bucket)
         k = max(2, args.steps // 4)
         ms_pv = timed(pv, cams, up_dev, world, k, 2)
         per_view = {"value": V * world * k / (ms_pv / 1000.0), "unit": UNIT,
@@ -579,7 +586,9 @@ def main():
                                "1024x1024, SH degree 3, fwd+bwd with depth/alpha outputs" % cfg,
                    "views_per_step_per_gpu": V, "global_views_per_step": V * world,
                    "parallelism": "dp%d over views, flat gradient buffer all-reduced once per step%s" % (
-                       world, (" in %d ranges overlapped with the backward" % args.comm_chunks) if (batched and world > 1) else ""),
+                       world, (" (%s)" % ("in-switch NVLS all-reduce kernel of this library" if getattr(runner.bucket, "nvls", False)
+                                          else "NCCL" if args.comm in ("nvls", "nccl") else "NCCL, %d ranges overlapped" % args.comm_chunks))
+                       if (batched and world > 1) else ""),
                    "api": ("multi-view batch (MultiViewRasterizer / tgr_*_batch), " +
                            ("fused per-stage launches" if args.streams == 0 else "%d streams" % args.streams)) if batched
                           else "single-view calls in a loop",

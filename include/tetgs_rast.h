@@ -201,6 +201,13 @@ uint64_t tgr_knn_bytes(int32_t P);
 int tgr_dist2(int32_t P, const float* points, float* mean_dist2, void* workspace, uint64_t workspace_bytes,
               void* stream);
 
+/* ---- gradient exchange over NVSwitch (new; the reference is single-GPU) ----
+ * Two-shot all-reduce (sum, fp32) of a buffer that lives in symmetric memory with a multicast mapping: rank r
+ * reduces slice r of the buffer inside the switch (multimem.ld_reduce) and broadcasts the sum to every GPU
+ * (multimem.st).  `multicast_ptr` is the multicast address of the buffer's first element, n_floats a multiple
+ * of 4.  The caller brackets the call with cross-rank barriers on the same stream. */
+int tgr_multimem_allreduce_f32(void* multicast_ptr, uint64_t n_floats, int32_t rank, int32_t world, void* stream);
+
 /* ---- per-stage device timing (CUDA events recorded on the launching stream) ----
  * tgr_profile_enable(1) makes every subsequent stage launch bracket itself with events;
  * tgr_profile_collect synchronises the recorded events and returns, per stage id (TGR_STAGE_*), the summed

@@ -126,6 +126,42 @@ class GradBucket:
         return self
 
 
+class SymmGradBucket(GradBucket):
+    """GradBucket whose flat buffer lives in symmetric memory (torch.distributed._symmetric_memory: allocation,
+    rendezvous, multicast mapping and the cross-rank barrier are plumbing).  `all_reduce` is then ONE kernel of this
+    library — `tgr_multimem_allreduce_f32`, a two-shot all-reduce with in-switch reduction over NVSwitch
+    (csrc/collective.cu) — instead of an NCCL call.  Falls back to NCCL when the devices have no multicast support
+    (`self.nvls` tells which path is live)."""
+
+    def __init__(self, P: int, M: int, device="cuda", names: Optional[Sequence[str]] = None, group=None):
+        import torch.distributed as dist
+        super().__init__(P, M, device, names)
+        self.group = group
+        self.hdl, self.nvls = None, False
+        if self._distributed(group):
+            import torch.distributed._symmetric_memory as symm_mem
+            flat = symm_mem.empty(self.flat.numel(), dtype=torch.float32, device=self.flat.device)
+            flat.zero_()
+            self.flat = flat
+            self.views = tuple(None if o is None else self._view(o, shp) for o, shp in zip(self.offsets, self.shapes))
+            g = group if group is not None else dist.group.WORLD
+            self.hdl = symm_mem.rendezvous(self.flat, g)
+            self.nvls = bool(getattr(self.hdl, "multicast_ptr", 0))
+
+    def all_reduce(self, group=None):
+        if not self.nvls:
+            return super().all_reduce(group if group is not None else self.group)
+        from . import _lib
+        h = self.hdl
+        mc = h.multicast_ptr + (self.flat.data_ptr() - h.buffer_ptrs[h.rank])
+        stream = torch.cuda.current_stream(self.flat.device).cuda_stream
+        h.barrier(channel=0)   # every rank's gradients are written (stream-ordered on each rank)
+        _lib.check(_lib.lib().tgr_multimem_allreduce_f32(mc, self.flat.numel(), h.rank, h.world_size, stream),
+                   "tgr_multimem_allreduce_f32")
+        h.barrier(channel=1)   # every rank's slice has been broadcast
+        return self
+
+
 def render_batch_fwd_bwd(inp: Dict[str, torch.Tensor], cams: Sequence[Dict[str, object]], degree: int,
                          upstream, bucket: GradBucket, extras: bool = False, keep_images: bool = False):
     """Forward + backward of this rank's views; gradients accumulate in `bucket` (first view overwrites, the
