@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TGR_ABI_VERSION 2
+#define TGR_ABI_VERSION 3
 #define TGR_TILE 16 /* 16x16 pixel tiles, config.h:16-17 */
 #define TGR_MAX_BATCH 8 /* views served by one launch of the per-Gaussian kernels (longer batches are chunked) */
 
@@ -245,6 +245,89 @@ int tgr_export_image_state(const tgr_params* p, float* final_T, uint32_t* n_cont
 uint64_t tgr_sort_temp_bytes(uint64_t n);
 int tgr_sort_pairs_u32(uint64_t n, uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
                        int begin_bit, int end_bit, void* temp, uint64_t temp_bytes, void* stream);
+
+/* ======================= rows "next" of the scope table ======================= */
+
+/* ---- f1: image loss, forward + gradient in two launches ----
+ * Replaces Edit_core/utils/loss_utils.py:17-63 (l1_loss, l2_loss, ssim / _ssim: five grouped 11x11 conv2d +
+ * ~20 elementwise ATen kernels, and as many again in autograd's backward) and the loss closure built at
+ * Edit_core/tetgs_texture/refine.py:241-247 (same code: paint_2dgs.py:341-347, refine_3dgs.py:273-279):
+ *
+ *   loss_v = l1_weight * mean|p_v - g_v| + l2_weight * mean (p_v - g_v)^2
+ *          + dssim_weight * (1 - mean ssim_map(p_v, g_v))                      per view v, means over [3,H,W]
+ *   total  = sum_v w_v * loss_v          w_v = view_weights[v], or 1/n_views when view_weights == NULL
+ *                                        (the reference's .mean() over its image batch, loss_utils.py:18,61)
+ *
+ * ssim_map exactly as loss_utils.py:44-59: Gaussian window 11, sigma 1.5 (fp32 weights normalised in fp32,
+ * loss_utils.py:23-25), zero padding 5, C1 = 0.01^2, C2 = 0.03^2, variances as E[x^2] - mu^2.
+ * `pred` is [V,3,H,W] fp32 (the rasterizer's colour output); `target` is [V,3,H,W] fp32, or uint8 with
+ * target_is_u8 != 0 (converted as u/255, general_utils.py:8: the training images are 8-bit).
+ * loss_out: [1 + V] floats = {total, loss_0 .. loss_{V-1}}, written on the device (no host sync).
+ * workspace: tgr_image_loss_bytes(V, W, H) bytes, 16-byte aligned; the forward leaves there what the backward
+ * needs (three fp32 maps per pixel and channel), so both calls get the same workspace, pred and target.
+ * backward: dL_dpred [V,3,H,W] = sum_v dL_dloss_view[v] * d loss_v / d pred, fully written; dL_dloss_view is a
+ * DEVICE array [V] (what autograd hands down: grad_total * w_v + grad_loss_v), NULL = 1/n_views.
+ * tgr_image_loss = forward + (dL_dpred != NULL) backward with dL_dloss_view = view_weights: the training step. */
+uint64_t tgr_image_loss_bytes(int32_t n_views, int32_t W, int32_t H);
+int tgr_image_loss_forward(int32_t n_views, int32_t W, int32_t H, const float* pred, const void* target,
+                           int32_t target_is_u8, const float* view_weights, float l1_weight, float l2_weight,
+                           float dssim_weight, float* loss_out, void* workspace, uint64_t workspace_bytes,
+                           void* stream);
+int tgr_image_loss_backward(int32_t n_views, int32_t W, int32_t H, const float* pred, const void* target,
+                            int32_t target_is_u8, const float* dL_dloss_view, float l1_weight, float l2_weight,
+                            float dssim_weight, float* dL_dpred, void* workspace, uint64_t workspace_bytes,
+                            void* stream);
+int tgr_image_loss(int32_t n_views, int32_t W, int32_t H, const float* pred, const void* target,
+                   int32_t target_is_u8, const float* view_weights, float l1_weight, float l2_weight,
+                   float dssim_weight, float* loss_out, float* dL_dpred, void* workspace,
+                   uint64_t workspace_bytes, void* stream);
+
+/* ---- f2: Adam over all parameter groups in ONE launch ----
+ * Replaces torch.optim.Adam(l, lr=0.0, eps=1e-15).step() as driven by TetGSOptimizer / EditTetGSOptimizer
+ * (Edit_core/tetgs_scene/tetgs_optimizer.py:66-104, 136-170): betas (0.9, 0.999) defaults, no weight decay,
+ * no amsgrad, per-group learning rates (points: exponential schedule evaluated on the host,
+ * utils/general_utils.py:25-58; SH dc: feature_lr, SH rest: feature_lr / 20).
+ *
+ *   m <- m + (g - m)(1 - beta1);  v <- beta2 v + (1 - beta2) g^2;
+ *   p <- p - (lr / (1 - beta1^t)) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps)        g = grad_scale * grad
+ *
+ * A group is a contiguous run of `count` floats in four parallel arrays.  The rasterizer keeps SH as [P,M,3] rows
+ * (dc = the first 3 floats of each 3M-float row, rest = the others) where the reference holds two tensors with
+ * two learning rates: element i of a group uses `lr` when (i % period) < split and `lr_alt` otherwise
+ * (period == 0: always `lr`).  grad may be the flat all-reduced gradient buffer itself (no copy).
+ * lr == 0 (and lr_alt == 0) still updates m and v, as torch does. */
+#define TGR_ADAM_MAX_GROUPS 16
+typedef struct tgr_adam_group {
+  float* param;           /* [count] */
+  const float* grad;      /* [count] */
+  float* exp_avg;         /* [count] */
+  float* exp_avg_sq;      /* [count] */
+  uint64_t count;
+  double lr, lr_alt;      /* doubles, like the Python floats torch divides by the bias correction */
+  uint32_t period, split;
+} tgr_adam_group;
+int tgr_adam_step(const tgr_adam_group* groups, int32_t n_groups, int32_t step /* t >= 1 */, double beta1,
+                  double beta2, double eps, float grad_scale, void* stream);
+
+/* ---- f3: device-side camera / settings construction for a batch of views ----
+ * Replaces the per-call preamble of render_image_gaussian_rasterizer (Edit_core/tetgs_scene/
+ * tetgs_model.py:479-503: cat + axis flip + torch.inverse + getWorld2View + getProjectionMatrix + bmm, about
+ * 25 small ATen launches, two .item() syncs and an H2D copy per view; the edit variants add a
+ * device->numpy->device round trip and a numpy inverse, tetgs_edit_3d.py:508-518) and
+ * utils/graphics_utils.py:39-49,68-86.  One launch, no host synchronisation, for V views:
+ *   c2w_v   = [camera_to_worlds[v]; 0 0 0 1] with columns 1 and 2 negated   (OpenGL -> COLMAP axes, :482-485)
+ *   w2c_v   = inverse(c2w_v)                                                 (:488; affine inverse, fp32)
+ *   viewmatrix = w2c_v^T            (flat memory: element (r,c) of w2c at [4c + r], what the kernels read)
+ *   P          = getProjectionMatrix(znear, zfar, fovx, fovy), P[0,2] = -cx, P[1,2] = -cy   (:493-499)
+ *   projmatrix = viewmatrix . P^T   (:501)
+ *   campos     = camera centre = c2w_v[:3,3]                                 (:502)
+ * camera_to_worlds: [V,3,4] row-major (nerfstudio convention, the tensor the reference indexes at :480);
+ * intrinsics: [V,4] = {fovx, fovy, cx, cy} (radians; cx, cy = K[0,0,2], K[0,1,2] in NDC units);
+ * out_cameras: [V,TGR_CAMERA_FLOATS] = {viewmatrix 16, projmatrix 16, campos 3, tan(fovx/2), tan(fovy/2), pad};
+ * all pointers are device memory. */
+#define TGR_CAMERA_FLOATS 40
+int tgr_build_cameras(int32_t n_views, const float* camera_to_worlds, const float* intrinsics, float znear,
+                      float zfar, float* out_cameras, void* stream);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), "missing export %s" % n
         assert n in _lib.SYMBOLS, "python binding missing for %s" % n
-    assert L.tgr_abi_version() == _lib.ABI_VERSION == 2
+    assert L.tgr_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_workspace_sizes_are_pure_functions():
@@ -58,6 +58,9 @@ def test_params_struct_layout_matches_header():
         return out
     assert fields("tgr_params") == [f[0] for f in TgrParams._fields_]
     assert fields("tgr_binding") == [f[0] for f in TgrBinding._fields_]
+    from youreditableavatar_b200._lib import TgrAdamGroup
+    assert fields("tgr_adam_group") == [f[0] for f in TgrAdamGroup._fields_]
+    assert C.sizeof(TgrAdamGroup) == 64
 
 
 def test_dropin_names_and_settings_fields():
@@ -106,6 +109,44 @@ def test_no_cpu_fallback():
         distCUDA2(torch.zeros(8, 3))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         r.markVisible(m)
+
+
+def test_training_step_mirrors_have_no_cpu_path():
+    """loss_utils / optimizer / cameras: same names as the reference modules, CPU tensors raise."""
+    from youreditableavatar_b200 import loss_utils, optimizer, cameras
+    a, b = torch.rand(1, 3, 8, 8), torch.rand(1, 3, 8, 8)
+    for fn in (loss_utils.l1_loss, loss_utils.l2_loss, loss_utils.ssim, loss_utils.image_loss):
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            fn(a, b)
+    with pytest.raises(RuntimeError, match=r"\(3, H, W\)"):
+        loss_utils.image_loss(torch.rand(8, 8), torch.rand(8, 8))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        optimizer.FusedAdam([{"params": [torch.zeros(4, requires_grad=True)], "lr": 1e-3}])
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        cameras.build_cameras(torch.zeros(2, 3, 4), 0.7, 0.7)
+    o = optimizer.OptimizationParams()
+    assert (o.iterations, o.position_lr_init, o.position_lr_final, o.position_lr_delay_mult, o.position_lr_max_steps,
+            o.feature_lr, o.opacity_lr, o.scaling_lr, o.rotation_lr) == (
+        15000, 0.00016, 0.0000016, 0.01, 30000, 0.0025, 0.05, 0.005, 0.001)      # tetgs_optimizer.py:10-19
+    for n in ("step", "zero_grad", "update_learning_rate", "add_param_group", "state_dict", "load_state_dict"):
+        assert callable(getattr(optimizer.TetGSOptimizer, n))                    # tetgs_optimizer.py:106-126
+
+
+def test_training_step_abi_argument_checks():
+    """The new entry points validate their arguments on the host before any launch (callable without a GPU)."""
+    from youreditableavatar_b200 import _lib
+    L = _lib.lib()
+    assert L.tgr_image_loss_bytes(8, 1024, 1024) >= 3 * 8 * 3 * 1024 * 1024 * 4
+    assert L.tgr_image_loss_bytes(1, 77, 45) == L.tgr_image_loss_bytes(1, 77, 45)
+    assert L.tgr_image_loss_forward(0, 8, 8, 0, 0, 0, 0, 0.8, 0.0, 0.2, 0, 0, 0, 0) == 1
+    assert b"bad sizes" in L.tgr_last_error()
+    assert L.tgr_image_loss_backward(1, 8, 8, 0, 0, 0, 0, 0.8, 0.0, 0.2, 0, 0, 0, 0) == 1
+    g = (_lib.TgrAdamGroup * 1)()
+    assert L.tgr_adam_step(g, 0, 1, 0.9, 0.999, 1e-15, 1.0, 0) == 0              # nothing to do
+    assert L.tgr_adam_step(g, 1, 0, 0.9, 0.999, 1e-15, 1.0, 0) == 1 and b"step" in L.tgr_last_error()
+    assert L.tgr_adam_step(g, 17, 1, 0.9, 0.999, 1e-15, 1.0, 0) == 1
+    assert L.tgr_build_cameras(0, 0, 0, 1e-4, 100.0, 0, 0) == 0
+    assert L.tgr_build_cameras(2, 0, 0, 1e-4, 100.0, 0, 0) == 1
 
 
 def test_product_never_imports_the_oracle():

@@ -49,6 +49,15 @@ class TgrBinding(C.Structure):
     ]
 
 
+class TgrAdamGroup(C.Structure):
+    """Mirror of `tgr_adam_group`."""
+
+    _fields_ = [
+        ("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+        ("count", C.c_uint64), ("lr", C.c_double), ("lr_alt", C.c_double), ("period", C.c_uint32), ("split", C.c_uint32),
+    ]
+
+
 # every symbol include/tetgs_rast.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "tgr_abi_version": (C.c_int, []),
@@ -83,10 +92,25 @@ SYMBOLS = {
     "tgr_sort_temp_bytes": (C.c_uint64, [C.c_uint64]),
     "tgr_sort_pairs_u32": (C.c_int, [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                      C.c_void_p, C.c_uint64, C.c_void_p]),
+    "tgr_image_loss_bytes": (C.c_uint64, [C.c_int32, C.c_int32, C.c_int32]),
+    "tgr_image_loss_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                         C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_uint64,
+                                         C.c_void_p]),
+    "tgr_image_loss_backward": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                          C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_uint64,
+                                          C.c_void_p]),
+    "tgr_image_loss": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                 C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                 C.c_void_p]),
+    "tgr_adam_step": (C.c_int, [C.POINTER(TgrAdamGroup), C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
+                                C.c_float, C.c_void_p]),
+    "tgr_build_cameras": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
 }
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_BATCH = 8
+ADAM_MAX_GROUPS = 16
+CAMERA_FLOATS = 40
 NUM_STAGES = 8
 STAGE_NAMES = ["preprocess", "depth_sort", "emit", "tile_sort", "ranges", "blend_fwd", "blend_bwd", "preprocess_bwd"]
 

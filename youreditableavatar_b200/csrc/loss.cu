@@ -1,0 +1,376 @@
+// loss.cu — image loss of the texture / refinement stages, forward + gradient.
+//
+// Reference: Edit_core/utils/loss_utils.py:17-63 (l1_loss, l2_loss, ssim/_ssim) and the closure
+// `(1 - dssim_factor) * l1_loss + dssim_factor * (1 - ssim)` at Edit_core/tetgs_texture/refine.py:245-247.
+// There the step right after the rasterizer is five grouped 11x11 conv2d launches plus ~20 elementwise ATen
+// kernels on [1,3,H,W] images, and autograd replays as many in the backward.  Here it is two launches for a
+// whole batch of views:
+//
+//   loss_fwd_kernel  one CTA per 32x32 tile of one channel of one view: pred / target tile + 5-pixel halo staged
+//                    in shared memory (zero padding = out-of-image loads return 0, loss_utils.py:45), separable
+//                    11-tap Gaussian for the five moments (mu1, mu2, E[x^2], E[y^2], E[xy]), ssim map, loss terms
+//                    block-reduced to one partial per CTA (fixed order: deterministic), and the three maps the
+//                    gradient needs  d ssim/d mu1, d ssim/d E[x^2], d ssim/d E[xy]  pre-scaled by d loss_v/d ssim.
+//   loss_bwd_kernel  the window is symmetric and the padding is zero, so the adjoint of the convolution is the
+//                    same convolution: d loss_v/dx = conv(A) + 2 x conv(B) + y conv(C) + the L1 / L2 terms,
+//                    times the upstream dL/d loss_v of the view (a device array, so autograd needs no extra pass).
+//   loss_finish_kernel  per-view sums of the CTA partials in double, total = sum_v w_v loss_v.
+//
+// Bound: HBM for the two streaming kernels — algorithmic bytes per pixel and channel: forward 4 (pred) + 4 | 1
+// (target fp32 | u8) + 12 (maps), backward 12 + 4 + 4 | 1 + 4 (gradient) = 44 | 38 B.
+#include <cmath>
+#include "common.cuh"
+
+namespace tgr {
+
+constexpr int LT = 32;             // output tile side
+constexpr int LR = 5;              // window radius: window_size 11 (loss_utils.py:32)
+constexpr int LW = 2 * LR + 1;     // 11
+constexpr int LH = LT + 2 * LR;    // 42: tile + halo
+constexpr int LTHREADS = 256;
+constexpr int LROWS = LT / (LTHREADS / LT);   // 4 output rows per thread in the vertical pass
+
+__constant__ float c_win[LW];
+
+struct LossArgs {
+  const float* pred;
+  const void* target;
+  const float* view_w;   // [V] or nullptr (1/V)
+  float* maps;           // [3][V*3*H*W]
+  float* partial;        // [V*3*tiles]
+  float* grad;           // [V*3*H*W]
+  int W, H, V;
+  float w_l1, w_l2, w_ss;
+};
+
+template <bool U8>
+__device__ __forceinline__ float load_target(const void* t, size_t i) {
+  if (U8) return (float)static_cast<const uint8_t*>(t)[i] / 255.0f;   // general_utils.py:8
+  return static_cast<const float*>(t)[i];
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) red[w] = v;
+  __syncthreads();
+  float s = 0.f;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < LTHREADS / 32; ++i) s += red[i];
+  }
+  return s;   // valid in thread 0
+}
+
+template <bool U8, bool SSIM>
+__global__ void __launch_bounds__(LTHREADS) loss_fwd_kernel(const LossArgs a) {
+  __shared__ float sP[LH][LH];
+  __shared__ float sG[LH][LH];
+  __shared__ float sHz[5][LH][LT];
+  __shared__ float red[LTHREADS / 32];
+
+  const int plane = blockIdx.z;                 // v * 3 + c
+  const int x0 = blockIdx.x * LT, y0 = blockIdx.y * LT;
+  const size_t base = (size_t)plane * a.H * a.W;
+  const int tid = threadIdx.x;
+  const int tx = tid & (LT - 1), ty = tid / LT;  // 32 x 8
+
+  const float inv_n = 1.0f / (3.0f * (float)a.H * (float)a.W);
+
+  if (SSIM) {
+    for (int i = tid; i < LH * LH; i += LTHREADS) {
+      const int r = i / LH, c = i - r * LH;
+      const int gy = y0 + r - LR, gx = x0 + c - LR;
+      float p = 0.f, g = 0.f;
+      if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
+        const size_t o = base + (size_t)gy * a.W + gx;
+        p = a.pred[o];
+        g = load_target<U8>(a.target, o);
+      }
+      sP[r][c] = p;
+      sG[r][c] = g;
+    }
+    __syncthreads();
+    // horizontal pass: rows of the halo'd tile, the tile's 32 columns
+    for (int r = ty; r < LH; r += LTHREADS / LT) {
+      float m1 = 0.f, m2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+#pragma unroll
+      for (int k = 0; k < LW; ++k) {
+        const float w = c_win[k];
+        const float p = sP[r][tx + k], g = sG[r][tx + k];
+        m1 = fmaf(w, p, m1);
+        m2 = fmaf(w, g, m2);
+        e11 = fmaf(w, p * p, e11);
+        e22 = fmaf(w, g * g, e22);
+        e12 = fmaf(w, p * g, e12);
+      }
+      sHz[0][r][tx] = m1;
+      sHz[1][r][tx] = m2;
+      sHz[2][r][tx] = e11;
+      sHz[3][r][tx] = e22;
+      sHz[4][r][tx] = e12;
+    }
+    __syncthreads();
+  }
+
+  // vertical pass + map: thread owns column tx, rows ty*4 .. ty*4+3
+  float acc = 0.f;
+  float q[5][LROWS];
+  if (SSIM) {
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+      float col[LROWS + LW - 1];
+#pragma unroll
+      for (int k = 0; k < LROWS + LW - 1; ++k) col[k] = sHz[m][ty * LROWS + k][tx];
+#pragma unroll
+      for (int j = 0; j < LROWS; ++j) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < LW; ++k) s = fmaf(c_win[k], col[j + k], s);
+        q[m][j] = s;
+      }
+    }
+  }
+  const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;   // loss_utils.py:54-55
+  const float gs = -a.w_ss * inv_n;                     // d loss_v / d ssim_map(pixel)
+  const size_t plane_sz = (size_t)a.V * 3 * a.H * a.W;
+#pragma unroll
+  for (int j = 0; j < LROWS; ++j) {
+    const int gy = y0 + ty * LROWS + j, gx = x0 + tx;
+    if (gy < a.H && gx < a.W) {
+      const size_t o = base + (size_t)gy * a.W + gx;
+      float p, g;
+      if (SSIM) {
+        p = sP[ty * LROWS + j + LR][tx + LR];
+        g = sG[ty * LROWS + j + LR][tx + LR];
+      } else {
+        p = a.pred[o];
+        g = load_target<U8>(a.target, o);
+      }
+      const float d = p - g;
+      float term = a.w_l1 * fabsf(d) + a.w_l2 * d * d;
+      if (SSIM) {
+        const float mu1 = q[0][j], mu2 = q[1][j];
+        const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
+        const float s1 = q[2][j] - mu1_sq, s2 = q[3][j] - mu2_sq, s12 = q[4][j] - mu12;   // loss_utils.py:50-52
+        const float A = mu1_sq + mu2_sq + C1, B = s1 + s2 + C2;
+        const float Cn = 2.f * mu12 + C1, D = 2.f * s12 + C2;
+        const float ssim = (Cn * D) / (A * B);                                            // loss_utils.py:57
+        term += a.w_ss * (1.f - ssim);
+        // derivatives of the map wrt the three window moments that depend on pred (mu1, E[x^2], E[xy]);
+        // sigma1_sq = E[x^2] - mu1^2 and sigma12 = E[xy] - mu1 mu2 folded into d/d mu1
+        const float iAB = 1.f / (A * B);
+        const float d_s1 = -Cn * D * iAB / B;
+        const float d_s12 = 2.f * Cn * iAB;
+        const float d_mu1 = 2.f * mu2 * D * iAB - 2.f * mu1 * Cn * D * iAB / A - 2.f * mu1 * d_s1 - mu2 * d_s12;
+        a.maps[o] = gs * d_mu1;
+        a.maps[plane_sz + o] = gs * d_s1;
+        a.maps[2 * plane_sz + o] = gs * d_s12;
+      }
+      acc += term;
+    }
+  }
+  const float s = block_sum(acc, red);
+  if (tid == 0) a.partial[((size_t)plane * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = s * inv_n;
+}
+
+template <bool U8, bool SSIM>
+__global__ void __launch_bounds__(LTHREADS) loss_bwd_kernel(const LossArgs a) {
+  __shared__ float sM[3][LH][LH];
+  __shared__ float sHz[3][LH][LT];
+
+  const int plane = blockIdx.z;
+  const int v = plane / 3;
+  const int x0 = blockIdx.x * LT, y0 = blockIdx.y * LT;
+  const size_t base = (size_t)plane * a.H * a.W;
+  const size_t plane_sz = (size_t)a.V * 3 * a.H * a.W;
+  const int tid = threadIdx.x;
+  const int tx = tid & (LT - 1), ty = tid / LT;
+  const float wv = a.view_w ? a.view_w[v] : 1.0f / (float)a.V;   // here: dL / d loss_v
+  const float inv_n = 1.0f / (3.0f * (float)a.H * (float)a.W);
+
+  float q[3][LROWS];
+  if (SSIM) {
+    for (int i = tid; i < LH * LH; i += LTHREADS) {
+      const int r = i / LH, c = i - r * LH;
+      const int gy = y0 + r - LR, gx = x0 + c - LR;
+      float m0 = 0.f, m1 = 0.f, m2 = 0.f;
+      if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
+        const size_t o = base + (size_t)gy * a.W + gx;
+        m0 = a.maps[o];
+        m1 = a.maps[plane_sz + o];
+        m2 = a.maps[2 * plane_sz + o];
+      }
+      sM[0][r][c] = m0;
+      sM[1][r][c] = m1;
+      sM[2][r][c] = m2;
+    }
+    __syncthreads();
+    for (int r = ty; r < LH; r += LTHREADS / LT) {
+      float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < LW; ++k) {
+        const float w = c_win[k];
+        h0 = fmaf(w, sM[0][r][tx + k], h0);
+        h1 = fmaf(w, sM[1][r][tx + k], h1);
+        h2 = fmaf(w, sM[2][r][tx + k], h2);
+      }
+      sHz[0][r][tx] = h0;
+      sHz[1][r][tx] = h1;
+      sHz[2][r][tx] = h2;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      float col[LROWS + LW - 1];
+#pragma unroll
+      for (int k = 0; k < LROWS + LW - 1; ++k) col[k] = sHz[m][ty * LROWS + k][tx];
+#pragma unroll
+      for (int j = 0; j < LROWS; ++j) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < LW; ++k) s = fmaf(c_win[k], col[j + k], s);
+        q[m][j] = s;
+      }
+    }
+  }
+  const float k1 = a.w_l1 * wv * inv_n, k2 = 2.f * a.w_l2 * wv * inv_n;
+#pragma unroll
+  for (int j = 0; j < LROWS; ++j) {
+    const int gy = y0 + ty * LROWS + j, gx = x0 + tx;
+    if (gy < a.H && gx < a.W) {
+      const size_t o = base + (size_t)gy * a.W + gx;
+      const float p = a.pred[o];
+      const float g = load_target<U8>(a.target, o);
+      const float d = p - g;
+      float gr = k1 * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) + k2 * d;   // torch.abs backward: sign(0) = 0
+      if (SSIM) gr += wv * (q[0][j] + 2.f * p * q[1][j] + g * q[2][j]);
+      a.grad[o] = gr;
+    }
+  }
+}
+
+// loss_out[1 + v] = sum of view v's partials (double, fixed order); loss_out[0] = sum_v w_v loss_v.
+__global__ void __launch_bounds__(1024) loss_finish_kernel(const float* __restrict__ partial, int per_view, int V,
+                                                           const float* __restrict__ view_w, float* __restrict__ out) {
+  __shared__ double red[32];
+  __shared__ double total;
+  if (threadIdx.x == 0) total = 0.0;
+  for (int v = 0; v < V; ++v) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < per_view; i += blockDim.x) s += (double)partial[(size_t)v * per_view + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+      out[1 + v] = (float)t;
+      total += t * (double)(view_w ? view_w[v] : 1.0f / (float)V);
+    }
+  }
+  if (threadIdx.x == 0) out[0] = (float)total;
+}
+
+static void upload_window() {
+  // loss_utils.py:23-25: float32 tensor of exp(-(x - 5)^2 / (2 sigma^2)), divided by its float32 sum
+  static thread_local int done_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (done_dev == dev) return;
+  float g[LW], s = 0.f;
+  for (int x = 0; x < LW; ++x) {
+    g[x] = (float)std::exp(-(double)((x - LW / 2) * (x - LW / 2)) / (2.0 * 1.5 * 1.5));
+    s += g[x];
+  }
+  for (int x = 0; x < LW; ++x) g[x] /= s;
+  cudaMemcpyToSymbol(c_win, g, sizeof(g));
+  done_dev = dev;
+}
+
+static inline uint64_t loss_tiles(int W, int H) { return (uint64_t)((W + LT - 1) / LT) * ((H + LT - 1) / LT); }
+
+}  // namespace tgr
+
+using namespace tgr;
+
+extern "C" uint64_t tgr_image_loss_bytes(int32_t n_views, int32_t W, int32_t H) {
+  if (n_views <= 0 || W <= 0 || H <= 0) return 256;
+  const uint64_t px = (uint64_t)n_views * 3 * (uint64_t)W * H;
+  return align_up(3 * px * 4, 256) + align_up((uint64_t)n_views * 3 * loss_tiles(W, H) * 4, 256) + 256;
+}
+
+static int loss_check(int32_t V, int32_t W, int32_t H, const void* pred, const void* target, const void* ws,
+                      uint64_t ws_bytes) {
+  if (V <= 0 || W <= 0 || H <= 0) { set_error("image_loss: bad sizes V=%d W=%d H=%d", V, W, H); return 1; }
+  if (!pred || !target || !ws) { set_error("image_loss: null pointer"); return 1; }
+  if (ws_bytes < tgr_image_loss_bytes(V, W, H)) { set_error("image_loss: workspace too small"); return 1; }
+  if ((uint64_t)V * 3 > 65535) { set_error("image_loss: too many views per call (%d)", V); return 1; }
+  return 0;
+}
+
+static LossArgs loss_args(int32_t V, int32_t W, int32_t H, const float* pred, const void* target, const float* view_w,
+                          float l1, float l2, float ss, float* grad, void* workspace) {
+  const uint64_t px = (uint64_t)V * 3 * (uint64_t)W * H;
+  LossArgs a;
+  a.pred = pred;
+  a.target = target;
+  a.view_w = view_w;
+  a.maps = static_cast<float*>(workspace);
+  a.partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + align_up(3 * px * 4, 256));
+  a.grad = grad;
+  a.W = W; a.H = H; a.V = V;
+  a.w_l1 = l1; a.w_l2 = l2; a.w_ss = ss;
+  return a;
+}
+
+#define TGR_LOSS_LAUNCH(K, u8, ssim, grid, s, a)                                                                   \
+  do {                                                                                                             \
+    if (u8) { if (ssim) K<true, true><<<grid, LTHREADS, 0, s>>>(a); else K<true, false><<<grid, LTHREADS, 0, s>>>(a); }   \
+    else    { if (ssim) K<false, true><<<grid, LTHREADS, 0, s>>>(a); else K<false, false><<<grid, LTHREADS, 0, s>>>(a); } \
+  } while (0)
+
+extern "C" int tgr_image_loss_forward(int32_t V, int32_t W, int32_t H, const float* pred, const void* target,
+                                      int32_t target_is_u8, const float* view_weights, float l1_weight,
+                                      float l2_weight, float dssim_weight, float* loss_out, void* workspace,
+                                      uint64_t workspace_bytes, void* stream) {
+  if (int rc = loss_check(V, W, H, pred, target, workspace, workspace_bytes)) return rc;
+  if (!loss_out) { set_error("image_loss: null loss_out"); return 1; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  upload_window();
+  const LossArgs a = loss_args(V, W, H, pred, target, view_weights, l1_weight, l2_weight, dssim_weight, nullptr, workspace);
+  const dim3 grid((W + LT - 1) / LT, (H + LT - 1) / LT, V * 3);
+  TGR_LOSS_LAUNCH(loss_fwd_kernel, target_is_u8 != 0, dssim_weight != 0.f, grid, s, a);
+  loss_finish_kernel<<<1, 1024, 0, s>>>(a.partial, (int)(3 * loss_tiles(W, H)), V, view_weights, loss_out);
+  count_launch(2);
+  return check_launch("image_loss_forward", false, s);
+}
+
+extern "C" int tgr_image_loss_backward(int32_t V, int32_t W, int32_t H, const float* pred, const void* target,
+                                       int32_t target_is_u8, const float* dL_dloss_view, float l1_weight,
+                                       float l2_weight, float dssim_weight, float* dL_dpred, void* workspace,
+                                       uint64_t workspace_bytes, void* stream) {
+  if (int rc = loss_check(V, W, H, pred, target, workspace, workspace_bytes)) return rc;
+  if (!dL_dpred) { set_error("image_loss: null dL_dpred"); return 1; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  upload_window();
+  const LossArgs a = loss_args(V, W, H, pred, target, dL_dloss_view, l1_weight, l2_weight, dssim_weight, dL_dpred, workspace);
+  const dim3 grid((W + LT - 1) / LT, (H + LT - 1) / LT, V * 3);
+  TGR_LOSS_LAUNCH(loss_bwd_kernel, target_is_u8 != 0, dssim_weight != 0.f, grid, s, a);
+  count_launch();
+  return check_launch("image_loss_backward", false, s);
+}
+
+extern "C" int tgr_image_loss(int32_t V, int32_t W, int32_t H, const float* pred, const void* target,
+                              int32_t target_is_u8, const float* view_weights, float l1_weight, float l2_weight,
+                              float dssim_weight, float* loss_out, float* dL_dpred, void* workspace,
+                              uint64_t workspace_bytes, void* stream) {
+  if (int rc = tgr_image_loss_forward(V, W, H, pred, target, target_is_u8, view_weights, l1_weight, l2_weight,
+                                      dssim_weight, loss_out, workspace, workspace_bytes, stream)) return rc;
+  if (!dL_dpred) return 0;
+  return tgr_image_loss_backward(V, W, H, pred, target, target_is_u8, view_weights, l1_weight, l2_weight, dssim_weight,
+                                 dL_dpred, workspace, workspace_bytes, stream);
+}
