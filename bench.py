@@ -53,6 +53,8 @@ def parse():
                     help="N > 1, gradient exchange: nvls = own in-switch all-reduce kernel on a symmetric-memory buffer "
                          "(default), nccl = one NCCL all-reduce, rows / sh = NCCL per Gaussian range overlapped with the backward")
     ap.add_argument("--comm-chunks", type=int, default=4, help="Gaussian ranges for --comm rows / sh")
+    ap.add_argument("--no-train-step", action="store_true",
+                    help="skip the train_step leg (render + image loss + backward + Adam, SURVEY §8 f1-f3)")
     ap.add_argument("--per-view-api", action="store_true",
                     help="ours: loop over the single-view drop-in calls instead of the multi-view batch")
     return ap.parse_args()
@@ -482,6 +484,164 @@ def cpu_oracle_baseline(cfg, budget_tiles=420):
                       % (P, t_pre, len(pick), len(nonempty), t_blend, frac)}
 
 
+# ----------------------------------------------------------------------------------------------------
+# Training step through the rows either side of the rasterizer: render V views, the
+# reference's image loss 0.8 L1 + 0.2 (1 - SSIM) against uint8 targets from pinned host memory, backward, Adam.
+# Both arms run the same semantics (one optimizer step per V-view batch, gradients summed over the views); the
+# learning rates are the reference's defaults x 1e-3 so that the synthetic scene — trained against random targets
+# here — does not drift during the timed region (the kernels' cost does not depend on the rates).
+def _train_opt():
+    from youreditableavatar_b200.optimizer import OptimizationParams
+    o = OptimizationParams()
+    k = 1e-3
+    return OptimizationParams(position_lr_init=o.position_lr_init * k, position_lr_final=o.position_lr_final * k,
+                              feature_lr=o.feature_lr * k, opacity_lr=o.opacity_lr * k, scaling_lr=o.scaling_lr * k,
+                              rotation_lr=o.rotation_lr * k)
+
+
+def _time_events(fn, reps):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def train_step_ours(P, res, act, cams, targets_host, V, steps, warmup, peak):
+    from youreditableavatar_b200 import _lib, loss_utils
+    from youreditableavatar_b200.optimizer import TetGSOptimizer
+    from youreditableavatar_b200.parallel import GradBucket, render_views_fwd_bwd
+    L = _lib.lib()
+    params = {k: act[k].clone() for k in ("means3D", "opacities", "scales", "rotations", "shs")}
+    bucket = GradBucket(P, 16, "cuda", names=GradBucket.TRAINING)
+    gv = bucket.named()
+    opt = TetGSOptimizer({"points": params["means3D"], "sh": params["shs"], "all_densities": params["opacities"],
+                          "scales": params["scales"], "quaternions": params["rotations"]}, _train_opt(), 1.0,
+                         grads={"points": gv["dL_dmeans3D"], "sh": gv["dL_dsh"], "all_densities": gv["dL_dopacity"],
+                                "scales": gv["dL_dscales"], "quaternions": gv["dL_drotations"]})
+    feeder = BatchFeeder([cam_to_host(c) for c in cams], targets_host)
+    ws = torch.empty(L.tgr_image_loss_bytes(V, res, res), dtype=torch.uint8, device="cuda")
+    box = {}
+
+    def upstream(color, depth, alpha):
+        out, grad = loss_utils.image_loss_and_grad(color, feeder.targets_dev(), 0.8, 0.0, 0.2, workspace=ws)
+        box["loss"] = out[0]
+        return grad, None, None
+
+    def step():
+        cs = feeder.begin_step()
+        opt.update_learning_rate()
+        render_views_fwd_bwd(params, cs, 3, upstream, bucket, extras=False)
+        opt.step()
+        return feeder.end_step(box["loss"])
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    n0 = L.tgr_kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    last_loss = feeder.drain()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    launches = (L.tgr_kernel_launches() - n0) // steps
+    # the two new kernels alone (inputs exceed the L2: 126 MB of images + 302 MB of maps; 944 MB of optimizer state)
+    color = torch.rand(V, 3, res, res, device="cuda")
+    tgt = targets_host.cuda()
+    ms_loss = _time_events(lambda: loss_utils.image_loss_and_grad(color, tgt, 0.8, 0.0, 0.2, workspace=ws), 10)
+    ms_adam = _time_events(opt.step, 10)
+    n_px = V * 3 * res * res
+    loss_bytes = n_px * (4 + 1 + 12 + 12 + 4 + 1 + 4)           # fwd 17 B + bwd 21 B per pixel-channel (u8 target)
+    n_par = sum(g["params"][0].numel() for g in opt.optimizer.param_groups)
+    adam_bytes = n_par * 28                                       # p, g, m, v read; p, m, v written
+    return {"value": V * 1000.0 / ms, "unit": UNIT, "ms_per_step": ms, "views_per_step": V, "kernel_launches_per_step": int(launches),
+            "loss": last_loss, "h2d_bytes_per_step": int(targets_host.numel() + V * 38 * 4), "d2h_bytes_per_step": 4,
+            "what": "BatchFeeder (uint8 targets + cameras from pinned host memory) -> multi-view render -> fused "
+                    "0.8 L1 + 0.2 (1 - SSIM) loss and gradient (tgr_image_loss, 3 launches) -> backward into the flat "
+                    "bucket -> one-launch Adam over 5 parameter groups (tgr_adam_step) -> async loss read-back",
+            "image_loss": {"ms": ms_loss, "algorithmic_bytes": loss_bytes, "achieved_gbs": loss_bytes / ms_loss / 1e6,
+                           "frac_of_hbm_peak": loss_bytes / ms_loss / 1e6 / peak, "launches": 3},
+            "adam": {"ms": ms_adam, "parameters": n_par, "algorithmic_bytes": adam_bytes,
+                     "achieved_gbs": adam_bytes / ms_adam / 1e6, "frac_of_hbm_peak": adam_bytes / ms_adam / 1e6 / peak,
+                     "launches": 1}}
+
+
+def train_step_reference(P, res, act, cams, targets_host, V, steps, warmup):
+    """The reference's own pieces: its CUDA rasterizer (oracle/_ref) one view per call, its loss as the ATen op
+    sequence of utils/loss_utils.py in fp32 (oracle/train_oracle.image_loss(dtype=float32)) with autograd,
+    torch.optim.Adam(eps=1e-15) over its six parameter groups (tetgs_optimizer.py:66-92)."""
+    from oracle import ref_cuda, train_oracle
+    o = _train_opt()
+    leaf = lambda t: t.clone().requires_grad_(True)
+    pts, opa, sca, rot = leaf(act["means3D"]), leaf(act["opacities"]), leaf(act["scales"]), leaf(act["rotations"])
+    dc, rest = leaf(act["shs"][:, :1]), leaf(act["shs"][:, 1:])
+    ta = torch.optim.Adam([{"params": [pts], "lr": o.position_lr_init}, {"params": [dc], "lr": o.feature_lr},
+                           {"params": [rest], "lr": o.feature_lr / 20.0}, {"params": [opa], "lr": o.opacity_lr},
+                           {"params": [sca], "lr": o.scaling_lr}, {"params": [rot], "lr": o.rotation_lr}], lr=0.0, eps=1e-15)
+    feeder = HostFeeder([cam_to_host(c) for c in cams], targets_host)
+
+    def step():
+        feeder.begin_step()
+        with torch.no_grad():
+            cur = {"means3D": pts, "opacities": opa, "scales": sca, "rotations": rot,
+                   "shs": torch.cat([dc, rest], dim=1)}                    # tetgs_model.py sh_coordinates: cat(dc, rest)
+        acc, loss = None, None
+        for i in range(V):
+            cam, tgt = feeder.view(i)
+            with torch.no_grad():
+                fwd = ref_cuda.forward(cur, cam, 3)
+            p = fwd[1].detach().requires_grad_(True)
+            l, _ = train_oracle.image_loss(p[None], (tgt.float() / 255.0)[None], 0.8, 0.0, 0.2, dtype=torch.float32)
+            (l / V).backward()
+            loss = l.detach() / V if loss is None else loss + l.detach() / V
+            with torch.no_grad():
+                g = ref_cuda.backward(cur, cam, 3, fwd, p.grad)
+                need = (2, 3, 5, 6, 7)
+                if acc is None:
+                    acc = [g[k] for k in need]
+                else:
+                    for a, k in zip(acc, need):
+                        a.add_(g[k])
+        opa.grad, pts.grad, sca.grad, rot.grad = acc[0], acc[1], acc[3], acc[4]
+        dc.grad, rest.grad = acc[2][:, :1].contiguous(), acc[2][:, 1:].contiguous()   # what cat's backward produces
+        ta.step()
+        return feeder.end_step(loss)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    last_loss = feeder.drain()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    color = torch.rand(1, 3, res, res, device="cuda")
+    tgt = torch.rand(1, 3, res, res, device="cuda")
+
+    def loss_once():
+        p = color.clone().requires_grad_(True)
+        train_oracle.image_loss(p, tgt, 0.8, 0.0, 0.2, dtype=torch.float32)[0].backward()
+
+    ms_loss = _time_events(loss_once, 10) * V
+    ms_adam = _time_events(ta.step, 10)
+    return {"value": V * 1000.0 / ms, "unit": UNIT, "ms_per_step": ms, "views_per_step": V, "loss": last_loss,
+            "what": "HostFeeder -> reference CUDA rasterizer one view per call -> loss_utils.py op sequence in fp32 "
+                    "(ATen conv2d + elementwise, autograd) -> gradient accumulation over the views -> torch.optim.Adam "
+                    "over 6 groups -> async loss read-back",
+            "image_loss": {"ms": ms_loss, "note": "V single-view fwd+bwd evaluations"},
+            "adam": {"ms": ms_adam}}
+
+
 def main():
     args = parse()
     world, rank, local = dist_setup(args)
@@ -638,9 +798,21 @@ def main():
         if per_view is not None:
             out["per_view_api"] = per_view
         out["stages"] = stage
+        if batched and world == 1 and not args.no_train_step:
+            try:
+                out["train_step"] = train_step_ours(P, res, act, cams, targets_host, V, max(4, args.steps // 2),
+                                                    max(args.warmup, 3), peak)
+            except Exception as ex:   # the rasterize metric above stands on its own
+                out["train_step"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_oracle_baseline(cfg)
     else:
+        if world == 1 and not args.no_train_step:
+            try:
+                out["train_step"] = train_step_reference(P, res, act, cams, targets_host, V, max(4, args.steps // 2),
+                                                         max(args.warmup, 3))
+            except Exception as ex:
+                out["train_step"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
         out["impl"] = "reference"
         out["reference_kind"] = "reference CUDA rasterizer, unmodified sources compiled for sm_100a into oracle/_ref"
         out["gpu_launches"] = None

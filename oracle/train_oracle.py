@@ -37,10 +37,11 @@ def gaussian_window(window_size: int = 11, sigma: float = 1.5) -> torch.Tensor:
 
 
 def ssim_map(img1: torch.Tensor, img2: torch.Tensor, window_size: int = 11) -> torch.Tensor:
-    """loss_utils.py:44-59 on [B,C,H,W] float64; the 2-D window is the float32 outer product (loss_utils.py:27-31)."""
+    """loss_utils.py:44-59 on [B,C,H,W] (float64 unless the caller asks otherwise); the 2-D window is the float32
+    outer product (loss_utils.py:27-31)."""
     C = img1.size(-3)
     w1 = gaussian_window(window_size).to(torch.float32).unsqueeze(1)
-    w2 = w1.mm(w1.t()).to(F64)
+    w2 = w1.mm(w1.t()).to(device=img1.device, dtype=img1.dtype)
     window = w2.unsqueeze(0).unsqueeze(0).expand(C, 1, window_size, window_size).contiguous()
     pad = window_size // 2
     mu1 = F.conv2d(img1, window, padding=pad, groups=C)
@@ -54,17 +55,20 @@ def ssim_map(img1: torch.Tensor, img2: torch.Tensor, window_size: int = 11) -> t
 
 
 def image_loss(pred: torch.Tensor, target: torch.Tensor, l1_weight: float = 0.8, l2_weight: float = 0.0,
-               dssim_weight: float = 0.2, view_weights: Optional[Sequence[float]] = None):
+               dssim_weight: float = 0.2, view_weights: Optional[Sequence[float]] = None, dtype=F64):
     """pred, target: [V,3,H,W].  Returns (total, per_view[V]) in float64 with autograd attached to `pred`.
     Per view: refine.py:247 with l1_loss / l2_loss / ssim of loss_utils.py:17-21,33-42 applied to that view alone
-    (the reference renders one view per step); total = sum_v w_v loss_v, w_v = 1/V by default."""
-    p, g = pred.to(F64), target.to(F64)
+    (the reference renders one view per step); total = sum_v w_v loss_v, w_v = 1/V by default.
+    dtype=torch.float32 on CUDA tensors is the reference's own precision and op sequence (five grouped conv2d +
+    elementwise ATen kernels) — what bench.py's `--impl reference` arm times."""
+    p, g = pred.to(dtype), target.to(dtype)
     V = p.shape[0]
     d = p - g
     per = l1_weight * d.abs().mean(dim=(1, 2, 3)) + l2_weight * (d * d).mean(dim=(1, 2, 3))
     if dssim_weight != 0.0:
         per = per + dssim_weight * (1.0 - ssim_map(p, g).mean(dim=(1, 2, 3)))
-    w = torch.full((V,), 1.0 / V, dtype=F64) if view_weights is None else torch.as_tensor(view_weights, dtype=F64)
+    w = torch.full((V,), 1.0 / V, dtype=dtype, device=p.device) if view_weights is None else \
+        torch.as_tensor(view_weights, dtype=dtype).to(p.device)
     return (w * per).sum(), per
 
 

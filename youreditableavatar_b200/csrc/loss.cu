@@ -40,13 +40,35 @@ struct LossArgs {
   float* partial;        // [V*3*tiles]
   float* grad;           // [V*3*H*W]
   int W, H, V;
+  int vec;               // W % 4 == 0 and 16-byte aligned images: tiles are staged with 16-byte loads
   float w_l1, w_l2, w_ss;
 };
 
+// u / 255 correctly rounded (general_utils.py:8 divides the 8-bit image by 255.0 on the CPU) without the IEEE
+// division sequence: q = RN(u r), r = RN(1/255), one Newton step on the exact residual.  Equal to (float)u / 255.0f
+// for all 256 inputs (checked exhaustively; tests compare the u8 and fp32 target paths bit for bit).
+__device__ __forceinline__ float u8_unit(uint32_t u) {
+  const float x = (float)u, r = 1.0f / 255.0f;
+  const float q = x * r;
+  return fmaf(fmaf(-q, 255.0f, x), r, q);
+}
+
 template <bool U8>
 __device__ __forceinline__ float load_target(const void* t, size_t i) {
-  if (U8) return (float)static_cast<const uint8_t*>(t)[i] / 255.0f;   // general_utils.py:8
+  if (U8) return u8_unit(static_cast<const uint8_t*>(t)[i]);
   return static_cast<const float*>(t)[i];
+}
+
+// Stages rows [y0 - 5, y0 + 37) x columns [x0 - 5, x0 + 37) of up to three fp32 planes (or a u8 plane) into shared
+// memory with 16-byte global loads: the 42 columns are covered by the 12 ALIGNED float4 starting at x0 - 8, so a
+// CTA issues 504 vector loads per plane instead of 1764 scalar ones; W % 4 == 0 makes every vector wholly inside
+// or wholly outside the image (outside = the zero padding of the convolution, loss_utils.py:45).
+constexpr int LV4 = 12;
+__device__ __forceinline__ void put4(float* row, int c, const float4 v) {
+  if (c >= 0) row[c] = v.x;
+  if (c + 1 >= 0) row[c + 1] = v.y;
+  if (c + 2 < LH) row[c + 2] = v.z;
+  if (c + 3 < LH) row[c + 3] = v.w;
 }
 
 __device__ __forceinline__ float block_sum(float v, float* red) {
@@ -63,11 +85,21 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return s;   // valid in thread 0
 }
 
+// Shared-memory geometry: the staged tile rows have pitch 43 and the row-filtered planes pitch 33 so that the
+// register-blocked horizontal pass (a thread owns 8 consecutive outputs of one row: 18 loads instead of 88, the
+// products p*p, g*g, p*g formed once per staged pixel instead of once per tap) is bank-conflict free both ways:
+// lane t reads row t/4, columns 8(t%4)+k -> bank (11 r + 8 j + k) mod 32, all 32 distinct; it writes bank
+// (r + 8 j + i) mod 32, all distinct.
+constexpr int LPP = LH + 1;        // 43: pitch of the staged tiles
+constexpr int LHP = LT + 1;        // 33: pitch of the horizontally filtered planes
+constexpr int LXB = 8;             // outputs per thread in the horizontal pass
+constexpr int LTASKS = LH * (LT / LXB);   // 168 (row, 8-column group) tasks per plane
+
 template <bool U8, bool SSIM>
 __global__ void __launch_bounds__(LTHREADS) loss_fwd_kernel(const LossArgs a) {
-  __shared__ float sP[LH][LH];
-  __shared__ float sG[LH][LH];
-  __shared__ float sHz[5][LH][LT];
+  __shared__ float sP[LH][LPP];
+  __shared__ float sG[LH][LPP];
+  __shared__ float sHz[5][LH][LHP];
   __shared__ float red[LTHREADS / 32];
 
   const int plane = blockIdx.z;                 // v * 3 + c
@@ -79,37 +111,74 @@ __global__ void __launch_bounds__(LTHREADS) loss_fwd_kernel(const LossArgs a) {
   const float inv_n = 1.0f / (3.0f * (float)a.H * (float)a.W);
 
   if (SSIM) {
-    for (int i = tid; i < LH * LH; i += LTHREADS) {
-      const int r = i / LH, c = i - r * LH;
-      const int gy = y0 + r - LR, gx = x0 + c - LR;
-      float p = 0.f, g = 0.f;
-      if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
-        const size_t o = base + (size_t)gy * a.W + gx;
-        p = a.pred[o];
-        g = load_target<U8>(a.target, o);
+    if (a.vec) {
+      for (int t = tid; t < LH * LV4; t += LTHREADS) {
+        const int r = t / LV4, j = t - r * LV4;
+        const int gy = y0 + r - LR, gx = x0 - 8 + 4 * j;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f), g = p;
+        if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
+          const size_t o = base + (size_t)gy * a.W + gx;
+          p = *reinterpret_cast<const float4*>(a.pred + o);
+          if (U8) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(a.target) + o);
+            g = make_float4(u8_unit(w & 0xffu), u8_unit((w >> 8) & 0xffu), u8_unit((w >> 16) & 0xffu), u8_unit(w >> 24));
+          } else {
+            g = *reinterpret_cast<const float4*>(static_cast<const float*>(a.target) + o);
+          }
+        }
+        put4(sP[r], 4 * j - 3, p);
+        put4(sG[r], 4 * j - 3, g);
       }
-      sP[r][c] = p;
-      sG[r][c] = g;
+    } else {
+      for (int r = ty; r < LH; r += LTHREADS / LT) {
+        const int gy = y0 + r - LR;
+        const bool row_ok = gy >= 0 && gy < a.H;
+        const size_t ro = base + (size_t)(row_ok ? gy : 0) * a.W;
+#pragma unroll
+        for (int c = tx; c < LH; c += LT) {
+          const int gx = x0 + c - LR;
+          float p = 0.f, g = 0.f;
+          if (row_ok && gx >= 0 && gx < a.W) {
+            p = a.pred[ro + gx];
+            g = load_target<U8>(a.target, ro + gx);
+          }
+          sP[r][c] = p;
+          sG[r][c] = g;
+        }
+      }
     }
     __syncthreads();
-    // horizontal pass: rows of the halo'd tile, the tile's 32 columns
-    for (int r = ty; r < LH; r += LTHREADS / LT) {
-      float m1 = 0.f, m2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+    // horizontal pass: 42 rows x 4 groups of 8 columns
+    if (tid < LTASKS) {
+      const int r = tid >> 2, c0 = (tid & 3) * LXB;
+      float m1[LXB], m2[LXB], e11[LXB], e22[LXB], e12[LXB];
 #pragma unroll
-      for (int k = 0; k < LW; ++k) {
-        const float w = c_win[k];
-        const float p = sP[r][tx + k], g = sG[r][tx + k];
-        m1 = fmaf(w, p, m1);
-        m2 = fmaf(w, g, m2);
-        e11 = fmaf(w, p * p, e11);
-        e22 = fmaf(w, g * g, e22);
-        e12 = fmaf(w, p * g, e12);
+      for (int i = 0; i < LXB; ++i) m1[i] = m2[i] = e11[i] = e22[i] = e12[i] = 0.f;
+#pragma unroll
+      for (int k = 0; k < LXB + LW - 1; ++k) {
+        const float p = sP[r][c0 + k], g = sG[r][c0 + k];
+        const float pp = p * p, gg = g * g, pg = p * g;
+#pragma unroll
+        for (int i = 0; i < LXB; ++i) {
+          const int t = k - i;                   // tap index of staged column k for output i
+          if (t >= 0 && t < LW) {
+            const float w = c_win[t];
+            m1[i] = fmaf(w, p, m1[i]);
+            m2[i] = fmaf(w, g, m2[i]);
+            e11[i] = fmaf(w, pp, e11[i]);
+            e22[i] = fmaf(w, gg, e22[i]);
+            e12[i] = fmaf(w, pg, e12[i]);
+          }
+        }
       }
-      sHz[0][r][tx] = m1;
-      sHz[1][r][tx] = m2;
-      sHz[2][r][tx] = e11;
-      sHz[3][r][tx] = e22;
-      sHz[4][r][tx] = e12;
+#pragma unroll
+      for (int i = 0; i < LXB; ++i) {
+        sHz[0][r][c0 + i] = m1[i];
+        sHz[1][r][c0 + i] = m2[i];
+        sHz[2][r][c0 + i] = e11[i];
+        sHz[3][r][c0 + i] = e22[i];
+        sHz[4][r][c0 + i] = e12[i];
+      }
     }
     __syncthreads();
   }
@@ -156,14 +225,17 @@ __global__ void __launch_bounds__(LTHREADS) loss_fwd_kernel(const LossArgs a) {
         const float s1 = q[2][j] - mu1_sq, s2 = q[3][j] - mu2_sq, s12 = q[4][j] - mu12;   // loss_utils.py:50-52
         const float A = mu1_sq + mu2_sq + C1, B = s1 + s2 + C2;
         const float Cn = 2.f * mu12 + C1, D = 2.f * s12 + C2;
-        const float ssim = (Cn * D) / (A * B);                                            // loss_utils.py:57
+        // A >= C1 and B ~ C2 + variances > 0: hardware reciprocals (1 ulp) instead of four IEEE divisions
+        const float iA = __fdividef(1.f, A), iB = __fdividef(1.f, B);
+        const float iAB = iA * iB;
+        const float CD = Cn * D;
+        const float ssim = CD * iAB;                                                      // loss_utils.py:57
         term += a.w_ss * (1.f - ssim);
         // derivatives of the map wrt the three window moments that depend on pred (mu1, E[x^2], E[xy]);
         // sigma1_sq = E[x^2] - mu1^2 and sigma12 = E[xy] - mu1 mu2 folded into d/d mu1
-        const float iAB = 1.f / (A * B);
-        const float d_s1 = -Cn * D * iAB / B;
+        const float d_s1 = -ssim * iB;
         const float d_s12 = 2.f * Cn * iAB;
-        const float d_mu1 = 2.f * mu2 * D * iAB - 2.f * mu1 * Cn * D * iAB / A - 2.f * mu1 * d_s1 - mu2 * d_s12;
+        const float d_mu1 = 2.f * mu2 * D * iAB - 2.f * mu1 * ssim * iA - 2.f * mu1 * d_s1 - mu2 * d_s12;
         a.maps[o] = gs * d_mu1;
         a.maps[plane_sz + o] = gs * d_s1;
         a.maps[2 * plane_sz + o] = gs * d_s12;
@@ -177,8 +249,8 @@ __global__ void __launch_bounds__(LTHREADS) loss_fwd_kernel(const LossArgs a) {
 
 template <bool U8, bool SSIM>
 __global__ void __launch_bounds__(LTHREADS) loss_bwd_kernel(const LossArgs a) {
-  __shared__ float sM[3][LH][LH];
-  __shared__ float sHz[3][LH][LT];
+  __shared__ float sM[3][LH][LPP];
+  __shared__ float sHz[3][LH][LHP];
 
   const int plane = blockIdx.z;
   const int v = plane / 3;
@@ -192,33 +264,61 @@ __global__ void __launch_bounds__(LTHREADS) loss_bwd_kernel(const LossArgs a) {
 
   float q[3][LROWS];
   if (SSIM) {
-    for (int i = tid; i < LH * LH; i += LTHREADS) {
-      const int r = i / LH, c = i - r * LH;
-      const int gy = y0 + r - LR, gx = x0 + c - LR;
-      float m0 = 0.f, m1 = 0.f, m2 = 0.f;
-      if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
-        const size_t o = base + (size_t)gy * a.W + gx;
-        m0 = a.maps[o];
-        m1 = a.maps[plane_sz + o];
-        m2 = a.maps[2 * plane_sz + o];
+    if (a.vec) {
+      for (int t = tid; t < LH * LV4; t += LTHREADS) {
+        const int r = t / LV4, j = t - r * LV4;
+        const int gy = y0 + r - LR, gx = x0 - 8 + 4 * j;
+        float4 m0 = make_float4(0.f, 0.f, 0.f, 0.f), m1 = m0, m2 = m0;
+        if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
+          const size_t o = base + (size_t)gy * a.W + gx;
+          m0 = *reinterpret_cast<const float4*>(a.maps + o);
+          m1 = *reinterpret_cast<const float4*>(a.maps + plane_sz + o);
+          m2 = *reinterpret_cast<const float4*>(a.maps + 2 * plane_sz + o);
+        }
+        put4(sM[0][r], 4 * j - 3, m0);
+        put4(sM[1][r], 4 * j - 3, m1);
+        put4(sM[2][r], 4 * j - 3, m2);
       }
-      sM[0][r][c] = m0;
-      sM[1][r][c] = m1;
-      sM[2][r][c] = m2;
+    } else {
+      for (int r = ty; r < LH; r += LTHREADS / LT) {
+        const int gy = y0 + r - LR;
+        const bool row_ok = gy >= 0 && gy < a.H;
+        const size_t ro = base + (size_t)(row_ok ? gy : 0) * a.W;
+#pragma unroll
+        for (int c = tx; c < LH; c += LT) {
+          const int gx = x0 + c - LR;
+          float m0 = 0.f, m1 = 0.f, m2 = 0.f;
+          if (row_ok && gx >= 0 && gx < a.W) {
+            m0 = a.maps[ro + gx];
+            m1 = a.maps[plane_sz + ro + gx];
+            m2 = a.maps[2 * plane_sz + ro + gx];
+          }
+          sM[0][r][c] = m0;
+          sM[1][r][c] = m1;
+          sM[2][r][c] = m2;
+        }
+      }
     }
     __syncthreads();
-    for (int r = ty; r < LH; r += LTHREADS / LT) {
-      float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+    if (tid < LTASKS) {
+      const int r = tid >> 2, c0 = (tid & 3) * LXB;
 #pragma unroll
-      for (int k = 0; k < LW; ++k) {
-        const float w = c_win[k];
-        h0 = fmaf(w, sM[0][r][tx + k], h0);
-        h1 = fmaf(w, sM[1][r][tx + k], h1);
-        h2 = fmaf(w, sM[2][r][tx + k], h2);
+      for (int m = 0; m < 3; ++m) {
+        float h[LXB];
+#pragma unroll
+        for (int i = 0; i < LXB; ++i) h[i] = 0.f;
+#pragma unroll
+        for (int k = 0; k < LXB + LW - 1; ++k) {
+          const float x = sM[m][r][c0 + k];
+#pragma unroll
+          for (int i = 0; i < LXB; ++i) {
+            const int t = k - i;
+            if (t >= 0 && t < LW) h[i] = fmaf(c_win[t], x, h[i]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < LXB; ++i) sHz[m][r][c0 + i] = h[i];
       }
-      sHz[0][r][tx] = h0;
-      sHz[1][r][tx] = h1;
-      sHz[2][r][tx] = h2;
     }
     __syncthreads();
 #pragma unroll
@@ -323,6 +423,9 @@ static LossArgs loss_args(int32_t V, int32_t W, int32_t H, const float* pred, co
   a.partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + align_up(3 * px * 4, 256));
   a.grad = grad;
   a.W = W; a.H = H; a.V = V;
+  // plane_sz * 4 and the maps base are multiples of 16 when W % 4 == 0 (workspace is 16-byte aligned by contract)
+  a.vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(workspace)) % 16 == 0) &&
+          (reinterpret_cast<uintptr_t>(target) % 16 == 0);
   a.w_l1 = l1; a.w_l2 = l2; a.w_ss = ss;
   return a;
 }

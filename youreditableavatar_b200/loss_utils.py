@@ -14,7 +14,7 @@ import torch
 from . import _lib
 from ._lib import check
 
-__all__ = ["l1_loss", "l2_loss", "ssim", "image_loss"]
+__all__ = ["l1_loss", "l2_loss", "ssim", "image_loss", "image_loss_and_grad"]
 
 
 def _as_batch(t: torch.Tensor, what: str) -> torch.Tensor:
@@ -83,6 +83,37 @@ def image_loss(pred: torch.Tensor, target: torch.Tensor, l1_weight: float = 0.8,
             raise RuntimeError("view_weights must hold one weight per view")
     total, per_view = _ImageLoss.apply(pred, target, w, float(l1_weight), float(l2_weight), float(dssim_weight))
     return (total, per_view) if return_per_view else total
+
+
+def image_loss_and_grad(pred: torch.Tensor, target: torch.Tensor, l1_weight: float = 0.8, l2_weight: float = 0.0,
+                        dssim_weight: float = 0.2, view_weights: Optional[torch.Tensor] = None,
+                        workspace: Optional[torch.Tensor] = None):
+    """Training-step form without autograd bookkeeping: one C-ABI call (`tgr_image_loss`: loss launch + gradient
+    launch) returning (losses[1 + V] = {total, per view}, d total / d pred [V,3,H,W]) — the upstream gradient the
+    rasterizer's backward consumes (`render_views_fwd_bwd(upstream=...)`).  `workspace` (uint8, >=
+    tgr_image_loss_bytes) can be passed to reuse one buffer across steps; view_weights is a CUDA fp32 tensor."""
+    pred, target = _as_batch(pred, "pred"), _as_batch(target, "target")
+    if not pred.is_cuda:
+        raise RuntimeError("image_loss: tensors must be CUDA tensors (there is no CPU path)")
+    if target.device != pred.device or target.shape != pred.shape:
+        raise RuntimeError("image_loss: prediction and target must have the same shape and device")
+    V, _, H, W = pred.shape
+    pred = pred.detach().contiguous().float()
+    u8 = target.dtype == torch.uint8
+    target = target.contiguous() if u8 else target.contiguous().float()
+    L = _lib.lib()
+    with torch.cuda.device(pred.device):
+        nbytes = L.tgr_image_loss_bytes(V, W, H)
+        if workspace is None or workspace.numel() < nbytes:
+            workspace = torch.empty(nbytes, dtype=torch.uint8, device=pred.device)
+        out = torch.empty(1 + V, dtype=torch.float32, device=pred.device)
+        grad = torch.empty_like(pred)
+        check(L.tgr_image_loss(V, W, H, pred.data_ptr(), target.data_ptr(), 1 if u8 else 0,
+                               0 if view_weights is None else view_weights.data_ptr(), float(l1_weight),
+                               float(l2_weight), float(dssim_weight), out.data_ptr(), grad.data_ptr(),
+                               workspace.data_ptr(), workspace.numel(),
+                               torch.cuda.current_stream(pred.device).cuda_stream), "tgr_image_loss")
+    return out, grad
 
 
 def l1_loss(network_output: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
