@@ -6,6 +6,7 @@ CPU, fp32) for the steps either side of the rasterizer:
   train_adam.npz     torch.optim.Adam(l, lr=0.0, eps=1e-15) driven exactly as TetGSOptimizer does
                      (Edit_core/tetgs_scene/tetgs_optimizer.py:66-117), position lr from the reference's
                      get_expon_lr_func (utils/general_utils.py:25-58); three steps
+  train_binding.npz  utils/graphics_utils.py triangle_area / calculate_distances (the binding rule's two primitives)
   train_cameras.npz  the camera preamble of tetgs_model.py:479-503 executed line by line with the reference's
                      getWorld2View / getProjectionMatrix (utils/graphics_utils.py)
 
@@ -162,8 +163,25 @@ def make_cameras():
     print("train_cameras.npz", V, "views")
 
 
+def make_binding():
+    """utils/graphics_utils.py triangle_area / calculate_distances on a random triangle soup."""
+    import contextlib
+    import io
+    gr = _ref_module("graphics_utils")
+    g = torch.Generator().manual_seed(31)
+    A, B, C = (torch.randn(200, 3, generator=g) for _ in range(3))
+    B[:20] = A[:20] + 1e-4 * torch.randn(20, 3, generator=g)            # slivers
+    pts = (A + B + C) / 3 + 0.01 * torch.randn(200, 3, generator=g)
+    with contextlib.redirect_stdout(io.StringIO()):                      # calculate_distances prints a shape
+        dist = gr.calculate_distances(pts, A, B, C)
+    np.savez_compressed(os.path.join(OUT, "train_binding.npz"), A=A.numpy(), B=B.numpy(), C=C.numpy(), points=pts.numpy(),
+                        area=gr.triangle_area(A, B, C).numpy(), distances=dist.numpy())
+    print("train_binding.npz")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     make_loss()
     make_adam()
     make_cameras()
+    make_binding()
