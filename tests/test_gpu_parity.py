@@ -449,3 +449,54 @@ def test_pair_record_backward_and_replay_fallback_agree(extras):
         gr = ref.backward(inp, cam, 3, fr, dL)
         for name, a, b in zip(["m2D", "col", "op", "m3D", "cov", "sh", "sc", "rot"], results[8], gr):
             assert rel_l2(a, b) <= GRAD_TOL, (name, rel_l2(a, b))
+
+
+@pytest.mark.gpu
+def test_multiview_capacity_hints_sync_free_path_and_overflow_fallback():
+    """Second and later batches of a shape launch binning / blending from a capacity hint without waiting for the
+    instance counts: same bits as the synchronous first batch; a hint that is too small (device-side overflow
+    detection) falls back to the synchronous path with identical results."""
+    from youreditableavatar_b200 import multiview as mv
+    from youreditableavatar_b200.parallel import settings_from_cam
+    _, inp, _ = small_scene(3000, 32, 128, 0)
+    V = 3
+    cams = [to_dev(scene.orbit_camera(v, V, 128, 128, device="cpu"), "cuda") for v in range(V)]
+    sets = [settings_from_cam(c, 3) for c in cams]
+    g = torch.Generator().manual_seed(7)
+    dLc = (torch.randn(V, 3, 128, 128, generator=g) / (3 * 128 * 128)).cuda()
+    e = torch.Tensor([])
+    args = (sets, inp["means3D"], e, inp["opacities"], inp["scales"], inp["rotations"], e, inp["shs"])
+
+    mv.set_capacity_hints(True)
+    try:
+        st0, color0, radii0, depth0, alpha0 = mv.c_rasterize_views(*args, extras=True)
+        assert st0.caps == st0.counts                                  # first batch of this shape: exact sizes
+        g0 = mv.c_rasterize_views_backward(st0, dLc)
+        st1, color1, radii1, depth1, alpha1 = mv.c_rasterize_views(*args, extras=True)
+        assert st1.counts == st0.counts and min(st1.caps) > max(st1.counts)   # launched from the hint
+        assert torch.equal(color1, color0) and torch.equal(radii1, radii0)
+        assert torch.equal(depth1, depth0) and torch.equal(alpha1, alpha0)
+        g1 = mv.c_rasterize_views_backward(st1, dLc)
+        for a, b in zip(g1, g0):
+            assert rel_l2(a, b) <= 2e-6
+        # a hint far too small: the kernels flag the overflow on the device, the batch is redone synchronously
+        for k in list(mv._capacity["hints"]):
+            mv._capacity["hints"][k] = 1
+        margin = mv._capacity["margin"]
+        mv._capacity["margin"] = 0
+        try:
+            st2, color2, radii2, _, _ = mv.c_rasterize_views(*args, extras=True)
+        finally:
+            mv._capacity["margin"] = margin
+        assert st2.caps == st2.counts == st0.counts
+        assert torch.equal(color2, color0) and torch.equal(radii2, radii0)
+        g2 = mv.c_rasterize_views_backward(st2, dLc)
+        for a, b in zip(g2, g0):
+            assert rel_l2(a, b) <= 2e-6
+        # switched off: always the synchronous path
+        mv.set_capacity_hints(False)
+        st3 = mv.c_rasterize_views(*args, extras=True)[0]
+        st4 = mv.c_rasterize_views(*args, extras=True)[0]
+        assert st3.caps == st3.counts and st4.caps == st4.counts
+    finally:
+        mv.set_capacity_hints(True)

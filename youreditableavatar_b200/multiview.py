@@ -57,7 +57,8 @@ class ViewBatchState:
 
     def __init__(self):
         self.params = None      # (TgrParams * V)
-        self.counts = None      # list[int]
+        self.counts = None      # list[int]: true instance counts per view
+        self.caps = None        # list[int]: instance capacity each view's binning buffer was sized (and carved) for
         self.tensors = None     # keeps every buffer the structs point into alive
         self.V = 0
         self.extras = False
@@ -70,8 +71,24 @@ def _align(x: int, a: int = 256) -> int:
     return (x + a - 1) // a * a
 
 
+# Capacity hints: the binning buffers of a batch are sized from the instance counts, which only exist on the device
+# after the preprocess kernel.  The first batch of a given shape waits for them (one host<->device sync, where the
+# reference has one per view, rasterizer_impl.cu:281).  Every later batch of that shape sizes its buffers from the
+# previous batch's largest count plus slack and launches depth sort / binning / blending WITHOUT waiting, so the GPU
+# never idles between the per-Gaussian kernel and the sorts; the counts are read afterwards (the host blocks while the
+# GPU already renders) and, should a view have outgrown its capacity (the kernels detect that on the device and
+# render nothing), the batch is redone the synchronous way.
+_capacity = {"enabled": True, "slack": 1.2, "margin": 65536, "hints": {}}
+
+
+def set_capacity_hints(enabled: bool = True, slack: float = 1.2) -> None:
+    """Turns the sync-free steady state of `c_rasterize_views` on / off (and forgets the recorded hints)."""
+    _capacity["enabled"], _capacity["slack"] = bool(enabled), float(slack)
+    _capacity["hints"].clear()
+
+
 def c_rasterize_views(settings: Sequence, means3D, colors, opacity, scales, rotations, cov3D_precomp, sh,
-                      extras: bool = False, n_streams: int = 0, binding=None):
+                      extras: bool = False, n_streams: int = 0, binding=None, _use_hint: bool = True):
     """Forward of V views.  `settings` is a sequence of GaussianRasterizationSettings (same image size, SH degree
     and scale_modifier; cameras differ).  Returns (state, color[V,3,H,W], radii[V,P] int32[, depth[V,1,H,W],
     alpha[V,1,H,W]]).  The per-view results are bit-identical to V single-view `c_rasterize_gaussians` calls.
@@ -104,7 +121,7 @@ def c_rasterize_views(settings: Sequence, means3D, colors, opacity, scales, rota
         depth = torch.empty(V, 1, H, W, **f32) if P else torch.zeros(V, 1, H, W, **f32)
         alpha = torch.empty(V, 1, H, W, **f32) if P else torch.zeros(V, 1, H, W, **f32)
     if P == 0:
-        state.counts = [0] * V
+        state.counts = state.caps = [0] * V
         return (state, color, radii) + ((depth, alpha) if extras else ())
 
     with torch.cuda.device(device):
@@ -147,20 +164,37 @@ def c_rasterize_views(settings: Sequence, means3D, colors, opacity, scales, rota
         main = torch.cuda.current_stream(device)
         bptr = C.byref(binding) if binding is not None else None
         check(L.tgr_forward_preprocess_batch(params, V, bptr, main.cuda_stream), "tgr_forward_preprocess_batch")
-        # the one host<->device sync of the batch (the reference has one per view, rasterizer_impl.cu:281)
-        check(L.tgr_wait_num_rendered(), "tgr_wait_num_rendered")
-        counts = [int(x) for x in slots.tolist()]
+        S = max(0, min(int(n_streams), V))
+        hkey = (device.index if device.index is not None else torch.cuda.current_device(), P, W, H, V, L.tgr_get_pair_factor())
+        hint = _capacity["hints"].get(hkey) if (_capacity["enabled"] and _use_hint and S == 0) else None
+        if hint is None:
+            # the one host<->device sync of the batch (the reference has one per view, rasterizer_impl.cu:281)
+            check(L.tgr_wait_num_rendered(), "tgr_wait_num_rendered")
+            counts = [int(x) for x in slots.tolist()]
+            cap_list = counts
+        else:
+            counts = None
+            cap_list = [int(hint * _capacity["slack"]) + _capacity["margin"]] * V
 
         binnings = []
         view_events = []
         for v in range(V):
-            binning = torch.empty(L.tgr_binning_bytes(P, counts[v], W, H), **u8)
+            binning = torch.empty(L.tgr_binning_bytes(P, cap_list[v], W, H), **u8)
             binnings.append(binning)
             params[v].binning_buffer, params[v].binning_bytes = binning.data_ptr(), binning.numel()
-        S = max(0, min(int(n_streams), V))
         if S == 0:
-            caps = (C.c_uint64 * V)(*counts)
+            caps = (C.c_uint64 * V)(*cap_list)
             check(L.tgr_forward_render_batch(params, caps, V, main.cuda_stream), "tgr_forward_render_batch")
+            if counts is None:
+                # launched ahead of the counts: read them now (the GPU is already sorting / blending) and verify
+                check(L.tgr_wait_num_rendered(), "tgr_wait_num_rendered")
+                counts = [int(x) for x in slots.tolist()]
+                if max(counts) > cap_list[0]:
+                    _capacity["hints"].pop(hkey, None)   # outgrown: redo this batch with exactly sized buffers
+                    return c_rasterize_views(settings, means3D, colors, opacity, scales, rotations, cov3D_precomp, sh,
+                                             extras=extras, n_streams=n_streams, binding=binding, _use_hint=False)
+            if _capacity["enabled"]:
+                _capacity["hints"][hkey] = max(counts)
             ev = torch.cuda.Event()
             ev.record(main)
             view_events = [ev] * V
@@ -182,7 +216,7 @@ def c_rasterize_views(settings: Sequence, means3D, colors, opacity, scales, rota
                 for s in streams:
                     main.wait_stream(s)
 
-    state.params, state.counts, state.n_streams = params, counts, S
+    state.params, state.counts, state.caps, state.n_streams = params, counts, list(cap_list), S
     state.view_events = view_events
     state.tensors = (means3D, colors, opacity, scales, rotations, cov3D_precomp, sh, cams, geom, img, binnings, radii)
     return (state, color, radii) + ((depth, alpha) if extras else ())
@@ -240,7 +274,7 @@ def c_rasterize_views_backward(state: ViewBatchState, dL_dout_color, dL_dout_dep
 
         main = torch.cuda.current_stream(device)
         S = state.n_streams
-        caps = (C.c_uint64 * V)(*state.counts)
+        caps = (C.c_uint64 * V)(*state.caps)
         if S == 0:
             check(L.tgr_backward_blend_batch(params, caps, V, main.cuda_stream), "tgr_backward_blend_batch")
         else:
@@ -252,11 +286,11 @@ def c_rasterize_views_backward(state: ViewBatchState, dL_dout_color, dL_dout_dep
                 s = streams[v % S]
                 if S > 1 and v < S:
                     s.wait_event(fork)
-                check(L.tgr_backward_blend(C.byref(params[v]), state.counts[v], s.cuda_stream), "tgr_backward_blend")
+                check(L.tgr_backward_blend(C.byref(params[v]), state.caps[v], s.cuda_stream), "tgr_backward_blend")
             if S > 1:
                 for s in streams:
                     main.wait_stream(s)
-        caps = (C.c_uint64 * V)(*state.counts)
+        caps = (C.c_uint64 * V)(*state.caps)
         bptr = C.byref(state.binding) if state.binding is not None else None
         nch = max(1, min(int(chunks), (P + 255) // 256))
         per = ((P + nch - 1) // nch + 255) // 256 * 256          # range starts must be multiples of 256
