@@ -410,28 +410,30 @@ __global__ void __launch_bounds__(LTHREADS) loss_bwd_kernel(const LossArgs a) {
   }
 }
 
-// loss_out[1 + v] = sum of view v's partials (double, fixed order); loss_out[0] = sum_v w_v loss_v.
+// loss_out[1 + v] = sum of view v's partials (double, fixed order: one warp per view, lane-strided then a shuffle
+// tree); loss_out[0] = sum_v w_v loss_v in view order.  Deterministic; a few microseconds for 8 x 3072 partials.
 __global__ void __launch_bounds__(1024) loss_finish_kernel(const float* __restrict__ partial, int per_view, int V,
                                                            const float* __restrict__ view_w, float* __restrict__ out) {
-  __shared__ double red[32];
-  __shared__ double total;
-  if (threadIdx.x == 0) total = 0.0;
-  for (int v = 0; v < V; ++v) {
-    double s = 0.0;
-    for (int i = threadIdx.x; i < per_view; i += blockDim.x) s += (double)partial[(size_t)v * per_view + i];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int v = warp; v < V; v += nwarps) {
+    const float* __restrict__ pv = partial + (size_t)v * per_view;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;     // four independent chains hide the load latency
+    int i = lane;
+    for (; i + 96 < per_view; i += 128) {
+      s0 += (double)pv[i]; s1 += (double)pv[i + 32]; s2 += (double)pv[i + 64]; s3 += (double)pv[i + 96];
+    }
+    for (; i < per_view; i += 32) s0 += (double)pv[i];
+    double s = (s0 + s1) + (s2 + s3);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double t = 0.0;
-      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
-      out[1 + v] = (float)t;
-      total += t * (double)(view_w ? view_w[v] : 1.0f / (float)V);
-    }
+    if (lane == 0) out[1 + v] = (float)s;
   }
-  if (threadIdx.x == 0) out[0] = (float)total;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double total = 0.0;
+    for (int v = 0; v < V; ++v) total += (double)out[1 + v] * (double)(view_w ? view_w[v] : 1.0f / (float)V);
+    out[0] = (float)total;
+  }
 }
 
 static void upload_window() {
