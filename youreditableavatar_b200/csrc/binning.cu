@@ -1,9 +1,9 @@
 // binning.cu — instance emission and tile ranges.
 //
-//   emit_kernel   replaces duplicateWithKeys (rasterizer_impl.cu:70-111) *and* the InclusiveSum that
-//                 feeds it (rasterizer_impl.cu:277): Gaussians are visited in (depth, id) order, a chained
-//                 scan (decoupled look-back, one word per CTA) gives every Gaussian its output offset,
-//                 and each (Gaussian, tile) instance is written as a 32-bit tile id + 32-bit Gaussian id.
+//   emit_*        replace duplicateWithKeys (rasterizer_impl.cu:70-111) *and* the InclusiveSum that
+//                 feeds it (rasterizer_impl.cu:277): Gaussians are visited in (depth, id) order; emit_count sums
+//                 the instances of every 1024-Gaussian tile, emit_scan turns the totals into output offsets,
+//                 emit_kernel writes each (Gaussian, tile) instance as a 32-bit tile id + 32-bit Gaussian id.
 //                 The tile rectangle was stored by the preprocess kernel, so getRect is not re-evaluated.
 //   ranges_kernel replaces identifyTileRanges (rasterizer_impl.cu:116-138) on the tile-sorted ids.
 #include <algorithm>
@@ -15,6 +15,7 @@ constexpr uint32_t SC_FLAG_AGG = 1u << 30;
 constexpr uint32_t SC_FLAG_INC = 2u << 30;
 constexpr uint32_t SC_VALUE = (1u << 30) - 1;
 constexpr uint32_t COOP_THRESHOLD = 24;  // rectangles with more tiles than this are written by the whole warp
+constexpr int EMIT_STAGE = 4096;         // instances of one CTA assembled in shared memory before the flush (32 KB)
 
 __device__ __forceinline__ uint32_t ldv(const uint32_t* p) {
   uint32_t v;
@@ -25,42 +26,110 @@ __device__ __forceinline__ void stv(uint32_t* p, uint32_t v) {
   asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(EMIT_THREADS) emit_kernel(const __grid_constant__ RenderBatch rb) {
+// Per-Gaussian instance counts of one emission tile (1024 Gaussians in depth order), shared by the two passes.
+struct EmitItems {
+  uint32_t gid[EMIT_IPT];
+  ushort4 rc[EMIT_IPT];
+  uint32_t cnt[EMIT_IPT];
+  uint32_t tsum;
+};
+__device__ __forceinline__ EmitItems emit_load(const RenderView& rv, uint32_t tile, int tid) {
+  EmitItems it;
+  it.tsum = 0;
+  const uint32_t slot0 = tile * EMIT_TILE + tid * EMIT_IPT;
+#pragma unroll
+  for (int i = 0; i < EMIT_IPT; ++i) {
+    const uint32_t slot = slot0 + i;
+    if (slot < (uint32_t)rv.P) {
+      it.gid[i] = rv.order[slot];
+      it.rc[i] = rv.rect[it.gid[i]];
+      it.cnt[i] = (uint32_t)(it.rc[i].z - it.rc[i].x) * (uint32_t)(it.rc[i].w - it.rc[i].y);
+    } else {
+      it.gid[i] = 0; it.rc[i] = make_ushort4(0, 0, 0, 0); it.cnt[i] = 0;
+    }
+    it.tsum += it.cnt[i];
+  }
+  return it;
+}
+
+// Pass 1: instances per emission tile -> scan_state[tile].  (The first version of the emission was ONE kernel with
+// a chained scan — decoupled look-back, one word per CTA; ncu showed it latency-bound on that chain: 22 of 45 stall
+// cycles at the barrier behind the look-back, 0.22 ms for 8 views.  Three dependency-free launches are faster.)
+__global__ void __launch_bounds__(EMIT_THREADS) emit_count_kernel(const __grid_constant__ RenderBatch rb) {
+  const RenderView& rv = rb.v[blockIdx.y];
+  if ((uint32_t)blockIdx.x * EMIT_TILE >= (uint32_t)rv.P) return;   // the grid is sized for the largest view
+  __shared__ uint32_t s_warp[EMIT_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const EmitItems it = emit_load(rv, blockIdx.x, tid);
+  const uint32_t wsum = __reduce_add_sync(0xffffffffu, it.tsum);
+  if (lane == 0) s_warp[warp] = wsum;
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int w = 0; w < EMIT_THREADS / 32; ++w) t += s_warp[w];
+    rv.scan_state[blockIdx.x] = t;
+  }
+}
+
+// Pass 2: exclusive scan of the per-tile totals in place (one CTA per view), overflow check against the capacity.
+__global__ void __launch_bounds__(1024) emit_scan_kernel(const __grid_constant__ RenderBatch rb) {
+  const RenderView& rv = rb.v[blockIdx.x];
+  const uint32_t ntiles = ((uint32_t)rv.P + EMIT_TILE - 1) / EMIT_TILE;
+  if (ntiles == 0) return;
+  uint32_t* __restrict__ st = rv.scan_state;
+  __shared__ uint32_t s_warp[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t per = (ntiles + 1023) / 1024;           // consecutive entries per thread
+  const uint32_t first = tid * per;
+  uint32_t sum = 0;
+  for (uint32_t k = 0; k < per; ++k) sum += (first + k < ntiles) ? st[first + k] : 0u;
+  uint32_t inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = s_warp[lane], winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    s_warp[lane] = winc - w;                             // exclusive warp offsets
+    if (lane == 31 && winc > rv.cap) rv.header->overflow = 1u;
+  }
+  __syncthreads();
+  uint32_t run = s_warp[warp] + inc - sum;
+  for (uint32_t k = 0; k < per; ++k) {
+    if (first + k < ntiles) {
+      const uint32_t c = st[first + k];
+      st[first + k] = run;
+      run += c;
+    }
+  }
+}
+
+// Pass 3: the instances.  A CTA owns emission tile blockIdx.x; its output offset is scan_state[tile].
+__global__ void __launch_bounds__(EMIT_THREADS, 4) emit_kernel(const __grid_constant__ RenderBatch rb) {
   const RenderView& rv = rb.v[blockIdx.y];
   const int P = rv.P;
   if ((uint32_t)blockIdx.x * EMIT_TILE >= (uint32_t)P) return;   // the grid is sized for the largest view
-  const uint32_t* __restrict__ order = rv.order;
-  const ushort4* __restrict__ rect = rv.rect;
   const uint32_t grid_w = (rv.W + TILE - 1) / TILE;
   uint32_t* __restrict__ keys = rv.key_a;
   uint32_t* __restrict__ vals = rv.val_a;
   const uint32_t cap = rv.cap;
-  GeomHeader* __restrict__ header = rv.header;
-  uint32_t* __restrict__ scan_state = rv.scan_state;
-  __shared__ uint32_t s_tile, s_prefix;
   __shared__ uint32_t s_warp[EMIT_THREADS / 32];
+  __shared__ uint32_t s_stage_k[EMIT_STAGE], s_stage_v[EMIT_STAGE];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = atomicAdd(&header->emit_ticket, 1u);
-  __syncthreads();
-  const uint32_t tile = s_tile;
-  const uint32_t slot0 = tile * EMIT_TILE + tid * EMIT_IPT;
+  const uint32_t tile = blockIdx.x;
+  const uint32_t s_prefix = rv.scan_state[tile];
 
-  uint32_t gid[EMIT_IPT];
-  ushort4 rc[EMIT_IPT];
-  uint32_t cnt[EMIT_IPT];
-  uint32_t tsum = 0;
-#pragma unroll
-  for (int i = 0; i < EMIT_IPT; ++i) {
-    const uint32_t slot = slot0 + i;
-    if (slot < (uint32_t)P) {
-      gid[i] = order[slot];
-      rc[i] = rect[gid[i]];
-      cnt[i] = (uint32_t)(rc[i].z - rc[i].x) * (uint32_t)(rc[i].w - rc[i].y);
-    } else {
-      gid[i] = 0; rc[i] = make_ushort4(0, 0, 0, 0); cnt[i] = 0;
-    }
-    tsum += cnt[i];
-  }
+  const EmitItems it = emit_load(rv, tile, tid);
+  const uint32_t tsum = it.tsum;
   // block exclusive scan of tsum
   uint32_t inc = tsum;
 #pragma unroll
@@ -76,50 +145,25 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_kernel(const __grid_constan
     if (w < warp) woff += s_warp[w];
     btotal += s_warp[w];
   }
-  // chained scan across CTAs: warp 0 looks back 32 predecessors per round trip (a one-word-per-hop walk by a
-  // single thread made the ~1000 resident CTAs a serial chain; ncu: 28 of 35 stall cycles were barrier waits)
-  if (warp == 0) {
-    uint32_t excl = 0;
-    if (tile == 0) {
-      if (lane == 0) stv(&scan_state[0], SC_FLAG_INC | btotal);
-    } else {
-      if (lane == 0) stv(&scan_state[tile], SC_FLAG_AGG | btotal);
-      int t = (int)tile - 1;
-      while (true) {
-        const int idx = t - lane;
-        const uint32_t v = idx >= 0 ? ldv(&scan_state[idx]) : SC_FLAG_INC;
-        const uint32_t ready = __ballot_sync(0xffffffffu, (v & ~SC_VALUE) != 0);
-        const uint32_t incl = __ballot_sync(0xffffffffu, (v & SC_FLAG_INC) != 0);
-        // lanes 0..n-1 are contiguous ready entries; stop at the first inclusive one among them
-        const int n_ready = __ffs(~ready) - 1 < 0 ? 32 : __ffs(~ready) - 1;
-        const int first_inc = incl ? __ffs(incl) - 1 : 32;
-        const int take = min(n_ready, first_inc + 1);
-        uint32_t part = lane < take ? (v & SC_VALUE) : 0u;
-        part = __reduce_add_sync(0xffffffffu, part);
-        excl += part;
-        if (first_inc < n_ready) break;
-        t -= take;
-      }
-      if (lane == 0) stv(&scan_state[tile], SC_FLAG_INC | (excl + btotal));
-    }
-    if (lane == 0) {
-      s_prefix = excl;
-      const uint32_t ntiles = ((uint32_t)P + EMIT_TILE - 1) / EMIT_TILE;
-      if (tile == ntiles - 1 && excl + btotal > cap) header->overflow = 1u;
-    }
-  }
-  __syncthreads();
-  uint32_t off = s_prefix + woff + inc - tsum;
+  // A CTA's instances form one contiguous run [s_prefix, s_prefix + btotal) of the output.  Threads own short,
+  // unaligned pieces of it (1.9 instances per Gaussian on the avatar scenes), so writing them directly costs one
+  // partial 32-byte sector per lane and store; instead the run is assembled in shared memory and flushed with
+  // coalesced stores.  Runs longer than the staging buffer (close-up views: huge rectangles) go straight to global.
+  const bool staged = btotal <= EMIT_STAGE;
+  uint32_t* __restrict__ kdst = staged ? s_stage_k : keys;
+  uint32_t* __restrict__ vdst = staged ? s_stage_v : vals;
+  const uint32_t lim = staged ? (uint32_t)EMIT_STAGE : cap;
+  uint32_t off = (staged ? 0u : s_prefix) + woff + inc - tsum;
 
 #pragma unroll
   for (int i = 0; i < EMIT_IPT; ++i) {
-    const uint32_t c = cnt[i];
-    const uint32_t w = rc[i].z - rc[i].x;
+    const uint32_t c = it.cnt[i];
+    const uint32_t w = it.rc[i].z - it.rc[i].x;
     if (c != 0 && c <= COOP_THRESHOLD) {
       uint32_t o = off;
-      for (uint32_t y = rc[i].y; y < rc[i].w; ++y)
-        for (uint32_t x = rc[i].x; x < rc[i].z; ++x) {
-          if (o < cap) { keys[o] = y * grid_w + x; vals[o] = gid[i]; }
+      for (uint32_t y = it.rc[i].y; y < it.rc[i].w; ++y)
+        for (uint32_t x = it.rc[i].x; x < it.rc[i].z; ++x) {
+          if (o < lim) { kdst[o] = y * grid_w + x; vdst[o] = it.gid[i]; }
           ++o;
         }
     }
@@ -130,29 +174,35 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_kernel(const __grid_constan
       big &= big - 1;
       const uint32_t bc = __shfl_sync(0xffffffffu, c, src);
       const uint32_t bw = __shfl_sync(0xffffffffu, w, src);
-      const uint32_t bx = __shfl_sync(0xffffffffu, (uint32_t)rc[i].x, src);
-      const uint32_t by = __shfl_sync(0xffffffffu, (uint32_t)rc[i].y, src);
+      const uint32_t bx = __shfl_sync(0xffffffffu, (uint32_t)it.rc[i].x, src);
+      const uint32_t by = __shfl_sync(0xffffffffu, (uint32_t)it.rc[i].y, src);
       const uint32_t bo = __shfl_sync(0xffffffffu, off, src);
-      const uint32_t bg = __shfl_sync(0xffffffffu, gid[i], src);
+      const uint32_t bg = __shfl_sync(0xffffffffu, it.gid[i], src);
       for (uint32_t k = lane; k < bc; k += 32) {
         const uint32_t o = bo + k;
-        if (o < cap) { keys[o] = (by + k / bw) * grid_w + (bx + k % bw); vals[o] = bg; }
+        if (o < lim) { kdst[o] = (by + k / bw) * grid_w + (bx + k % bw); vdst[o] = bg; }
       }
     }
     off += c;
+  }
+  if (staged) {
+    __syncthreads();
+    const uint32_t base = s_prefix;
+    for (uint32_t k = tid; k < btotal; k += EMIT_THREADS) {
+      const uint32_t o = base + k;
+      if (o < cap) { keys[o] = s_stage_k[k]; vals[o] = s_stage_v[k]; }
+    }
   }
 }
 
 int launch_emit(const RenderBatch& rb, cudaStream_t s) {
   int ntiles = 0;
-  for (int v = 0; v < rb.V; ++v) {
-    const int nt = (rb.v[v].P + EMIT_TILE - 1) / EMIT_TILE;
-    if (nt > 0) cudaMemsetAsync(rb.v[v].scan_state, 0, (size_t)(nt + 1) * 4, s);
-    ntiles = std::max(ntiles, nt);
-  }
+  for (int v = 0; v < rb.V; ++v) ntiles = std::max(ntiles, (rb.v[v].P + EMIT_TILE - 1) / EMIT_TILE);
   if (ntiles == 0) return 0;
+  emit_count_kernel<<<dim3(ntiles, rb.V), EMIT_THREADS, 0, s>>>(rb);
+  emit_scan_kernel<<<rb.V, 1024, 0, s>>>(rb);
   emit_kernel<<<dim3(ntiles, rb.V), EMIT_THREADS, 0, s>>>(rb);
-  count_launch();
+  count_launch(3);
   return check_launch("emit", false, s);
 }
 

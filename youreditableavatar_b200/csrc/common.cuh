@@ -60,7 +60,7 @@ struct GeomHeader {        // 128 bytes
   uint32_t num_rendered;   // total (Gaussian,tile) instances = sum of tiles touched
   uint32_t overflow;       // set when num_rendered > capacity of the binning buffer
   uint32_t num_visible;    // Gaussians with radius > 0
-  uint32_t emit_ticket;    // dynamic block id for the emit kernel's chained scan
+  uint32_t reserved0;      // (was the ticket of the chained-scan emission; unused since the three-pass emission)
   uint32_t pad[28];
 };
 
