@@ -75,6 +75,9 @@ __global__ void __launch_bounds__(EMIT_THREADS) emit_count_kernel(const __grid_c
 // Pass 2: exclusive scan of the per-tile totals in place (one CTA per view), overflow check against the capacity.
 __global__ void __launch_bounds__(1024) emit_scan_kernel(const __grid_constant__ RenderBatch rb) {
   const RenderView& rv = rb.v[blockIdx.x];
+  // this CTA is the one per-view launch that precedes the tile sort: it also clears the view's tile ranges
+  // (ranges_kernel only writes the boundaries it finds), which saves a memset node per view
+  for (uint32_t t = threadIdx.x; t < rv.T; t += blockDim.x) rv.ranges[t] = make_uint2(0u, 0u);
   const uint32_t ntiles = ((uint32_t)rv.P + EMIT_TILE - 1) / EMIT_TILE;
   if (ntiles == 0) return;
   uint32_t* __restrict__ st = rv.scan_state;
@@ -206,7 +209,10 @@ int launch_emit(const RenderBatch& rb, cudaStream_t s) {
   return check_launch("emit", false, s);
 }
 
-// per-tile [start,end) in the tile-sorted instance list; ranges must be zero-initialised
+// per-tile [start,end) in the tile-sorted instance list; ranges are zero-initialised by emit_scan_kernel (or a
+// memset when nothing is emitted).  Four list entries per thread (one 16-byte load): a quarter of the CTAs of the
+// one-entry-per-thread version, whose cost was CTA scheduling, not memory.
+constexpr int RANGE_IPT = 4;
 __global__ void __launch_bounds__(256) ranges_kernel(const __grid_constant__ RenderBatch rb) {
   const RenderView& rv = rb.v[blockIdx.y];
   const uint32_t* __restrict__ keys = rv.sorted_keys;
@@ -215,29 +221,43 @@ __global__ void __launch_bounds__(256) ranges_kernel(const __grid_constant__ Ren
   uint2* __restrict__ ranges = rv.ranges;
   const uint32_t L = min(header->num_rendered, cap);
   if (header->overflow) return;
-  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= L) return;
-  const uint32_t cur = keys[idx];
-  if (idx == 0) {
-    ranges[cur].x = 0;
+  const uint32_t idx0 = (blockIdx.x * blockDim.x + threadIdx.x) * RANGE_IPT;
+  if (idx0 >= L) return;
+  uint32_t k[RANGE_IPT];
+  if (idx0 + RANGE_IPT <= L) {
+    const uint4 q = *reinterpret_cast<const uint4*>(keys + idx0);
+    k[0] = q.x; k[1] = q.y; k[2] = q.z; k[3] = q.w;
   } else {
-    const uint32_t prev = keys[idx - 1];
-    if (cur != prev) {
-      ranges[prev].y = idx;
-      ranges[cur].x = idx;
+#pragma unroll
+    for (int i = 0; i < RANGE_IPT; ++i) k[i] = idx0 + i < L ? keys[idx0 + i] : 0u;
+  }
+  uint32_t prev = idx0 ? keys[idx0 - 1] : 0u;
+#pragma unroll
+  for (int i = 0; i < RANGE_IPT; ++i) {
+    const uint32_t idx = idx0 + i;
+    if (idx < L) {
+      const uint32_t cur = k[i];
+      if (idx == 0) {
+        ranges[cur].x = 0;
+      } else if (cur != prev) {
+        ranges[prev].y = idx;
+        ranges[cur].x = idx;
+      }
+      if (idx == L - 1) ranges[cur].y = L;
+      prev = cur;
     }
   }
-  if (idx == L - 1) ranges[cur].y = L;
 }
 
-int launch_ranges(const RenderBatch& rb, cudaStream_t s) {
+int launch_ranges(const RenderBatch& rb, bool zero_first, cudaStream_t s) {
   uint32_t cap_max = 0;
   for (int v = 0; v < rb.V; ++v) {
-    cudaMemsetAsync(rb.v[v].ranges, 0, (size_t)rb.v[v].T * sizeof(uint2), s);
+    if (zero_first) cudaMemsetAsync(rb.v[v].ranges, 0, (size_t)rb.v[v].T * sizeof(uint2), s);
     cap_max = std::max(cap_max, rb.v[v].cap);
   }
   if (cap_max == 0) return 0;
-  ranges_kernel<<<dim3((cap_max + 255) / 256, rb.V), 256, 0, s>>>(rb);
+  const uint32_t per_cta = 256 * RANGE_IPT;
+  ranges_kernel<<<dim3((cap_max + per_cta - 1) / per_cta, rb.V), 256, 0, s>>>(rb);
   count_launch();
   return check_launch("ranges", false, s);
 }

@@ -235,7 +235,7 @@ static int render_group(const tgr_params* views, const uint64_t* caps, int32_t n
     prof_end(TGR_STAGE_TILE_SORT, s);
   }
   prof_begin(TGR_STAGE_RANGES, s);
-  if (int rc = launch_ranges(rb, s)) return rc;
+  if (int rc = launch_ranges(rb, !any, s)) return rc;   // emit_scan_kernel cleared the ranges when anything was emitted
   prof_end(TGR_STAGE_RANGES, s);
   const bool extras = p0.extras && p0.out_depth && p0.out_alpha;
   prof_begin(TGR_STAGE_BLEND_FWD, s);

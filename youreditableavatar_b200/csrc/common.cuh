@@ -21,6 +21,11 @@ constexpr int RS_IPT = 16;
 constexpr int RS_TILE = RS_THREADS * RS_IPT;  // 4096 pairs per CTA
 constexpr int RS_BINS = 256;
 constexpr int RS_MAX_PASSES = 4;
+#ifndef RS_MIN_CTAS
+#define RS_MIN_CTAS 3   // resident CTAs per SM the pass kernel is compiled for: 80 registers.  Measured with 4 (64
+                        // registers, 52 B of spills, max shared-memory carve-out): depth sort 0.412 -> 0.436 ms, tile
+                        // sort 0.316 -> 0.334 ms per 8-view batch — slower, so 3 stays
+#endif
 
 struct SortPlan {
   int npasses;
@@ -424,7 +429,7 @@ int launch_sort_pairs(uint64_t n_host, const uint32_t* n_dev, uint32_t* keys_a, 
 int launch_sort_pairs_batch(const SortBatch& sb, bool iota_vals, int begin_bit, int end_bit, cudaStream_t s,
                             bool* result_in_b);
 int launch_emit(const RenderBatch& rb, cudaStream_t s);
-int launch_ranges(const RenderBatch& rb, cudaStream_t s);
+int launch_ranges(const RenderBatch& rb, bool zero_first, cudaStream_t s);
 int launch_tile_order(const RenderBatch& rb, cudaStream_t s);
 int launch_unit_build(const RenderBatch& rb, cudaStream_t s);
 uint32_t num_queues();  // number of SMs of the current device (one work queue per SM)

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) radix_hist_kernel(const __grid_constant__
 
 // ---- one digit pass ------------------------------------------------------------------------------
 template <bool IOTA>
-__global__ void __launch_bounds__(RS_THREADS, 3) radix_pass_kernel(const __grid_constant__ SortBatch sb, int pass, int flip,
+__global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) radix_pass_kernel(const __grid_constant__ SortBatch sb, int pass, int flip,
                                                                    int begin_bit, int nbits, uint32_t ntiles_max) {
   // per-segment buffers: pass `pass` reads A (flip = 0) or B (flip = 1) and writes the other
   const SortSeg& seg = sb.s[blockIdx.y];
