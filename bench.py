@@ -642,8 +642,27 @@ def train_step_reference(P, res, act, cams, targets_host, V, steps, warmup):
             "adam": {"ms": ms_adam}}
 
 
+_result_fd = None
+
+
+def emit_result(obj):
+    """The ONE JSON line of the run, written to the process's original stdout."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _result_fd is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_result_fd, line)
+
+
 def main():
+    global _result_fd
     args = parse()
+    # stdout carries exactly one JSON line: libraries write to fd 1 directly (NCCL prints its version banner there
+    # when NCCL_DEBUG is set), so fd 1 is pointed at stderr for the run and the result goes to the saved descriptor
+    sys.stdout.flush()
+    _result_fd = os.dup(1)
+    os.dup2(2, 1)
     world, rank, local = dist_setup(args)
     if args.gpus != world and rank == 0 and world > 1:
         print("warning: --gpus %d but WORLD_SIZE %d" % (args.gpus, world), file=sys.stderr)
@@ -655,7 +674,7 @@ def main():
         if not ref_cuda.available():
             if rank == 0:
                 cb = cpu_oracle_baseline(cfg)
-                print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
+                emit_result(({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
                                   "n_gpus": world, "steps": 1, "warmup": 0, "ms_per_step": 1000.0 / cb["value"],
                                   "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                                   "data": "synthetic", "config": {"workload": cfg}, "cpu_baseline": cb,
@@ -819,7 +838,7 @@ def main():
         out["cpu_baseline"] = {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
                                "sample": "not a CPU run: the reference ships no CPU rasterizer; this arm is its CUDA "
                                          "rasterizer on the same B200 (see ours-arm cpu_baseline for the CPU oracle)"}
-    print(json.dumps(out))
+    emit_result(out)
 
 
 if __name__ == "__main__":
