@@ -14,7 +14,8 @@ Prints ONE JSON line on rank 0.
   value   views/s over all ranks, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e     same metric as a training step through the public operator API with HOST buffers: every view's camera
           and uint8 target image come from pinned host memory, the image loss and its upstream gradients are
-          formed on the device from the rendered outputs, and the step's loss is read back, all inside the timed
+          formed on the device from the rendered outputs (ours: colour MSE by this library's image-loss kernels;
+          reference arm: the same loss with torch ops), and the step's loss is read back, all inside the timed
           region (Gaussian parameters are model state and stay resident, as in the reference's training loops)
   roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md.
 `--impl reference` times the UNMODIFIED reference CUDA rasterizer (oracle/_ref, built by oracle/build_ref.py)
@@ -327,6 +328,7 @@ class OursRunner:
         # "rows" / "sh": NCCL all-reduces of Gaussian ranges overlapped with the backward
         self.bucket = bucket if bucket is not None else \
             (SymmGradBucket if comm == "nvls" else GradBucket)(P, 16, "cuda", names=GradBucket.TRAINING)
+        self.loss_ws = None   # workspace of the image-loss kernels (e2e leg), allocated on first use
 
     def step(self, cams, ups, world, feeder=None):
         from youreditableavatar_b200.parallel import render_views_fwd_bwd
@@ -338,7 +340,22 @@ class OursRunner:
         def upstream(color, depth, alpha):
             if feeder is None:
                 return ups if self.extras else (ups[0], None, None)
-            dLc, dLd, dLa, box["loss"] = image_loss(color, depth, alpha, feeder.targets_dev())
+            # same loss as image_loss() below (what the reference arm evaluates with torch ops): the colour MSE against
+            # the uint8 targets and its gradient come from this library's image-loss kernels (tgr_image_loss, L2
+            # weights: two streaming launches for the whole batch), the small depth / coverage terms stay torch ops
+            from youreditableavatar_b200 import loss_utils
+            if self.loss_ws is None:
+                from youreditableavatar_b200 import _lib
+                V_, _, H_, W_ = color.shape
+                self.loss_ws = torch.empty(_lib.lib().tgr_image_loss_bytes(V_, W_, H_), dtype=torch.uint8, device=color.device)
+            out, dLc = loss_utils.image_loss_and_grad(color, feeder.targets_dev(), 0.0, 1.0, 0.0, workspace=self.loss_ws)
+            loss, dLd, dLa = out[0], None, None
+            if depth is not None:
+                cov = alpha - 1.0
+                loss = loss + 5e-4 * (depth * depth).mean() + 0.5 * (cov * cov).mean()
+                dLd = depth * (1e-3 / depth.numel())
+                dLa = cov * (1.0 / alpha.numel())
+            box["loss"] = loss
             return dLc, dLd, dLa
 
         if self.comm in ("rows", "sh"):   # NCCL all-reduces issued range by range from inside the backward
