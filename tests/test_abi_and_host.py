@@ -160,3 +160,26 @@ def test_product_never_imports_the_oracle():
         for f in os.listdir(os.path.join(ROOT, mod)):
             if f.endswith(".py"):
                 assert "oracle" not in open(os.path.join(ROOT, mod, f)).read()
+
+
+def test_bench_result_line_is_the_only_thing_on_stdout():
+    """bench.py points fd 1 at stderr for the run (NCCL's banner, extension printf, stray prints) and writes its one
+    JSON line to the saved descriptor — the driver parses stdout as a single JSON object."""
+    import json
+    import subprocess
+    import sys
+    import textwrap
+    code = textwrap.dedent('''
+        import importlib.util, os, sys
+        spec = importlib.util.spec_from_file_location("bench", %r)
+        b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)
+        sys.stdout.flush(); b._result_fd = os.dup(1); os.dup2(2, 1)
+        os.system("echo banner-written-to-fd-1")
+        print("stray python print")
+        b.emit_result({"metric": b.METRIC, "value": 1.0})
+    ''') % os.path.join(ROOT, "bench.py")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = r.stdout.splitlines()
+    assert len(lines) == 1 and json.loads(lines[0])["value"] == 1.0
+    assert "banner-written-to-fd-1" in r.stderr and "stray python print" in r.stderr
