@@ -155,3 +155,52 @@ def test_keep_inheritance_matches_numpy_restatement_and_concat_feeds_the_rasteri
     assert torch.allclose(full["scales"][:K], act["scales"][idx_o], rtol=1e-5)
     assert torch.allclose(full["opacities"][:K], act["opacities"][idx_o], atol=1e-6)
     assert float(full["opacities"][K:].min()) > 0.999
+
+
+def test_edit_pipeline_end_to_end_renders_through_the_oracle(tmp_path):
+    """init_mesh.npy -> bind -> checkpoint -> geometry edit (edit_mesh.npy with kept faces first) -> inherit the kept
+    Gaussians by tet id -> bind fresh ones on the edit sub-mesh -> the concatenation is what the rasterizer is fed:
+    rendered here with the float64 oracle (CPU).  Kept Gaussians alone reproduce the part of the original image
+    they rendered as part of the original model; the edited model covers at least as much of the image."""
+    from oracle import oracle
+    verts, faces, f2t = _mesh(10)
+    formats.save_surface_mesh(str(tmp_path / "init_mesh.npy"), verts, faces, f2t)
+    m = formats.load_surface_mesh(str(tmp_path / "init_mesh.npy"))
+    fi, _ = scene.bind_faces(m["vertices"], m["faces"])
+    gs = scene.make_gaussians(m["vertices"], m["faces"], fi.numel(), seed=2)
+    formats.save_checkpoint(str(tmp_path / "last.pt"), gs, m["face_to_global_tet_idx"])
+    gs, _ = formats.load_checkpoint(str(tmp_path / "last.pt"))
+    # the "edit": faces in the upper part of the body are regenerated (same geometry here, new tet ids), the rest kept
+    centre_z = m["vertices"][m["faces"]].mean(1)[:, 2]
+    keep_f = centre_z <= 0.2
+    kf = int(keep_f.sum())
+    order = torch.cat([torch.where(keep_f)[0], torch.where(~keep_f)[0]])
+    faces2 = m["faces"][order]
+    f2t2 = m["face_to_global_tet_idx"][order].clone()
+    f2t2[kf:] += int(f2t2.max()) + 1                        # regenerated region: tetrahedra that did not exist before
+    # edit sub-mesh gets its own vertex block, as mesh_exporter_part.py:150-158 concatenates keep + edit vertices
+    kv = m["vertices"].shape[0]
+    verts2 = torch.cat([m["vertices"], m["vertices"]])
+    faces2 = faces2.clone()
+    faces2[kf:] += kv
+    formats.save_surface_mesh(str(tmp_path / "edit_mesh.npy"), verts2, faces2, f2t2, keep_vertices_num=kv, keep_faces_num=kf)
+    em = formats.load_surface_mesh(str(tmp_path / "edit_mesh.npy"))
+    keep = formats.inherit_keep_gaussians(gs, gs["face_to_global_tet_idx"], em["face_to_global_tet_idx"])
+    n_keep = keep["keep_xyz"].shape[0]
+    kept_faces = set(torch.where(keep_f)[0].tolist())
+    assert set(keep["keep_face_indices"].long().reshape(-1).tolist()) <= kept_faces and n_keep > 0
+    ev, ef = formats.split_edit_mesh(em)
+    edit = formats.bind_edit_gaussians(ev, ef)
+    full = formats.concat_keep_edit(keep, edit)
+    cam = scene.orbit_camera(0, 4, 48, 48, device="cpu")
+    out_full = oracle.rasterize({k: v.double() for k, v in full.items()}, cam, degree=3)
+    keep_only = {k: v[:n_keep].double() for k, v in full.items()}
+    out_keep = oracle.rasterize(keep_only, cam, degree=3)
+    act = scene.activate(gs)
+    subset = {k: v[keep["keep_indices"]].double() for k, v in act.items()}
+    out_subset = oracle.rasterize(subset, cam, degree=3)    # the same Gaussians taken straight from the original model
+    assert torch.isfinite(out_full["color"]).all() and out_full["num_rendered"] > out_keep["num_rendered"] > 0
+    assert float(out_full["alpha"].sum()) >= float(out_keep["alpha"].sum()) - 1e-9
+    # inheritance + concatenation (log/exp, logit/sigmoid, normalised quaternions, fp32 storage) change nothing visible
+    assert out_keep["num_rendered"] == out_subset["num_rendered"]
+    assert float((out_keep["color"] - out_subset["color"]).abs().max()) < 1e-5
