@@ -11,20 +11,8 @@
 
 namespace tgr {
 
-constexpr uint32_t SC_FLAG_AGG = 1u << 30;
-constexpr uint32_t SC_FLAG_INC = 2u << 30;
-constexpr uint32_t SC_VALUE = (1u << 30) - 1;
 constexpr uint32_t COOP_THRESHOLD = 24;  // rectangles with more tiles than this are written by the whole warp
 constexpr int EMIT_STAGE = 4096;         // instances of one CTA assembled in shared memory before the flush (32 KB)
-
-__device__ __forceinline__ uint32_t ldv(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void stv(uint32_t* p, uint32_t v) {
-  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 
 // Per-Gaussian instance counts of one emission tile (1024 Gaussians in depth order), shared by the two passes.
 struct EmitItems {
