@@ -183,3 +183,60 @@ def test_bench_result_line_is_the_only_thing_on_stdout():
     lines = r.stdout.splitlines()
     assert len(lines) == 1 and json.loads(lines[0])["value"] == 1.0
     assert "banner-written-to-fd-1" in r.stderr and "stray python print" in r.stderr
+
+
+def test_fused_adam_host_logic_with_a_recording_library(monkeypatch):
+    """FusedAdam.step() marshals the groups into the C structs: one launch for groups that share the step count,
+    separate launches (own bias correction) for a group that skipped iterations, gradients taken from `.grad` or from
+    an external buffer, SH row rates passed as period / split.  The C library is replaced by a recorder, the CUDA
+    stream / device context by no-ops, so the marshalling runs on CPU tensors."""
+    import contextlib
+    import types
+    from youreditableavatar_b200 import _lib, optimizer
+
+    calls = []
+
+    class FakeLib:
+        def tgr_adam_step(self, groups, n, step, b1, b2, eps, grad_scale, stream):
+            calls.append({"n": n, "step": step, "b1": b1, "b2": b2, "eps": eps, "scale": grad_scale,
+                          "groups": [(groups[i].param, groups[i].grad, groups[i].exp_avg, groups[i].exp_avg_sq,
+                                      groups[i].count, groups[i].lr, groups[i].lr_alt, groups[i].period, groups[i].split)
+                                     for i in range(n)]})
+            return 0
+
+    monkeypatch.setattr(_lib, "lib", lambda: FakeLib())
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: types.SimpleNamespace(cuda_stream=0))
+
+    opt = object.__new__(optimizer.FusedAdam)            # add_param_group refuses CPU tensors: fill the fields directly
+    a, b, sh = torch.zeros(5, 3), torch.zeros(7), torch.zeros(4, 16, 3)
+    ext = torch.ones(4, 16, 3)
+    opt.defaults, opt.state, opt.grad_scale = dict(lr=0.0, betas=(0.9, 0.999), eps=1e-15), {}, 1.0
+    opt.param_groups = [
+        {"params": [a], "lr": 1e-3, "betas": (0.9, 0.999), "eps": 1e-15, "name": "points"},
+        {"params": [b], "lr": 5e-2, "betas": (0.9, 0.999), "eps": 1e-15, "name": "all_densities"},
+        {"params": [sh], "lr": 2.5e-3, "lr_alt": 2.5e-3 / 20, "period": 48, "split": 3, "grad": ext,
+         "betas": (0.9, 0.999), "eps": 1e-15, "name": "sh"}]
+    a.grad = torch.ones_like(a)                          # b has no gradient in the first iteration
+    opt.step()
+    assert len(calls) == 1 and calls[0]["n"] == 2 and calls[0]["step"] == 1 and calls[0]["eps"] == 1e-15
+    g0, g1 = calls[0]["groups"]
+    assert g0[0] == a.data_ptr() and g0[1] == a.grad.data_ptr() and g0[4] == 15 and g0[5] == 1e-3 and g0[7] == 0
+    assert g1[0] == sh.data_ptr() and g1[1] == ext.data_ptr() and g1[4] == 4 * 48
+    assert g1[5] == 2.5e-3 and abs(g1[6] - 2.5e-3 / 20) < 1e-18 and (g1[7], g1[8]) == (48, 3)
+    assert g0[2] == opt.state[0]["exp_avg"].data_ptr() and g0[3] == opt.state[0]["exp_avg_sq"].data_ptr()
+    assert 1 not in opt.state                            # skipped like torch.optim skips a parameter without .grad
+    calls.clear()
+    b.grad = torch.ones_like(b)
+    opt.step()                                           # a, sh at step 2; b at step 1 -> two launches
+    assert sorted((c["step"], c["n"]) for c in calls) == [(1, 1), (2, 2)]
+    assert [c for c in calls if c["step"] == 1][0]["groups"][0][0] == b.data_ptr()
+    sd = opt.state_dict()
+    assert float(sd["state"][0]["step"]) == 2.0 and float(sd["state"][1]["step"]) == 1.0
+    assert sd["param_groups"][2]["period"] == 48 and "grad" not in sd["param_groups"][2]
+    # a gradient of the wrong size is refused before anything is launched
+    opt.param_groups[2]["grad"] = torch.ones(3)
+    calls.clear()
+    with pytest.raises(RuntimeError, match="does not match"):
+        opt.step()
+    assert not calls and opt.state[0]["step"] == 2      # refused as a whole: no step was counted

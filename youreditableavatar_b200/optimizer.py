@@ -105,8 +105,10 @@ class FusedAdam:
 
     @torch.no_grad()
     def step(self) -> None:
-        groups = (TgrAdamGroup * _lib.ADAM_MAX_GROUPS)()
-        n, step, device = 0, None, None
+        # groups that share (step count, device) go into one launch — all of them in the reference's loops, where
+        # every parameter receives a gradient every iteration; a group that skipped iterations (no gradient then,
+        # torch.optim skips it too) has its own bias correction and therefore its own launch
+        ready = []
         for idx, g in enumerate(self.param_groups):
             p = g["params"][0]
             grad = g.get("grad")
@@ -116,29 +118,31 @@ class FusedAdam:
                 continue                       # torch.optim skips parameters without a gradient
             if grad.dtype != torch.float32 or grad.numel() != p.numel() or grad.device != p.device:
                 raise RuntimeError("FusedAdam: gradient of group %r does not match its parameter" % g.get("name", idx))
-            grad = grad if grad.is_contiguous() else grad.contiguous()
+            ready.append((idx, g, p, grad if grad.is_contiguous() else grad.contiguous()))
+        batches: Dict[tuple, list] = {}
+        for idx, g, p, grad in ready:          # nothing is counted or launched unless every group validated
             st = self._state_of(idx, p)
             st["step"] += 1
-            if step is None:
-                step, device = st["step"], p.device
-            elif st["step"] != step or p.device != device:
-                raise RuntimeError("FusedAdam: all groups must share the step count and the device (one launch)")
-            e = groups[n]
-            e.param, e.grad = p.data_ptr(), grad.data_ptr()
-            e.exp_avg, e.exp_avg_sq = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
-            e.count = p.numel()
-            e.lr = float(g["lr"])
-            e.lr_alt = float(g.get("lr_alt", g["lr"]))
-            e.period, e.split = int(g.get("period", 0)), int(g.get("split", 0))
-            g["_keepalive"] = grad
-            n += 1
-        if n == 0:
-            return
-        b1, b2 = self.param_groups[0]["betas"]
-        with torch.cuda.device(device):
-            stream = torch.cuda.current_stream(device).cuda_stream
-            check(_lib.lib().tgr_adam_step(groups, n, step, float(b1), float(b2), float(self.param_groups[0]["eps"]),
-                                           float(self.grad_scale), stream), "tgr_adam_step")
+            batches.setdefault((st["step"], p.device), []).append((g, p, grad, st))
+        b1, b2 = self.param_groups[0]["betas"] if self.param_groups else (0.9, 0.999)
+        for (step, device), entries in batches.items():
+            groups = (TgrAdamGroup * _lib.ADAM_MAX_GROUPS)()
+            keep = []
+            for n, (g, p, grad, st) in enumerate(entries):
+                e = groups[n]
+                e.param, e.grad = p.data_ptr(), grad.data_ptr()
+                e.exp_avg, e.exp_avg_sq = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
+                e.count = p.numel()
+                e.lr = float(g["lr"])
+                e.lr_alt = float(g.get("lr_alt", g["lr"]))
+                e.period, e.split = int(g.get("period", 0)), int(g.get("split", 0))
+                keep.append(grad)
+            with torch.cuda.device(device):
+                stream = torch.cuda.current_stream(device).cuda_stream
+                check(_lib.lib().tgr_adam_step(groups, len(entries), step, float(b1), float(b2),
+                                               float(self.param_groups[0]["eps"]), float(self.grad_scale), stream),
+                      "tgr_adam_step")
+            del keep                           # the launch is stream-ordered after the producers of `grad`
 
     def zero_grad(self, set_to_none: bool = True) -> None:
         for g in self.param_groups:
