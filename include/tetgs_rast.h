@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TGR_ABI_VERSION 3
+#define TGR_ABI_VERSION 4
 #define TGR_TILE 16 /* 16x16 pixel tiles, config.h:16-17 */
 #define TGR_MAX_BATCH 8 /* views served by one launch of the per-Gaussian kernels (longer batches are chunked) */
 
@@ -115,16 +115,6 @@ typedef struct tgr_binding {
 /* ---- library ---- */
 int tgr_abi_version(void);
 const char* tgr_last_error(void);     /* thread-local message of the last non-zero status */
-
-/* Contribution records: the forward appends one 32-byte record per blended (pixel, Gaussian) to the binning
- * buffer, which turns the blend backward into a flat, fully occupied loop (csrc/pair_bwd.cu).  The buffer holds
- * `records_per_instance` records per (Gaussian, tile) instance (process-wide setting; default 0 = no records, the
- * backward replays tile-list segments, csrc/blend_bwd.cu); if a view needs more than the buffer holds, its backward
- * transparently falls back to the replay.  Measured on C3 (8-view batch): records make the backward 1.7x faster
- * and the forward 1.7x slower — break-even there, hence opt-in.  Set it before sizing buffers:
- * tgr_binning_bytes depends on it. */
-int tgr_set_pair_factor(int records_per_instance);
-int tgr_get_pair_factor(void);
 
 /* ---- workspace sizes (pure functions of the arguments; rasterizer_impl.h:66-72 `required<T>`) ---- */
 uint64_t tgr_geom_bytes(int32_t P);

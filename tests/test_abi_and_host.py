@@ -240,3 +240,15 @@ def test_fused_adam_host_logic_with_a_recording_library(monkeypatch):
     with pytest.raises(RuntimeError, match="does not match"):
         opt.step()
     assert not calls and opt.state[0]["step"] == 2      # refused as a whole: no step was counted
+    opt.param_groups[2]["grad"] = ext
+    # a failing launch leaves the step counts where they were (they advance only after the launch was accepted)
+    monkeypatch.setattr(optimizer, "check", lambda rc, what="": (_ for _ in ()).throw(RuntimeError("launch failed")))
+    with pytest.raises(RuntimeError, match="launch failed"):
+        opt.step()
+    assert opt.state[0]["step"] == 2 and opt.state[1]["step"] == 1
+    monkeypatch.undo()
+    # per-group betas / eps smuggled in through load_state_dict are refused instead of silently stepped with group 0's
+    sd = opt.state_dict()
+    sd["param_groups"][1]["betas"] = (0.5, 0.999)
+    with pytest.raises(RuntimeError, match="shared by all groups"):
+        opt.load_state_dict(sd)

@@ -95,8 +95,10 @@ def test_checkpoint_round_trip_uses_the_reference_key_names(tmp_path):
     formats.save_checkpoint(p, gs, f2t, iteration=7000, train_losses=[0.5, 0.4])
     raw = torch.load(p, weights_only=False)
     sd = raw["state_dict"]
-    assert {"_points", "_scales", "_quaternions", "all_densities", "_sh_coordinates_dc", "_sh_coordinates_rest",
-            "_surface_mesh_faces", "_verts_points", "face_to_global_tet_idx", "ori_points", "normals"} <= set(sd)
+    # exactly the parameters a surface-bound reference model registers (tetgs_model.py:100-242): its loader is a
+    # strict load_state_dict (:674), so a missing or an extra key fails there
+    assert set(sd) == set(formats.REFERENCE_STATE_KEYS)
+    assert sd["surface_mesh_thickness"].shape == () and float(sd["surface_mesh_thickness"]) == pytest.approx(1e-6)
     P = fi.numel()
     assert sd["_points"].shape == (P, 1) and sd["all_densities"].shape == (P, 1) and sd["_sh_coordinates_dc"].shape == (P, 1, 3)
     assert sd["_sh_coordinates_rest"].shape == (P, 15, 3) and raw["iteration"] == 7000
@@ -109,6 +111,12 @@ def test_checkpoint_round_trip_uses_the_reference_key_names(tmp_path):
         assert torch.equal(gs2[k], gs[k]), k
     assert torch.allclose(gs2["vert_normals"], gs["vert_normals"], atol=1e-6)
     assert torch.equal(gs2["face_to_global_tet_idx"], f2t)
+    assert gs2["surface_mesh_thickness"] == pytest.approx(1e-6)
+    # Gaussians that are not bound by the reference's rule (subsampled here) are refused when SAVING
+    sub = {k: (v[::2].contiguous() if k in ("face_index", "bary", "delta", "log_scales", "raw_quats", "opacity_logits", "shs")
+               else v) for k, v in gs.items()}
+    with pytest.raises(ValueError, match="1-or-3-per-face"):
+        formats.save_checkpoint(str(tmp_path / "bad.pt"), sub, f2t)
     # a checkpoint whose Gaussian count contradicts its mesh is refused (the reference would fail in load_state_dict)
     bad = dict(sd)
     bad["_scales"] = sd["_scales"][:-1]

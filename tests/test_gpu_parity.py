@@ -418,40 +418,6 @@ def test_multiview_module_autograd_matches_single_view_modules():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("extras", [False, True])
-def test_pair_record_backward_and_replay_fallback_agree(extras):
-    """Three ways through the blend backward must give the same gradients: contribution records (opt-in), no
-    records at all (segment replay, the default), and a record buffer that overflows on the device (replay fallback chosen by
-    the device-side flag).  Checked against the reference CUDA build when present."""
-    from youreditableavatar_b200 import _lib
-    L = _lib.lib()
-    _, inp, cam = small_scene(20000, 48, 256, 1)
-    g = torch.Generator().manual_seed(11)
-    dL = (torch.randn(3, 256, 256, generator=g) / (3 * 256 * 256)).cuda()
-    dD = (torch.randn(1, 256, 256, generator=g) / (256 * 256)).cuda() if extras else None
-    dA = (torch.randn(1, 256, 256, generator=g) / (256 * 256)).cuda() if extras else None
-    results = {}
-    old = L.tgr_get_pair_factor()
-    try:
-        for factor in (8, 0, 1):
-            assert L.tgr_set_pair_factor(factor) == 0
-            fo = ours_forward(inp, cam, 3, extras=extras)
-            results[factor] = ours_backward(inp, cam, 3, fo, dL, dD, dA)
-    finally:
-        L.tgr_set_pair_factor(old)
-    for factor in (0, 1):
-        for name, a, b in zip(["m2D", "col", "op", "m3D", "cov", "sh", "sc", "rot"], results[factor], results[8]):
-            # the record path forms "colour behind" as C_final - C_in_front - own (cancellation), the replay sums it
-            assert rel_l2(a, b) <= 1e-4, (factor, name, rel_l2(a, b))
-    if not extras:
-        ref = _ref()
-        fr = ref.forward(inp, cam, 3)
-        gr = ref.backward(inp, cam, 3, fr, dL)
-        for name, a, b in zip(["m2D", "col", "op", "m3D", "cov", "sh", "sc", "rot"], results[8], gr):
-            assert rel_l2(a, b) <= GRAD_TOL, (name, rel_l2(a, b))
-
-
-@pytest.mark.gpu
 def test_multiview_capacity_hints_sync_free_path_and_overflow_fallback():
     """Second and later batches of a shape launch binning / blending from a capacity hint without waiting for the
     instance counts: same bits as the synchronous first batch; a hint that is too small (device-side overflow

@@ -62,8 +62,6 @@ class TgrAdamGroup(C.Structure):
 SYMBOLS = {
     "tgr_abi_version": (C.c_int, []),
     "tgr_last_error": (C.c_char_p, []),
-    "tgr_set_pair_factor": (C.c_int, [C.c_int]),
-    "tgr_get_pair_factor": (C.c_int, []),
     "tgr_geom_bytes": (C.c_uint64, [C.c_int32]),
     "tgr_image_bytes": (C.c_uint64, [C.c_int32, C.c_int32]),
     "tgr_binning_bytes": (C.c_uint64, [C.c_int32, C.c_uint64, C.c_int32, C.c_int32]),
@@ -107,7 +105,7 @@ SYMBOLS = {
     "tgr_build_cameras": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
 }
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_BATCH = 8
 ADAM_MAX_GROUPS = 16
 CAMERA_FLOATS = 40

@@ -50,6 +50,9 @@ class _RasterizeBound(torch.autograd.Function):
     def forward(ctx, delta, log_scales, raw_quats, opacity_logits, shs, mesh, raster_settings, extras, verts_grad):
         P = delta.shape[0]
         dev = delta.device
+        # the reference keeps delta and the opacity logits as [P,1] (`_points`, `all_densities`, tetgs_model.py:172,202);
+        # gradients go back in whatever shape / dtype the caller's tensors have
+        ctx.in_meta = tuple((t.shape, t.dtype) for t in (delta, log_scales, raw_quats, opacity_logits, shs))
         c = lambda t: t.detach().contiguous().float()
         delta, log_scales, raw_quats, opacity_logits, shs = map(c, (delta.reshape(-1), log_scales, raw_quats,
                                                                     opacity_logits.reshape(-1), shs))
@@ -92,7 +95,9 @@ class _RasterizeBound(torch.autograd.Function):
                                                 **kw)
         ctx.extra_grads = grads
         _RasterizeBound.last_vertex_grad = grads["verts"]
-        return grads["delta"], grads["log_scales"], grads["raw_quats"], grads["opacity_logits"], out[5], None, None, None, None
+        back = (grads["delta"], grads["log_scales"], grads["raw_quats"], grads["opacity_logits"], out[5])
+        back = tuple(g.reshape(shape).to(dtype) for g, (shape, dtype) in zip(back, ctx.in_meta))
+        return back + (None, None, None, None)
 
 
 def rasterize_bound(delta, log_scales, raw_quats, opacity_logits, shs, mesh: MeshBinding, raster_settings,

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtetgs_rast.so")
 STAMP = os.path.join(HERE, ".libtetgs_rast.stamp")
-SOURCES = ["c_abi.cu", "preprocess.cu", "sort.cu", "binning.cu", "blend_fwd.cu", "blend_bwd.cu", "pair_bwd.cu",
+SOURCES = ["c_abi.cu", "preprocess.cu", "sort.cu", "binning.cu", "blend_fwd.cu", "blend_bwd.cu",
            "preprocess_bwd.cu", "knn.cu", "collective.cu", "loss.cu", "adam.cu", "cameras.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -268,7 +268,6 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const __grid_constant_
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < TO_BUCKETS; i += 1024) s_cnt[i] = 0;
   if (queue_counters != nullptr && tid < MAX_QUEUES) queue_counters[tid] = 0;
-  if (tid == 0) { rv.unit_count[1] = 0; rv.unit_count[2] = 0; }   // contribution-record cursor / overflow flag
   __syncthreads();
   auto bucket_of = [&](uint32_t t) {
     const uint2 r = ranges[t];
@@ -375,9 +374,7 @@ __global__ void __launch_bounds__(1024) unit_build_kernel(const __grid_constant_
     if (tid == 0) s_carry = carry + tot;
     __syncthreads();
   }
-  // the segment replay is the FALLBACK: a view whose contribution records are complete has no replay work
-  const bool replay = rv.use_pairs == 0u || unit_count[2] != 0u;
-  if (tid == 0) *unit_count = replay ? min(s_carry, units_cap) : 0u;
+  if (tid == 0) *unit_count = min(s_carry, units_cap);
 }
 
 int launch_unit_build(const RenderBatch& rb, cudaStream_t s) {

@@ -28,16 +28,12 @@ constexpr int BL_STAGES = 4;  // shared-memory ring depth (how far consumers may
 
 
 
-// PAIRS: also append one contribution record per blended (pixel, Gaussian) for the flat backward (pair_bwd.cu).
-// The append sits on the blending chain of the busiest warps, so that variant evaluates 2 candidates per step
-// instead of 4 to stay within 56 registers; see DESIGN.md for the measured trade-off.
-template <bool EXTRAS, bool PAIRS>
+template <bool EXTRAS>
 __global__ void __launch_bounds__(BL_THREADS, 4) blend_fwd_kernel(const __grid_constant__ RenderBatch rb, uint32_t num_queues) {
-  constexpr int FG = PAIRS ? 2 : 4;   // candidates evaluated together by a consumer lane group
+  constexpr int FG = 4;   // candidates evaluated together by a consumer lane group
   __shared__ __align__(16) float4 s_xy[BL_STAGES][BL_BATCH + 1];   // x, y, hx, hy   (+1: the PAD_ENTRY dummy)
   __shared__ __align__(16) float4 s_co[BL_STAGES][BL_BATCH + 1];   // conic xx, xy, yy, opacity
   __shared__ __align__(16) float4 s_cd[BL_STAGES][BL_BATCH + 1];   // r, g, b, depth
-  __shared__ uint32_t s_id[BL_STAGES][BL_BATCH + 1];               // Gaussian ids (for the contribution records)
   __shared__ __align__(4) uint8_t s_list[8][SUB_GROUPS * LIST_BYTES];  // per consumer warp and lane group: candidates of the current batch
   __shared__ __align__(8) uint64_t s_full[BL_STAGES], s_empty[BL_STAGES];
   __shared__ uint32_t s_stop[BL_STAGES];
@@ -78,10 +74,6 @@ __global__ void __launch_bounds__(BL_THREADS, 4) blend_fwd_kernel(const __grid_c
   float* __restrict__ ckpt_z = rv.ckpt_z;
   float4* __restrict__ final_state = rv.final_state;
   float* __restrict__ final_z = rv.final_z;
-  float4* __restrict__ pairs = rv.pairs;                 // contribution records for the fast backward (pair_bwd.cu)
-  uint2* __restrict__ pair_meta = rv.pair_meta;
-  uint32_t* __restrict__ pair_state = rv.unit_count;     // [1] blocks handed out, [2] overflow
-  const uint32_t pair_cap = PAIRS ? rv.pair_blocks_cap : 0u;
   const uint32_t tiles_x = (W + TILE - 1) / TILE;
   const uint32_t tile_id = rv.order_fwd[s_rank / (uint32_t)rb.V];
   const uint32_t tile_bx = tile_id % tiles_x, tile_by = tile_id / tiles_x;
@@ -107,11 +99,7 @@ __global__ void __launch_bounds__(BL_THREADS, 4) blend_fwd_kernel(const __grid_c
       if (lane == 0) s_stop[stage] = 1;
       return true;
     };
-    if (PAIRS)
-      producer_loop<BL_STAGES, false, true>(point_list + range.x, total, rounds, xy_ext, conic_opacity, rgb_depth, s_xy,
-                                            s_co, s_cd, s_id, s_full, s_empty, lane, stop);
-    else
-      producer_loop<BL_STAGES, false, false>(point_list + range.x, total, rounds, xy_ext, conic_opacity, rgb_depth, s_xy,
+    producer_loop<BL_STAGES, false, false>(point_list + range.x, total, rounds, xy_ext, conic_opacity, rgb_depth, s_xy,
                                              s_co, s_cd, nullptr, s_full, s_empty, lane, stop);
     return;
   }
@@ -134,11 +122,6 @@ __global__ void __launch_bounds__(BL_THREADS, 4) blend_fwd_kernel(const __grid_c
   float C[3] = {0.f, 0.f, 0.f};
   float Dz = 0.f;
 
-  // Contribution records: one 32-byte record {id, lane, T, C.rgb, Dz, G} per blended (pixel, Gaussian), written
-  // straight into the block of PAIR_BLOCK records this warp currently owns.  pair_fill = records already in it
-  // (PAIR_BLOCK = no block yet); pair_next (lane 0 only) = id of the block requested ahead of time.
-  uint32_t pair_blk = PAIR_NONE, pair_next = PAIR_NONE, pair_fill = PAIR_BLOCK;
-  const uint32_t lt_mask = (1u << lane) - 1u;
   const uint32_t ckpt_base = seg_base[tile_id];
   const int pix_in_tile = warp * 32 + lane;
   for (int b = 0; b < rounds; ++b) {
@@ -166,9 +149,7 @@ __global__ void __launch_bounds__(BL_THREADS, 4) blend_fwd_kernel(const __grid_c
       // the kernel bound by the single-warp latency of the heaviest tile, not by SM throughput.
 #pragma unroll 1
       for (int i = 0; i < longest; i += FG) {
-        uint32_t packed;
-        if (FG == 4) packed = i < ncand ? *reinterpret_cast<const uint32_t*>(cand8 + i) : PAD_WORD;
-        else packed = i < ncand ? (uint32_t)*reinterpret_cast<const uint16_t*>(cand8 + i) : (PAD_WORD & 0xffffu);
+        const uint32_t packed = i < ncand ? *reinterpret_cast<const uint32_t*>(cand8 + i) : PAD_WORD;
         int j[FG];
         bool ok[FG];
         float alpha[FG], G[FG];
@@ -192,31 +173,6 @@ __global__ void __launch_bounds__(BL_THREADS, 4) blend_fwd_kernel(const __grid_c
           const bool term = act && (test_T < 0.0001f);
           done = done || term;
           const bool blend = act && !term;
-          if (PAIRS && pair_cap != 0) {
-            // append this candidate's contributions (warp-uniform control flow; every lane writes its own sector)
-            const uint32_t bal = __ballot_sync(0xffffffffu, blend);
-            if (bal) {
-              if (pair_fill + 32u > (uint32_t)PAIR_BLOCK) {   // close the block, move to the one requested earlier
-                if (lane == 0) {
-                  if (pair_blk < pair_cap) pair_meta[pair_blk] = make_uint2(tile_id * 8u + (uint32_t)warp, pair_fill);
-                  if (pair_next == PAIR_NONE) pair_next = atomicAdd(&pair_state[1], 1u);   // very first block of this warp
-                }
-                pair_blk = __shfl_sync(0xffffffffu, pair_next, 0);
-                if (lane == 0) {
-                  if (pair_blk >= pair_cap) pair_state[2] = 1u;   // overflow: this view's backward replays segments
-                  pair_next = atomicAdd(&pair_state[1], 1u);      // request the next block now, use it much later
-                }
-                pair_fill = 0;
-              }
-              const uint32_t slot = pair_fill + __popc(bal & lt_mask);
-              pair_fill += __popc(bal);
-              if (blend && pair_blk < pair_cap) {
-                float4* rec = pairs + ((size_t)pair_blk * PAIR_BLOCK + slot) * 2;
-                rec[0] = make_float4(__uint_as_float(s_id[stage][j[k]]), __uint_as_float((uint32_t)lane), T, C[0]);
-                rec[1] = make_float4(C[1], C[2], EXTRAS ? Dz : 0.f, G[k]);
-              }
-            }
-          }
           if (blend) {
             C[0] += cd[k].x * alpha[k] * T;
             C[1] += cd[k].y * alpha[k] * T;
@@ -233,11 +189,6 @@ __global__ void __launch_bounds__(BL_THREADS, 4) blend_fwd_kernel(const __grid_c
     if (lane == 0) mbar_arrive(&s_empty[stage]);
   }
 
-  // close this warp's open block and the one it requested ahead (unused: zero records)
-  if (PAIRS && pair_cap != 0 && lane == 0) {
-    if (pair_blk < pair_cap) pair_meta[pair_blk] = make_uint2(tile_id * 8u + (uint32_t)warp, pair_fill);
-    if (pair_next < pair_cap) pair_meta[pair_next] = make_uint2(0u, 0u);
-  }
   if (inside) {
     final_T[pix_id] = T;
     n_contrib[pix_id] = last_contributor;
@@ -268,15 +219,8 @@ int launch_blend_fwd(const RenderBatch& rb, bool extras, bool debug, cudaStream_
   if (int rc = launch_tile_order(rb, s)) return rc;
   // one CTA per (view, tile); the device-side queue hands out the work
   const dim3 grid(rb.T_max * (uint32_t)rb.V, 1, 1);
-  bool pairs = false;
-  for (int v = 0; v < rb.V; ++v) pairs = pairs || rb.v[v].pair_blocks_cap != 0;
-  if (pairs) {
-    if (extras) blend_fwd_kernel<true, true><<<grid, BL_THREADS, 0, s>>>(rb, num_queues());
-    else blend_fwd_kernel<false, true><<<grid, BL_THREADS, 0, s>>>(rb, num_queues());
-  } else {
-    if (extras) blend_fwd_kernel<true, false><<<grid, BL_THREADS, 0, s>>>(rb, num_queues());
-    else blend_fwd_kernel<false, false><<<grid, BL_THREADS, 0, s>>>(rb, num_queues());
-  }
+  if (extras) blend_fwd_kernel<true><<<grid, BL_THREADS, 0, s>>>(rb, num_queues());
+  else blend_fwd_kernel<false><<<grid, BL_THREADS, 0, s>>>(rb, num_queues());
   count_launch();
   return check_launch("blend_fwd", debug, s);
 }

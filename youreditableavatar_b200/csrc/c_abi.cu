@@ -11,8 +11,6 @@ namespace tgr {
 static thread_local char g_err[512] = "";
 
 static std::atomic<uint64_t> g_launches{0};
-static std::atomic<int> g_pair_factor{0};
-int pair_factor() { return g_pair_factor.load(std::memory_order_relaxed); }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
@@ -91,13 +89,6 @@ using namespace tgr;
 extern "C" {
 
 int tgr_abi_version(void) { return TGR_ABI_VERSION; }
-
-int tgr_set_pair_factor(int records_per_instance) {
-  if (records_per_instance < 0 || records_per_instance > 256) { set_error("pair factor %d out of range", records_per_instance); return 1; }
-  g_pair_factor.store(records_per_instance, std::memory_order_relaxed);
-  return 0;
-}
-int tgr_get_pair_factor(void) { return pair_factor(); }
 
 uint64_t tgr_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
 
@@ -185,9 +176,6 @@ static RenderView make_render_view(const tgr_params& p, uint64_t cap, bool tile_
   r.sorted_keys = tile_sorted_in_b ? b.key_b : b.key_a;
   r.point_list = tile_sorted_in_b ? b.val_b : b.val_a;
   r.grad_acc = b.grad_acc; r.ckpt = b.ckpt; r.ckpt_z = b.ckpt_z; r.units = b.units;
-  r.pairs = b.pairs; r.pair_meta = b.pair_meta;
-  r.pair_blocks_cap = (uint32_t)std::min<uint64_t>(b.pair_blocks_cap, 0x00ffffffull);
-  r.use_pairs = r.pair_blocks_cap != 0 ? 1u : 0u;
   r.ranges = im.ranges; r.tile_last = im.tile_last; r.order_fwd = im.order_fwd; r.seg_base = im.seg_base;
   r.unit_count = im.unit_count; r.final_T = im.final_T; r.n_contrib = im.n_contrib; r.final_state = im.final_state;
   r.final_z = im.final_z;
@@ -370,10 +358,6 @@ static int backward_blend_group(const tgr_params* views, const uint64_t* caps, i
     extras = extras || (views[k].extras && (views[k].dL_dout_depth || views[k].dL_dout_alpha));
   }
   prof_begin(TGR_STAGE_BLEND_BWD, s);
-  // fast path: flat loop over the forward's contribution records; a view whose record buffer overflowed (device
-  // flag) is skipped there and replayed segment by segment by the fallback kernel, whose work list is empty
-  // otherwise
-  if (int rc = launch_pair_bwd(rb, extras, p0.debug != 0, s)) return rc;   // no-op without record buffers
   if (int rc = launch_blend_bwd(rb, extras, p0.debug != 0, s)) return rc;
   prof_end(TGR_STAGE_BLEND_BWD, s);
   return 0;
@@ -497,9 +481,10 @@ int tgr_export_binning(const tgr_params* p, uint64_t R, uint64_t* keys, uint32_t
   bool in_b = false;
   const uint32_t* vals = sorted_vals(p, b, &in_b);
   const uint32_t* tk = in_b ? b.key_b : b.key_a;
-  if (R > 0 && (keys || ids))
+  if (R > 0 && (keys || ids)) {
     export_keys_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>((uint32_t)R, tk, vals, g.rgb_depth, keys, ids);
     count_launch();
+  }
   if (ranges) {
     const uint32_t T = (uint32_t)((p->W + TILE - 1) / TILE) * ((p->H + TILE - 1) / TILE);
     cudaMemcpyAsync(ranges, im.ranges, (size_t)T * 8, cudaMemcpyDeviceToDevice, s);

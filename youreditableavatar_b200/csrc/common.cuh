@@ -131,8 +131,7 @@ struct ImageView {
   float4* final_state;   // [N] (T_final, C_r, C_g, C_b) without background: end state of the forward recurrence
   float* final_z;        // [N] depth accumulator at the end of the forward (extras)
   uint32_t* seg_base;    // [T+1] first checkpoint slot of each tile (exclusive scan of ceil(len/SEG))
-  uint32_t* unit_count;  // [32] [0] number of backward work units of this view, [1] pair blocks handed out by the forward,
-                         //      [2] set when the pair buffer overflowed (the backward must replay segments)
+  uint32_t* unit_count;  // [32] [0] number of backward work units of this view
   uint64_t bytes;
 };
 
@@ -168,28 +167,8 @@ struct BinView {
   float* ckpt_z;     // [units_cap*256] same for the depth accumulator (extras)
   uint2* units;      // [units_cap] backward work units (tile, segment)
   uint64_t units_cap;
-  float4* pairs;     // [pair_blocks_cap * PAIR_BLOCK * 2] contribution records written by the forward (blend_fwd.cu, pair_bwd.cu)
-  uint2* pair_meta;  // [pair_blocks_cap] {tile * 8 + warp, records used} of each block
-  uint64_t pair_blocks_cap;
   uint64_t bytes;
 };
-
-// Contribution records ("pairs"): the forward appends one 32-byte record per (pixel, Gaussian) that is actually
-// blended; the fast backward (pair_bwd.cu) is then a flat loop over records.  Capacity = pair_factor() records per
-// instance + one partial chunk per (tile, warp); 0 disables the records (segment-replay backward only).
-// A forward warp owns one BLOCK of PAIR_BLOCK records at a time (blocks come from a per-view atomic cursor, the next
-// one is requested ahead of time so the atomic's latency never sits on the blending chain); a block is closed when
-// fewer than 32 slots are left, its meta word holds the number of records used.
-constexpr int PAIR_BLOCK = 256;            // records per block (8 KB)
-constexpr uint32_t PAIR_NONE = 0xffffffffu;
-int pair_factor();                         // process-wide setting (tgr_set_pair_factor), default 0 = off
-__host__ inline uint64_t pair_blocks_capacity(uint64_t R, int32_t W, int32_t H) {
-  const uint64_t f = (uint64_t)pair_factor();
-  if (f == 0 || R == 0) return 0;
-  const uint64_t T = (uint64_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
-  // f records per instance at >= 7/8 block utilisation, plus an open and a prefetched block per (tile, warp)
-  return (f * R + (PAIR_BLOCK - 32) - 1) / (PAIR_BLOCK - 32) + (T < R ? T : R) * 16 + 1;
-}
 
 constexpr int GRAD_ACC = 12;  // mean2D.xy, conic.xyz, opacity, rgb, depth, 2 pad
 
@@ -254,10 +233,6 @@ struct RenderView {
   float4* ckpt;
   float* ckpt_z;
   uint2* units;
-  float4* pairs;
-  uint2* pair_meta;
-  uint32_t pair_blocks_cap;
-  uint32_t use_pairs;       // backward: 1 = this view goes through the pair records, 0 = segment replay
   // image state
   uint2* ranges;
   uint32_t* tile_last;
@@ -321,9 +296,6 @@ __host__ inline BinView carve_bin(void* base, int32_t P, uint64_t R, int32_t W, 
   b.ckpt = carve<float4>(p, b.units_cap * TILE_PIX);
   b.ckpt_z = carve<float>(p, b.units_cap * TILE_PIX);
   b.units = carve<uint2>(p, b.units_cap);
-  b.pair_blocks_cap = pair_blocks_capacity(R, W, H);
-  b.pairs = carve<float4>(p, b.pair_blocks_cap * PAIR_BLOCK * 2);
-  b.pair_meta = carve<uint2>(p, b.pair_blocks_cap);
   b.bytes = (uint64_t)(p - static_cast<char*>(base)) + 128;
   return b;
 }
@@ -435,7 +407,6 @@ int launch_unit_build(const RenderBatch& rb, cudaStream_t s);
 uint32_t num_queues();  // number of SMs of the current device (one work queue per SM)
 int launch_blend_fwd(const RenderBatch& rb, bool extras, bool debug, cudaStream_t s);
 int launch_blend_bwd(const RenderBatch& rb, bool extras, bool debug, cudaStream_t s);
-int launch_pair_bwd(const RenderBatch& rb, bool extras, bool debug, cudaStream_t s);
 int launch_preprocess_bwd(const tgr_params& p, const tgr_binding* bind, const ViewBatch& vb, cudaStream_t s);
 int launch_mark_visible(int32_t P, const float* means3D, const float* view, const float* proj, uint8_t* present,
                         cudaStream_t s);

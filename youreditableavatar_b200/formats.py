@@ -81,15 +81,42 @@ def split_edit_mesh(mesh: Dict[str, object]) -> Tuple[torch.Tensor, torch.Tensor
 
 
 # ---------------------------------------------------------------------------------------------- checkpoints
-def gaussians_to_state_dict(gs: Dict[str, torch.Tensor], face_to_global_tet_idx: Optional[torch.Tensor] = None
+# every key of a surface-bound reference model's state_dict (the nn.Parameters registered at tetgs_model.py:100-242);
+# `face_to_global_tet_idx` only exists when the model was built with it (:116-119), `_sh_coordinates_rest` when sh_levels > 1
+REFERENCE_STATE_KEYS = ("_surface_mesh_faces", "surface_mesh_thickness", "_verts_points", "face_to_global_tet_idx",
+                        "_points", "ori_points", "normals", "all_densities", "_scales", "_quaternions",
+                        "_sh_coordinates_dc", "_sh_coordinates_rest")
+
+
+def check_reference_binding(gs: Dict[str, torch.Tensor]) -> None:
+    """The reference re-derives the binding from the mesh when it loads a checkpoint (`load_init_model`,
+    tetgs_model.py:643-675: 1 Gaussian per small face, 3 per large one, in face order).  A parameter set whose binding
+    is anything else (subsampled, padded, re-ordered) cannot be expressed in that format: refuse to SAVE it rather than
+    write a file that only fails when it is loaded."""
+    fi, bary = scene.bind_faces(gs["verts"].float(), gs["faces"].long())
+    have = gs["face_index"].long().reshape(-1)
+    if fi.numel() != have.numel() or not torch.equal(fi.to(have.device).long(), have) or \
+            not torch.allclose(bary.to(gs["bary"].device), gs["bary"].float(), atol=1e-6):
+        raise ValueError("these Gaussians are not bound by the reference's 1-or-3-per-face rule (%d Gaussians, the rule "
+                         "binds %d to this mesh): the reference checkpoint format cannot hold them"
+                         % (have.numel(), fi.numel()))
+
+
+def gaussians_to_state_dict(gs: Dict[str, torch.Tensor], face_to_global_tet_idx: Optional[torch.Tensor] = None,
+                            surface_mesh_thickness: Optional[float] = None, spatial_extent: float = 1.0
                             ) -> Dict[str, torch.Tensor]:
     """Raw-parameter dict (scene.make_gaussians / binding.MeshBinding layout) -> the reference's state-dict names and
     shapes (tetgs_model.py:100-242): delta [P,1] as `_points`, log-scales, un-normalised quaternions, opacity logits
-    [P,1], SH split into dc [P,1,3] / rest [P,M-1,3], the mesh, and the derived `ori_points` / `normals`."""
+    [P,1], SH split into dc [P,1,3] / rest [P,M-1,3], the mesh, the derived `ori_points` / `normals`, and the scalar
+    `surface_mesh_thickness` (default: spatial extent / 1e6, tetgs_model.py:105-106) — `load_init_model` loads the
+    dict with a strict `load_state_dict` (:674), so every registered parameter has to be there."""
     faces = gs["faces"].long()
     fi = gs["face_index"].long()
     w = gs["bary"][..., None]
+    if surface_mesh_thickness is None:
+        surface_mesh_thickness = float(spatial_extent) / 1_000_000
     sd = {
+        "surface_mesh_thickness": torch.tensor(float(surface_mesh_thickness), device=gs["verts"].device),
         "_points": gs["delta"].reshape(-1, 1).clone(),
         "_scales": gs["log_scales"].clone(),
         "_quaternions": gs["raw_quats"].clone(),
@@ -135,14 +162,18 @@ def gaussians_from_state_dict(sd: Dict[str, torch.Tensor], device=None) -> Dict[
     }
     if "face_to_global_tet_idx" in sd:
         gs["face_to_global_tet_idx"] = t("face_to_global_tet_idx").long().reshape(-1)
+    if "surface_mesh_thickness" in sd:
+        gs["surface_mesh_thickness"] = float(sd["surface_mesh_thickness"])
     return gs
 
 
 def save_checkpoint(path: str, gs: Dict[str, torch.Tensor], face_to_global_tet_idx: Optional[torch.Tensor] = None,
-                    **extras) -> None:
+                    surface_mesh_thickness: Optional[float] = None, spatial_extent: float = 1.0, **extras) -> None:
     """tetgs_model.py:635-640 `save_model`: {'state_dict': ..., **kwargs} (the loops pass train_losses, epoch,
-    iteration, optimizer_state_dict — refine.py:345-373)."""
-    ckpt = {"state_dict": gaussians_to_state_dict(gs, face_to_global_tet_idx)}
+    iteration, optimizer_state_dict — refine.py:345-373).  Raises ValueError when `gs` is not bound by the reference's
+    rule (see `check_reference_binding`)."""
+    check_reference_binding(gs)
+    ckpt = {"state_dict": gaussians_to_state_dict(gs, face_to_global_tet_idx, surface_mesh_thickness, spatial_extent)}
     ckpt.update(extras)
     torch.save(ckpt, path)
 

@@ -165,7 +165,7 @@ def c_rasterize_views(settings: Sequence, means3D, colors, opacity, scales, rota
         bptr = C.byref(binding) if binding is not None else None
         check(L.tgr_forward_preprocess_batch(params, V, bptr, main.cuda_stream), "tgr_forward_preprocess_batch")
         S = max(0, min(int(n_streams), V))
-        hkey = (device.index if device.index is not None else torch.cuda.current_device(), P, W, H, V, L.tgr_get_pair_factor())
+        hkey = (device.index if device.index is not None else torch.cuda.current_device(), P, W, H, V)
         hint = _capacity["hints"].get(hkey) if (_capacity["enabled"] and _use_hint and S == 0) else None
         if hint is None:
             # the one host<->device sync of the batch (the reference has one per view, rasterizer_impl.cu:281)
@@ -315,17 +315,21 @@ class _RasterizeViews(torch.autograd.Function):
                 extras, n_streams):
         res = c_rasterize_views(settings, means3D, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, sh,
                                 extras=extras, n_streams=n_streams)
-        ctx.state = res[0]
+        ctx.state = res[0]      # ctypes structs, counts, workspaces (opaque byte buffers autograd has no business with)
         ctx.extras = extras
+        # the parameter tensors go through save_for_backward so that autograd's version counters catch an in-place
+        # update between forward and backward (e.g. FusedAdam.step(), which writes parameters in place)
+        ctx.save_for_backward(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)
         ctx.mark_non_differentiable(res[2])
         return tuple(res[1:])
 
     @staticmethod
     def backward(ctx, grad_color, _grad_radii, grad_depth=None, grad_alpha=None):
+        _ = ctx.saved_tensors   # raises autograd's own errors: freed graph (second backward), in-place modification
         kw = dict(dL_dout_depth=grad_depth, dL_dout_alpha=grad_alpha) if ctx.extras else {}
+        # the state is kept: with retain_graph=True the backward can run again (it re-zeroes its accumulators)
         (g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rots) = c_rasterize_views_backward(
             ctx.state, grad_color, **kw)
-        ctx.state = None
         return (g_means3D, g_means2D, g_sh, g_colors, g_opac, g_scales, g_rots, g_cov3D, None, None, None)
 
 

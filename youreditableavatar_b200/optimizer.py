@@ -96,6 +96,16 @@ class FusedAdam:
             raise RuntimeError("FusedAdam: betas and eps are shared by all groups (one launch)")
         self.param_groups.append(g)
 
+    def _check_shared_hyperparameters(self) -> None:
+        """One launch steps every group with the same betas and eps; groups that disagree (only possible through
+        `load_state_dict` or by editing `param_groups`) must not be stepped silently with group 0's values."""
+        for i, g in enumerate(self.param_groups[1:], 1):
+            g0 = self.param_groups[0]
+            if tuple(g["betas"]) != tuple(g0["betas"]) or g["eps"] != g0["eps"]:
+                raise RuntimeError("FusedAdam: group %r has betas / eps %r / %r but group %r has %r / %r — they are shared "
+                                   "by all groups (one launch)" % (g.get("name", i), tuple(g["betas"]), g["eps"],
+                                                                   g0.get("name", 0), tuple(g0["betas"]), g0["eps"]))
+
     def _state_of(self, idx: int, p: torch.Tensor) -> Dict:
         st = self.state.get(idx)
         if st is None:
@@ -119,11 +129,11 @@ class FusedAdam:
             if grad.dtype != torch.float32 or grad.numel() != p.numel() or grad.device != p.device:
                 raise RuntimeError("FusedAdam: gradient of group %r does not match its parameter" % g.get("name", idx))
             ready.append((idx, g, p, grad if grad.is_contiguous() else grad.contiguous()))
+        self._check_shared_hyperparameters()
         batches: Dict[tuple, list] = {}
         for idx, g, p, grad in ready:          # nothing is counted or launched unless every group validated
             st = self._state_of(idx, p)
-            st["step"] += 1
-            batches.setdefault((st["step"], p.device), []).append((g, p, grad, st))
+            batches.setdefault((st["step"] + 1, p.device), []).append((g, p, grad, st))
         b1, b2 = self.param_groups[0]["betas"] if self.param_groups else (0.9, 0.999)
         for (step, device), entries in batches.items():
             groups = (TgrAdamGroup * _lib.ADAM_MAX_GROUPS)()
@@ -142,6 +152,8 @@ class FusedAdam:
                 check(_lib.lib().tgr_adam_step(groups, len(entries), step, float(b1), float(b2),
                                                float(self.param_groups[0]["eps"]), float(self.grad_scale), stream),
                       "tgr_adam_step")
+            for _, _, _, st in entries:        # counted only once the launch of its batch has been accepted
+                st["step"] = step
             del keep                           # the launch is stream-ordered after the producers of `grad`
 
     def zero_grad(self, set_to_none: bool = True) -> None:
@@ -167,10 +179,14 @@ class FusedAdam:
     def load_state_dict(self, sd: Dict) -> None:
         if len(sd["param_groups"]) != len(self.param_groups):
             raise ValueError("loaded state dict has a different number of parameter groups")
-        for g, d in zip(self.param_groups, sd["param_groups"]):
-            for k, v in d.items():
-                if k != "params":
-                    g[k] = v
+        merged = [dict(g, **{k: v for k, v in d.items() if k != "params"})
+                  for g, d in zip(self.param_groups, sd["param_groups"])]
+        live, self.param_groups = self.param_groups, merged
+        try:                                   # a checkpoint with per-group betas / eps cannot be stepped by one launch:
+            self._check_shared_hyperparameters()   # refused before anything of the live optimizer is touched
+        except RuntimeError:
+            self.param_groups = live
+            raise
         self.state = {}
         for i, s in sd["state"].items():
             p = self.param_groups[int(i)]["params"][0]
