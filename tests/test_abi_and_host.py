@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), "missing export %s" % n
         assert n in _lib.SYMBOLS, "python binding missing for %s" % n
-    assert L.tgr_abi_version() == _lib.ABI_VERSION == 3
+    assert L.tgr_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_workspace_sizes_are_pure_functions():
