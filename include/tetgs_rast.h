@@ -39,7 +39,10 @@ typedef struct tgr_params {
   int32_t W, H;         /* image width / height */
   float tan_fovx, tan_fovy;
   float scale_modifier;
-  int32_t prefiltered;  /* accepted for API parity; a culled point is simply skipped */
+  int32_t prefiltered;  /* 1: the caller asserts that every Gaussian passes the near-plane test (it ran mark_visible).
+                           A Gaussian that fails it anyway is skipped and flagged: word [3] of host_num_rendered /
+                           tgr_read_header becomes 1 and the Python operator raises the reference's message — the
+                           reference prints it and __trap()s the context (auxiliary.h:154-160) */
   int32_t debug;        /* 1: synchronise + report CUDA errors after every stage (auxiliary.h:166-173) */
   int32_t extras;       /* 1: also produce depth/alpha images (new) */
   int32_t accumulate;   /* backward: 1 = add into the output gradient tensors instead of overwriting them
@@ -80,7 +83,8 @@ typedef struct tgr_params {
   float* dL_dsh;        /* [P,M,3] or NULL when M == 0 */
   float* dL_dscales;    /* [P,3] or NULL */
   float* dL_drotations; /* [P,4] or NULL */
-  /* pinned host mirror of num_rendered written asynchronously by tgr_forward_preprocess (may be NULL) */
+  /* pinned host mirror of the geom header, FOUR words {num_rendered, overflow, num_visible, prefilter_violation},
+   * written asynchronously by tgr_forward_preprocess (may be NULL) */
   uint32_t* host_num_rendered;
 } tgr_params;
 
@@ -178,7 +182,7 @@ int tgr_backward_blend_batch(const tgr_params* views, const uint64_t* num_render
 int tgr_backward_preprocess_batch(const tgr_params* views, const uint64_t* num_rendered_capacities, int32_t n_views,
                                   const tgr_binding* bind, int32_t gaussian_first, int32_t gaussian_count, void* stream);
 
-/* Synchronously reads {num_rendered, overflow, num_visible, reserved} from a geom buffer header. */
+/* Synchronously reads {num_rendered, overflow, num_visible, prefilter_violation} from a geom buffer header. */
 int tgr_read_header(const void* geom_buffer, uint32_t out[4], void* stream);
 
 /* ---- mark_visible: replaces Rasterizer::markVisible (rasterizer_impl.cu:141-153) ---- */
@@ -218,10 +222,11 @@ int tgr_profile_collect(float* sum_ms, int32_t* launches);
 
 /* ---- parity / debugging helpers (used by tests; not on the hot path) ----
  * Reconstructs the reference's sorted 64-bit keys (tile << 32 | depth bits, rasterizer_impl.cu:102-104),
- * the sorted Gaussian ids and the per-tile ranges from the opaque buffers. keys/ids have R entries,
- * ranges 2*T entries.  Any output pointer may be NULL. */
-int tgr_export_binning(const tgr_params* p, uint64_t num_rendered, uint64_t* keys, uint32_t* ids,
-                       uint32_t* ranges, void* stream);
+ * the sorted Gaussian ids and the per-tile ranges from the opaque buffers. keys/ids have num_rendered entries,
+ * ranges 2*T entries; num_rendered_capacity is what the binning buffer was sized for (>= num_rendered).
+ * Any output pointer may be NULL. */
+int tgr_export_binning(const tgr_params* p, uint64_t num_rendered_capacity, uint64_t num_rendered, uint64_t* keys,
+                       uint32_t* ids, uint32_t* ranges, void* stream);
 /* Copies per-Gaussian preprocess records out of the geom buffer: depth[P], xy[2P], conic_opacity[4P],
  * rgb[3P], tiles_touched[P].  Any output pointer may be NULL. */
 int tgr_export_geom(const tgr_params* p, float* depth, float* xy, float* conic_opacity, float* rgb,

@@ -66,7 +66,8 @@ def _params_for_export(P, W, H, geom, binning, img):
     return p
 
 
-def export_binning(P, W, H, fwd):
+def export_binning(P, W, H, fwd, cap=None):
+    """cap: instance capacity the binning buffer was sized for (defaults to R: the single-view calls size it exactly)."""
     R, color, radii, geom, binning, img = fwd[:6]
     dev = geom.device
     T = ((W + 15) // 16) * ((H + 15) // 16)
@@ -75,7 +76,8 @@ def export_binning(P, W, H, fwd):
     ranges = torch.empty(T, 2, dtype=torch.int32, device=dev)
     p = _params_for_export(P, W, H, geom, binning, img)
     st = torch.cuda.current_stream(dev).cuda_stream
-    check(_lib.lib().tgr_export_binning(C.byref(p), R, keys.data_ptr(), ids.data_ptr(), ranges.data_ptr(), st))
+    check(_lib.lib().tgr_export_binning(C.byref(p), R if cap is None else cap, R, keys.data_ptr(), ids.data_ptr(),
+                                        ranges.data_ptr(), st))
     torch.cuda.synchronize()
     return keys, ids, ranges
 

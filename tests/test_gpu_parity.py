@@ -219,13 +219,81 @@ def test_dropin_module_autograd():
     for k, v in leaves.items():
         assert v.grad is not None and torch.isfinite(v.grad).all(), k
     assert means2D.grad is not None and float(means2D.grad.abs().sum()) > 0
-    assert rasterizer.markVisible(inp["means3D"]).dtype == torch.bool
+    vis = rasterizer.markVisible(inp["means3D"])
+    assert vis.dtype == torch.bool and vis.shape == (P,)
     with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
         rasterizer(means3D=inp["means3D"], means2D=means2D, opacities=inp["opacities"], scales=inp["scales"],
                    rotations=inp["rotations"])
     with pytest.raises(RuntimeError, match="means3D must have dimensions"):
         rasterizer(means3D=inp["means3D"].reshape(-1), means2D=means2D, shs=inp["shs"], opacities=inp["opacities"],
                    scales=inp["scales"], rotations=inp["rotations"])
+
+
+def test_mark_visible_matches_reference():
+    """`_C.mark_visible` (rasterize_points.cu:198-217 -> checkFrustum, rasterizer_impl.cu:54-66): the near-plane test of
+    in_frustum, bit for bit against the reference build — shells (all visible), a cloud straddling the camera, points
+    exactly on the 0.2 plane, NaN / inf coordinates, and the empty set."""
+    ref = _ref()
+    from youreditableavatar_b200.rasterizer import c_mark_visible
+    _, inp, cam = small_scene(20000, 48, 128, 1)
+    cloud, ccam = random_cloud(50000, 200, 120, seed=9)
+    for means, c in ((inp["means3D"], cam), (cloud["means3D"] * 3.0, ccam)):
+        m = means.clone()
+        # a handful of special rows: on the plane (z_view == 0.2 up to rounding), NaN, +-inf
+        vm = c["viewmatrix"]
+        Rm, t = vm[:3, :3], vm[3, :3]                       # row-vector convention: p_view = p @ Rm + t
+        on_plane = (torch.tensor([[0.0, 0.0, 0.2], [0.3, -0.1, 0.2], [0.0, 0.0, 0.20000002]], device=m.device) - t) @ torch.linalg.inv(Rm)
+        m[:3] = on_plane
+        m[3] = float("nan")
+        m[4, 0] = float("inf")
+        m[5, 2] = float("-inf")
+        mine = c_mark_visible(m, c["viewmatrix"], c["projmatrix"])
+        theirs = ref.dgr().mark_visible(m, c["viewmatrix"], c["projmatrix"])
+        assert mine.dtype == torch.bool and torch.equal(mine, theirs), int((mine != theirs).sum())
+        assert 0 < int(mine.sum()) <= m.shape[0]
+    empty = c_mark_visible(inp["means3D"][:0], cam["viewmatrix"], cam["projmatrix"])
+    assert empty.shape == (0,) and empty.dtype == torch.bool
+    # radii > 0 implies visible: the rasterizer's own culling uses the same test
+    out = ours_forward(cloud, ccam, 3)
+    assert bool((c_mark_visible(cloud["means3D"], ccam["viewmatrix"], ccam["projmatrix"]) | (out[2] == 0)).all())
+
+
+def test_prefiltered_semantics():
+    """`prefiltered=True` is the caller's promise that every Gaussian passes the near-plane test (it filtered with
+    mark_visible).  Kept promise: identical results to prefiltered=False (the reference too: the flag only arms the
+    check).  Broken promise: the reference prints "Point is filtered although prefiltered is set..." and __trap()s
+    (auxiliary.h:154-160), which kills the CUDA context; here the same message is raised as an exception and the
+    context stays usable — single-view operator, autograd module and multi-view batch."""
+    ref = _ref()
+    from youreditableavatar_b200 import rasterizer as rz, multiview as mv
+    from youreditableavatar_b200.parallel import settings_from_cam
+    cloud, cam = random_cloud(6000, 200, 120, seed=3)
+    vis = rz.c_mark_visible(cloud["means3D"], cam["viewmatrix"], cam["projmatrix"])
+    assert 0 < int(vis.sum()) < 6000
+    kept = {k: v[vis].contiguous() for k, v in cloud.items()}
+    e = torch.Tensor([])
+
+    def fwd(inp, prefiltered):
+        return rz.c_rasterize_gaussians(cam["bg"], inp["means3D"], e, inp["opacities"], inp["scales"], inp["rotations"], 1.0,
+                                        e, cam["viewmatrix"], cam["projmatrix"], cam["tanfovx"], cam["tanfovy"],
+                                        cam["image_height"], cam["image_width"], inp["shs"], 3, cam["campos"], prefiltered, False)
+
+    a, b = fwd(kept, True), fwd(kept, False)
+    assert a[0] == b[0] and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    theirs = ref.dgr().rasterize_gaussians(cam["bg"], kept["means3D"], e, kept["opacities"], kept["scales"], kept["rotations"],
+                                           1.0, e, cam["viewmatrix"], cam["projmatrix"], float(cam["tanfovx"]),
+                                           float(cam["tanfovy"]), cam["image_height"], cam["image_width"], kept["shs"], 3,
+                                           cam["campos"], True, False)       # the reference with the promise kept
+    assert theirs[0] == a[0] and torch.equal(theirs[2], a[2]) and (theirs[1] - a[1]).abs().max().item() <= IMG_TOL
+    with pytest.raises(RuntimeError, match="Point is filtered although prefiltered is set"):
+        fwd(cloud, True)
+    c = fwd(cloud, False)                                   # the context is alive and the unfiltered call is unchanged
+    assert c[0] == a[0] and torch.equal(c[1], a[1])
+    sets = [settings_from_cam(cam, 3)._replace(prefiltered=True)] * 2
+    with pytest.raises(RuntimeError, match="Point is filtered although prefiltered is set"):
+        mv.c_rasterize_views(sets, cloud["means3D"], e, cloud["opacities"], cloud["scales"], cloud["rotations"], e, cloud["shs"])
+    res = mv.c_rasterize_views(sets, kept["means3D"], e, kept["opacities"], kept["scales"], kept["rotations"], e, kept["shs"])
+    assert torch.equal(res[1][0], a[1]) and torch.equal(res[1][1], a[1])
 
 
 @pytest.mark.parametrize("n,bits", [(1, 32), (1000, 32), (4096, 12), (4097, 8), (1 << 20, 32), (3_000_001, 13), (50000, 31)])

@@ -81,7 +81,8 @@ SYMBOLS = {
     "tgr_mark_visible": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tgr_knn_bytes": (C.c_uint64, [C.c_int32]),
     "tgr_dist2": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
-    "tgr_export_binning": (C.c_int, [C.POINTER(TgrParams), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tgr_export_binning": (C.c_int, [C.POINTER(TgrParams), C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]),
     "tgr_export_geom": (C.c_int, [C.POINTER(TgrParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tgr_export_image_state": (C.c_int, [C.POINTER(TgrParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "tgr_kernel_launches": (C.c_uint64, []),

@@ -255,7 +255,7 @@ static int preprocess_views(const tgr_params* views, int32_t n, const tgr_bindin
   const tgr_params* p0 = &views[0];
   if (p0->P == 0) {
     for (int32_t v = 0; v < n; ++v)
-      if (views[v].host_num_rendered) *views[v].host_num_rendered = 0;
+      if (views[v].host_num_rendered) for (int k = 0; k < 4; ++k) views[v].host_num_rendered[k] = 0;
     return 0;
   }
   if (int rc = check_gaussians(p0, bind)) return rc;
@@ -277,7 +277,8 @@ static int preprocess_views(const tgr_params* views, int32_t n, const tgr_bindin
   for (int32_t v = 0; v < n; ++v) {
     if (!views[v].host_num_rendered) continue;
     GeomView g = carve_geom(views[v].geom_buffer, p0->P);
-    cudaMemcpyAsync(views[v].host_num_rendered, &g.header->num_rendered, sizeof(uint32_t), cudaMemcpyDeviceToHost, s);
+    // {num_rendered, overflow (still 0 here), num_visible, prefilter_violation}
+    cudaMemcpyAsync(views[v].host_num_rendered, &g.header->num_rendered, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s);
     any = true;
   }
   if (any) cudaEventRecord(count_event(), s);
@@ -472,11 +473,13 @@ __global__ void export_keys_kernel(uint32_t R, const uint32_t* __restrict__ tile
   if (ids_out) ids_out[i] = id;
 }
 
-int tgr_export_binning(const tgr_params* p, uint64_t R, uint64_t* keys, uint32_t* ids, uint32_t* ranges, void* stream) {
-  if (int rc = validate(p, true, R)) return rc;
+int tgr_export_binning(const tgr_params* p, uint64_t cap, uint64_t R, uint64_t* keys, uint32_t* ids, uint32_t* ranges,
+                       void* stream) {
+  if (R > cap) { set_error("export_binning: num_rendered %llu exceeds the capacity %llu", (unsigned long long)R, (unsigned long long)cap); return 1; }
+  if (int rc = validate(p, true, cap)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   GeomView g = carve_geom(p->geom_buffer, p->P);
-  BinView b = carve_bin(p->binning_buffer, p->P, R, p->W, p->H);
+  BinView b = carve_bin(p->binning_buffer, p->P, cap, p->W, p->H);
   ImageView im = carve_image(p->image_buffer, p->W, p->H);
   bool in_b = false;
   const uint32_t* vals = sorted_vals(p, b, &in_b);

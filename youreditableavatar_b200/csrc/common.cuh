@@ -65,7 +65,8 @@ struct GeomHeader {        // 128 bytes
   uint32_t num_rendered;   // total (Gaussian,tile) instances = sum of tiles touched
   uint32_t overflow;       // set when num_rendered > capacity of the binning buffer
   uint32_t num_visible;    // Gaussians with radius > 0
-  uint32_t reserved0;      // (was the ticket of the chained-scan emission; unused since the three-pass emission)
+  uint32_t prefilter_violation;  // set when tgr_params.prefiltered != 0 and a Gaussian failed the near-plane test: the
+                                 // reference prints and __trap()s there (auxiliary.h:154-160); here the host raises
   uint32_t pad[28];
 };
 
@@ -186,6 +187,7 @@ struct ViewDesc {
   const float* campos;
   float tan_fovx, tan_fovy;
   int32_t W, H;
+  int32_t prefiltered, pad0;
   // forward outputs of this view
   int32_t* radii;
   GeomHeader* header;

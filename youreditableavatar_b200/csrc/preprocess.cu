@@ -222,9 +222,11 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const tgr_params p, con
       ushort4 rect_out = make_ushort4(0, 0, 0, 0);
       uint32_t key_out = 0x7fffffffu;
 
-      // near culling (auxiliary.h:139-164): keep iff view-space z > 0.2
+      // near culling (auxiliary.h:139-164): dropped iff view-space z <= 0.2 (so a NaN depth passes, as it does there)
       const float3 p_view = xform4x3(p_orig, view);
-      if (p_view.z > 0.2f) {
+      const bool culled = p_view.z <= 0.2f;
+      if (culled && vd.prefiltered) vd.header->prefilter_violation = 1u;   // auxiliary.h:154-160
+      if (!culled) {
         const float4 p_hom = xform4x4(p_orig, proj);
         const float p_w = 1.0f / (p_hom.w + 0.0000001f);
         const float3 p_proj = {p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w};
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const tgr_params p, con
 ViewDesc make_view_desc(const tgr_params& p, const GeomView& g, const float* grad_acc) {
   ViewDesc d{};
   d.viewmatrix = p.viewmatrix; d.projmatrix = p.projmatrix; d.campos = p.campos;
-  d.tan_fovx = p.tan_fovx; d.tan_fovy = p.tan_fovy; d.W = p.W; d.H = p.H;
+  d.tan_fovx = p.tan_fovx; d.tan_fovy = p.tan_fovy; d.W = p.W; d.H = p.H; d.prefiltered = p.prefiltered;
   d.radii = p.radii; d.header = g.header; d.depth_key = g.depth_key; d.rect = g.rect;
   d.xy_ext = g.xy_ext; d.conic_opacity = g.conic_opacity; d.rgb_depth = g.rgb_depth; d.clamped = g.clamped;
   d.grad_acc = grad_acc;
@@ -340,14 +342,14 @@ int launch_preprocess(const tgr_params& p, const tgr_binding* bind, const ViewBa
   return check_launch("preprocess", p.debug != 0, s);
 }
 
-// visibility mask (rasterizer_impl.cu:54-66): view-space z > 0.2
+// visibility mask (checkFrustum, rasterizer_impl.cu:54-66 -> in_frustum, auxiliary.h:139-164): !(view-space z <= 0.2)
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means, const float* __restrict__ view,
                                     uint8_t* __restrict__ present) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= P) return;
   const float3 po = {means[3 * idx], means[3 * idx + 1], means[3 * idx + 2]};
   const float3 pv = xform4x3(po, view);
-  present[idx] = pv.z > 0.2f ? 1 : 0;
+  present[idx] = (pv.z <= 0.2f) ? 0 : 1;
 }
 
 int launch_mark_visible(int32_t P, const float* means3D, const float* view, const float* /*proj*/, uint8_t* present,

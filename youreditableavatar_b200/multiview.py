@@ -40,14 +40,22 @@ _pinned_counts = {}
 
 
 def _count_slots(device: torch.device, n: int) -> torch.Tensor:
-    """Pinned int32 slots for the asynchronous instance-count read-back of a batch (double-buffered)."""
+    """Pinned 4-word slots {num_rendered, overflow, num_visible, prefilter_violation} for the asynchronous header
+    read-back of a batch (double-buffered)."""
     key = device.index if device.index is not None else torch.cuda.current_device()
     ent = _pinned_counts.get(key)
     if ent is None or ent[0].shape[1] < n:
-        ent = [torch.zeros(2, max(n, 64), dtype=torch.int32).pin_memory(), 0]
+        ent = [torch.zeros(2, max(n, 64), 4, dtype=torch.int32).pin_memory(), 0]
         _pinned_counts[key] = ent
     ent[1] ^= 1
     return ent[0][ent[1], :n]
+
+
+def _read_counts(slots: torch.Tensor) -> List[int]:
+    rows = slots.tolist()
+    for r in rows:
+        rz.check_prefilter(r)
+    return [int(r[0]) for r in rows]
 
 
 class ViewBatchState:
@@ -159,7 +167,7 @@ def c_rasterize_views(settings: Sequence, means3D, colors, opacity, scales, rota
             if extras:
                 p.out_depth = depth[v].data_ptr()
                 p.out_alpha = alpha[v].data_ptr()
-            p.host_num_rendered = slots[v:v + 1].data_ptr()
+            p.host_num_rendered = slots[v].data_ptr()
 
         main = torch.cuda.current_stream(device)
         bptr = C.byref(binding) if binding is not None else None
@@ -170,7 +178,7 @@ def c_rasterize_views(settings: Sequence, means3D, colors, opacity, scales, rota
         if hint is None:
             # the one host<->device sync of the batch (the reference has one per view, rasterizer_impl.cu:281)
             check(L.tgr_wait_num_rendered(), "tgr_wait_num_rendered")
-            counts = [int(x) for x in slots.tolist()]
+            counts = _read_counts(slots)
             cap_list = counts
         else:
             counts = None
@@ -188,7 +196,7 @@ def c_rasterize_views(settings: Sequence, means3D, colors, opacity, scales, rota
             if counts is None:
                 # launched ahead of the counts: read them now (the GPU is already sorting / blending) and verify
                 check(L.tgr_wait_num_rendered(), "tgr_wait_num_rendered")
-                counts = [int(x) for x in slots.tolist()]
+                counts = _read_counts(slots)
                 if max(counts) > cap_list[0]:
                     _capacity["hints"].pop(hkey, None)   # outgrown: redo this batch with exactly sized buffers
                     return c_rasterize_views(settings, means3D, colors, opacity, scales, rotations, cov3D_precomp, sh,

@@ -27,15 +27,26 @@ __all__ = [
 _pinned = {}
 
 
+PREFILTER_MESSAGE = "Point is filtered although prefiltered is set. This shouldn't happen!"   # auxiliary.h:158
+
+
 def _pinned_slot(device: torch.device) -> torch.Tensor:
-    """Ring of pinned int32 slots per device for the asynchronous num_rendered read-back."""
+    """Ring of pinned 4-word slots per device for the asynchronous read-back of the geom header
+    {num_rendered, overflow, num_visible, prefilter_violation}."""
     key = device.index if device.index is not None else torch.cuda.current_device()
     ent = _pinned.get(key)
     if ent is None:
-        ent = [torch.zeros(64, dtype=torch.int32).pin_memory(), 0]
+        ent = [torch.zeros(64, 4, dtype=torch.int32).pin_memory(), 0]
         _pinned[key] = ent
     ent[1] = (ent[1] + 1) % 64
-    return ent[0][ent[1]:ent[1] + 1]
+    return ent[0][ent[1]]
+
+
+def check_prefilter(header_words) -> None:
+    """The reference prints this message and __trap()s (which kills the CUDA context) when `prefiltered=True` was
+    promised but a Gaussian fails the near-plane test (auxiliary.h:154-160); here it is an exception."""
+    if int(header_words[3]) != 0:
+        raise RuntimeError(PREFILTER_MESSAGE)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -155,7 +166,8 @@ def c_rasterize_gaussians(bg, means3D, colors, opacity, scales, rotations, scale
         # the one host<->device sync of a forward (the reference has the same one, rasterizer_impl.cu:281);
         # the GPU keeps sorting Gaussians by depth while the host waits for the count
         check(L.tgr_wait_num_rendered(), "tgr_wait_num_rendered")
-        R = int(slot.item())
+        R = int(slot[0])
+        check_prefilter(slot)
         binning = torch.empty(L.tgr_binning_bytes(P, R, W, H), **u8)
         p.binning_buffer, p.binning_bytes = binning.data_ptr(), binning.numel()
         check(L.tgr_forward_render(C.byref(p), R, stream), "tgr_forward_render")
