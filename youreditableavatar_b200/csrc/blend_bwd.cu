@@ -8,14 +8,18 @@
 //     The reference walks the whole tile list in one CTA; here the ~585 non-empty tiles of an avatar view
 //     become ~3-4 k independent units that the block scheduler balances dynamically, and the never-blended
 //     tail beyond the tile's last contributor (tile_last) is not even staged;
-//   * same producer/consumer ring and warp-block footprint culling as the forward: a warp only replays the
-//     Gaussians that can reach alpha >= 1/255 inside its 8x4 pixel block, at or before its last contributor;
-//   * two candidates are evaluated together (loads / power / exp / reciprocal are independent; only the
-//     transmittance and behind-colour updates are serial);
-//   * gradients are committed per contributing pixel with 16-byte VECTOR reductions (red.global.add.v4.f32)
-//     into one packed accumulator row grad_acc[g][12] = {dmean2D.xy, dconic.xx/xy/yy, dopacity, drgb, dz, -, -}:
-//     3 instructions per (pixel, Gaussian) where the reference issues 9 scalar atomics; warp-shuffle
-//     pre-reductions were measured slower on B200 (see the comment at the reduction);
+//   * same producer warp / mbarrier ring as the forward;
+//   * PAIR-CENTRIC consumers (pipeline.cuh): a warp owns an 8x4 pixel block, but its lanes stand for (entry, pixel)
+//     candidates and then for surviving pairs, not for pixels.  The first version mapped pixels to lanes and walked
+//     the candidates in a loop: ncu showed its gradient block running with 5.8 of 32 lanes active and 1.5 G warp
+//     instructions per 8-view batch (2.17 ms).  Here the alpha evaluation runs on 32 candidates per instruction and
+//     the gradient arithmetic + reductions on 32 surviving pairs per instruction; the per-pixel recurrences
+//     (transmittance, colour behind) live in shared memory and are the only serialised part;
+//   * the backward evaluates exp / reciprocal with the hardware approximations (ex2.approx, rcp.approx): the gradient
+//     tolerance is relative L2 1e-3, the approximations are good to ~1e-7 relative.  (The forward stays IEEE: its
+//     alpha >= 1/255 and T < 1e-4 decisions define n_contrib, which is compared bit for bit.)
+//   * gradients are committed per pair with 16-byte VECTOR reductions (red.global.add.v4.f32) into one packed
+//     accumulator row grad_acc[g][12] = {dmean2D.xy, dconic.xx/xy/yy, dopacity, drgb, dz, -, -};
 //   * extras: gradients of the depth / alpha images flow through the same recurrence.
 #include <algorithm>
 #include "common.cuh"
@@ -25,17 +29,35 @@ namespace tgr {
 
 constexpr int BL_STAGES = 4;  // shared-memory ring depth (how far consumers may drift apart)
 
-constexpr int BG = 2;  // candidates evaluated together by a consumer warp
-
 __device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// per consumer warp
+struct BwdWarpState {
+  uint32_t hits[BL_BATCH];        // hit words of the current batch
+  uint2 pairs[PB_CAP];            // {entry | pixel << 7, G bits}
+  float4 tb[32];                  // per pixel: T (after the current entry), colour behind B.rgb
+  float4 dpix[32];                // per pixel: dL/dcolour rgb, dL/ddepth
+  float4 misc[32];                // per pixel: Bz (depth behind), tail, T_final, -
+  int last[32];                   // per pixel: last contributor (1-based list position)
+};
 
 template <bool EXTRAS>
-__global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const __grid_constant__ RenderBatch rb) {
+__global__ void __launch_bounds__(BL_THREADS, 4) blend_bwd_kernel(const __grid_constant__ RenderBatch rb) {
   const RenderView& rv = rb.v[blockIdx.y];   // one launch serves every view of the batch
   const uint2* __restrict__ units = rv.units;
   const uint32_t* __restrict__ unit_count = rv.unit_count;
@@ -58,10 +80,11 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const __grid_cons
   const float* __restrict__ dL_dalpha_img = rv.dL_dalpha;
   float* __restrict__ grad_acc = rv.grad_acc;
   __shared__ uint32_t s_id[BL_STAGES][BL_BATCH + 1];
-  __shared__ __align__(16) float4 s_xy[BL_STAGES][BL_BATCH + 1];   // +1: the PAD_ENTRY dummy record
+  __shared__ __align__(16) float4 s_xy[BL_STAGES][BL_BATCH + 1];
   __shared__ __align__(16) float4 s_co[BL_STAGES][BL_BATCH + 1];
   __shared__ __align__(16) float4 s_cd[BL_STAGES][BL_BATCH + 1];
-  __shared__ __align__(4) uint8_t s_list[8][SUB_GROUPS * LIST_BYTES];  // per consumer warp and lane group: candidates of the current batch
+  extern __shared__ __align__(16) unsigned char s_dyn[];                 // 8 x BwdWarpState (static + dynamic > 48 KB)
+  BwdWarpState* s_warp = reinterpret_cast<BwdWarpState*>(s_dyn);
 
   // ---- work unit = (tile, segment): list positions [seg*SEG, min((seg+1)*SEG, total)) of one tile -------
   if (blockIdx.x >= *unit_count) return;
@@ -85,10 +108,6 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const __grid_cons
       mbar_init(&s_empty[s], 8);   // one arrival per consumer warp
     }
   }
-  if (tid < BL_STAGES) {
-    init_pad_record(s_xy[tid], s_co[tid], s_cd[tid]);
-    s_id[tid][PAD_ENTRY] = 0;
-  }
   __syncthreads();
 
   if (warp == 8) {
@@ -100,56 +119,130 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const __grid_cons
   }
 
   // ========================= CONSUMERS =========================
-  int lx, ly, group;
-  lane_pixel(warp, lane, lx, ly, group);
-  const uint32_t px = tile_bx * TILE + lx;
-  const uint32_t py = tile_by * TILE + ly;
-  const bool inside = px < (uint32_t)W && py < (uint32_t)H;
-  const uint32_t pix_id = (uint32_t)W * py + px;
-  const float2 pixf = {(float)px, (float)py};
-  const int pix_in_tile = warp * 32 + lane;
-  const float bx0 = (float)(tile_bx * TILE + (warp & 1) * 8);   // origin of this warp's 8x4 pixel block
-  const float by0 = (float)(tile_by * TILE + (warp >> 1) * 4);
-
-  const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
-  const int warp_last = __reduce_max_sync(0xffffffffu, last_contributor);
-
-  // State of the forward recurrence at the END of this segment.  Behind-colour B = sum_{j >= seg_hi} c_j a_j T_j
-  // = C_final - C(before seg_hi); T = transmittance before entry seg_hi.  If nothing contributes at or after
-  // seg_hi (it is the tile's last needed segment) the end state is the final state.
-  float T_final = 0.f, T = 0.f;
-  float B[3] = {0.f, 0.f, 0.f};
-  float Bz = 0.f;
-  if (inside) {
-    const float4 fs = final_state[pix_id];
-    T_final = fs.x;
-    T = fs.x;
-    if (seg_hi < total) {
-      const size_t slot = ((size_t)seg_base[tile_id] + (size_t)(seg_hi / SEG)) * TILE_PIX + pix_in_tile;
-      const float4 ck = ckpt[slot];
-      T = ck.x;
-      B[0] = fs.y - ck.y; B[1] = fs.z - ck.z; B[2] = fs.w - ck.w;
-      if (EXTRAS) Bz = final_depth[pix_id] - ckpt_z[slot];
-    }
-  }
-
-  const size_t HW = (size_t)H * W;
-  float dpix[3] = {0.f, 0.f, 0.f};
-  float ddep = 0.f, dalp = 0.f;
-  if (inside) {
-    dpix[0] = dL_dpix[0 * HW + pix_id];
-    dpix[1] = dL_dpix[1 * HW + pix_id];
-    dpix[2] = dL_dpix[2 * HW + pix_id];
-    if (EXTRAS) {
-      if (dL_ddepth) ddep = dL_ddepth[pix_id];
-      if (dL_dalpha_img) dalp = dL_dalpha_img[pix_id];
-    }
-  }
-  // d(out)/dalpha_i through the final transmittance: colour gets +T_final*bg, the alpha image -T_final
-  float tail = bg[0] * dpix[0] + bg[1] * dpix[1] + bg[2] * dpix[2];
-  if (EXTRAS) tail -= dalp;
+  BwdWarpState& ws = s_warp[warp];
+  const int bx0 = (int)(tile_bx * TILE) + (warp & 1) * 8;   // pixel origin of this warp's 8x4 block
+  const int by0 = (int)(tile_by * TILE) + (warp >> 1) * 4;
   const float ddelx_dx = 0.5f * W;
   const float ddely_dy = 0.5f * H;
+  int warp_last;
+  {
+    // lane l owns pixel (l & 7, l >> 3) of the block for the set-up of the per-pixel state
+    const int lx = lane & 7, ly = lane >> 3;
+    const uint32_t px = (uint32_t)(bx0 + lx), py = (uint32_t)(by0 + ly);
+    const bool inside = px < (uint32_t)W && py < (uint32_t)H;
+    const uint32_t pix_id = (uint32_t)W * py + px;
+    // the forward numbers the pixels of a block by ITS lane layout (lane_pixel, pipeline.cuh)
+    const int fwd_lane = (((ly / SUB_H) * SUB_GX + lx / SUB_W) * SUB_LANES) + (ly % SUB_H) * SUB_W + (lx % SUB_W);
+    const int pix_in_tile = warp * 32 + fwd_lane;
+    const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
+    warp_last = __reduce_max_sync(0xffffffffu, last_contributor);
+
+    // State of the forward recurrence at the END of this segment.  Behind-colour B = sum_{j >= seg_hi} c_j a_j T_j
+    // = C_final - C(before seg_hi); T = transmittance before entry seg_hi.  If nothing contributes at or after
+    // seg_hi (it is the tile's last needed segment) the end state is the final state.
+    float T_final = 0.f, T = 0.f, B0 = 0.f, B1 = 0.f, B2 = 0.f, Bz = 0.f;
+    float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f, ddep = 0.f, dalp = 0.f;
+    if (inside) {
+      const float4 fs = final_state[pix_id];
+      T_final = fs.x;
+      T = fs.x;
+      if (seg_hi < total) {
+        const size_t slot = ((size_t)seg_base[tile_id] + (size_t)(seg_hi / SEG)) * TILE_PIX + pix_in_tile;
+        const float4 ck = ckpt[slot];
+        T = ck.x;
+        B0 = fs.y - ck.y; B1 = fs.z - ck.z; B2 = fs.w - ck.w;
+        if (EXTRAS) Bz = final_depth[pix_id] - ckpt_z[slot];
+      }
+      const size_t HW = (size_t)H * W;
+      dp0 = dL_dpix[0 * HW + pix_id];
+      dp1 = dL_dpix[1 * HW + pix_id];
+      dp2 = dL_dpix[2 * HW + pix_id];
+      if (EXTRAS) {
+        if (dL_ddepth) ddep = dL_ddepth[pix_id];
+        if (dL_dalpha_img) dalp = dL_dalpha_img[pix_id];
+      }
+    }
+    // d(out)/dalpha_i through the final transmittance: colour gets +T_final*bg, the alpha image -T_final
+    float tail = bg[0] * dp0 + bg[1] * dp1 + bg[2] * dp2;
+    if (EXTRAS) tail -= dalp;
+    ws.tb[lane] = make_float4(T, B0, B1, B2);
+    ws.dpix[lane] = make_float4(dp0, dp1, dp2, ddep);
+    ws.misc[lane] = make_float4(Bz, tail, T_final, 0.f);
+    ws.last[lane] = last_contributor;
+  }
+  __syncwarp();
+
+  const uint32_t lt = (1u << lane) - 1u;
+  int npairs = 0;      // pairs waiting in the ring (warp-uniform)
+  int phead = 0;       // ring position of the oldest one
+
+  // Commits the oldest min(32, npairs) pairs of the ring: ordered update of the per-pixel recurrences, then the
+  // gradient arithmetic and the reductions at full width.
+  auto commit = [&](int stage, int batch_first_pos) {
+    const int n = min(npairs, 32);
+    const bool act = lane < n;
+    uint32_t pw = 0;
+    float G = 0.f;
+    if (act) {
+      const uint2 pr = ws.pairs[(phead + lane) & (PB_CAP - 1)];
+      pw = pr.x;
+      G = __uint_as_float(pr.y);
+    }
+    const int j = (int)(pw & 127u);
+    const int pix = (int)((pw >> 7) & 31u);
+    const float4 con_o = s_co[stage][j];
+    const float4 cd = s_cd[stage][j];
+    const float alpha = min(0.99f, con_o.w * G);
+    const float rinv = rcp_approx(1.f - alpha);
+    // pairs of this round that fall on the same pixel go one after the other, in list order (= lane order)
+    const uint32_t peers = __match_any_sync(0xffffffffu, act ? pix : 32 + lane);
+    const int rank = __popc(peers & lt);
+    const int maxrank = __reduce_max_sync(0xffffffffu, act ? rank : 0);
+    float Ti = 0.f, Bb0 = 0.f, Bb1 = 0.f, Bb2 = 0.f, Bbz = 0.f, tail = 0.f, T_final = 0.f;
+    for (int r = 0; r <= maxrank; ++r) {
+      if (act && rank == r) {
+        // T holds the transmittance AFTER this entry; Ti before it.  B = (unnormalised) colour blended behind it.
+        const float4 tb = ws.tb[pix];
+        Ti = tb.x * rinv;
+        const float w = alpha * Ti;
+        Bb0 = tb.y; Bb1 = tb.z; Bb2 = tb.w;
+        ws.tb[pix] = make_float4(Ti, fmaf(cd.x, w, tb.y), fmaf(cd.y, w, tb.z), fmaf(cd.z, w, tb.w));
+        const float4 mi = ws.misc[pix];
+        Bbz = mi.x; tail = mi.y; T_final = mi.z;
+        if (EXTRAS) ws.misc[pix].x = fmaf(cd.w, w, mi.x);
+      }
+      __syncwarp();
+    }
+    if (act) {
+      const float4 dp = ws.dpix[pix];
+      const float4 g = s_xy[stage][j];
+      const float dx = g.x - (float)(bx0 + (pix & 7)), dy = g.y - (float)(by0 + (pix >> 3));
+      const float w = alpha * Ti;
+      // dC/dalpha_i = c_i*Ti - B/(1-alpha_i)   (same quantity as backward.cu:515-525's (c - accum_rec)*T)
+      float dL_dalpha = (cd.x * Ti - Bb0 * rinv) * dp.x + (cd.y * Ti - Bb1 * rinv) * dp.y + (cd.z * Ti - Bb2 * rinv) * dp.z;
+      float gz = 0.f;
+      if (EXTRAS) {
+        dL_dalpha += (cd.w * Ti - Bbz * rinv) * dp.w;
+        gz = w * dp.w;
+      }
+      dL_dalpha += (-T_final * rinv) * tail;
+      // the 0.99 cap is straight-through in the reference (backward.cu:494-497 recomputes alpha with the min)
+      const float dL_dG = con_o.w * dL_dalpha;
+      const float gdx = G * dx;
+      const float gdy = G * dy;
+      const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
+      const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
+      float* row = grad_acc + (size_t)s_id[stage][j] * GRAD_ACC;
+      red_add_v4(row + 0, dL_dG * dG_ddelx * ddelx_dx, dL_dG * dG_ddely * ddely_dy, -0.5f * gdx * dx * dL_dG,
+                 -0.5f * gdx * dy * dL_dG);
+      red_add_v4(row + 4, -0.5f * gdy * dy * dL_dG, G * dL_dalpha, w * dp.x, w * dp.y);
+      if (EXTRAS) red_add_v2(row + 8, w * dp.z, gz);
+      else atomicAdd(row + 8, w * dp.z);
+    }
+    (void)batch_first_pos;
+    phead = (phead + n) & (PB_CAP - 1);
+    npairs -= n;
+  };
 
   for (int b = 0; b < rounds; ++b) {
     const int stage = b % BL_STAGES;
@@ -158,77 +251,47 @@ __global__ void __launch_bounds__(BL_THREADS) blend_bwd_kernel(const __grid_cons
     if (batch_first_pos - (BL_BATCH - 1) < warp_last) {  // else: whole batch lies behind this block's last contributor
       // entries at list positions >= warp_last lie behind this block's last contributor: batch entry e sits at
       // position batch_first_pos - e, so only e > batch_first_pos - warp_last can matter
-      int longest;
-      const int ncand = cons_classify(max(0, batch_first_pos - warp_last + 1), min(BL_BATCH, count - b * BL_BATCH),
-                                      s_xy[stage], s_list[warp], bx0, by0, lane, longest);
-      const uint16_t* cand = reinterpret_cast<const uint16_t*>(s_list[warp] + group * LIST_BYTES);
-      // Candidates are taken BG at a time (one 16-bit load = two batch-local indices) so the loads / power /
-      // exp of one overlap the serial transmittance + behind-colour recurrences of the other.
-      {
-#pragma unroll 1
-        for (int i = 0; i < longest; i += BG) {
-          const uint32_t packed = i < ncand ? (uint32_t)cand[i >> 1] : (PAD_WORD & 0xffffu);
-          int j[BG];
-          bool valid[BG];
-          float G[BG], alpha[BG], rinv[BG];
-          float2 d[BG];
-          float4 con_o[BG], cd[BG];
+      const int nhits = classify_hits(max(0, batch_first_pos - warp_last + 1), min(BL_BATCH, count - b * BL_BATCH),
+                                      s_xy[stage], ws.hits, bx0, by0, lane);
+      for (int h0 = 0; h0 < nhits; h0 += 32) {
+        // lane i <- hit h0 + i; rectangles laid end to end: start = exclusive prefix of the pixel counts
+        const uint32_t hw = (h0 + lane < nhits) ? ws.hits[h0 + lane] : 0u;
+        const int n = (h0 + lane < nhits) ? hit_pixels(hw) : 0;
+        int incl = n;
 #pragma unroll
-          for (int k = 0; k < BG; ++k) j[k] = (int)((packed >> (8 * k)) & 0xffu);
-#pragma unroll
-          for (int k = 0; k < BG; ++k) {
-            const int pos = batch_first_pos - j[k];  // 0-based list position
-            const float4 g = s_xy[stage][j[k]];
-            con_o[k] = s_co[stage][j[k]];
-            cd[k] = s_cd[stage][j[k]];
-            d[k] = {g.x - pixf.x, g.y - pixf.y};
-            const float power =
-                -0.5f * (con_o[k].x * d[k].x * d[k].x + con_o[k].z * d[k].y * d[k].y) - con_o[k].y * d[k].x * d[k].y;
-            G[k] = expf(power);
-            alpha[k] = min(0.99f, con_o[k].w * G[k]);
-            rinv[k] = __frcp_rn(1.f - alpha[k]);
-            valid[k] = (pos < last_contributor) && (power <= 0.0f) && (alpha[k] >= 1.0f / 255.0f);
-          }
-#pragma unroll
-          for (int k = 0; k < BG; ++k) {
-            if (!__any_sync(0xffffffffu, valid[k])) continue;
-            if (valid[k]) {
-              // T holds the transmittance AFTER this entry; Ti before it.  With B the (unnormalised) colour
-              // blended behind this entry:  dC/dalpha_i = c_i*Ti - B/(1-alpha_i)
-              // (same quantity as backward.cu:515-525's (c - accum_rec)*T, written without the running average)
-              const float Ti = T * rinv[k];
-              const float w = alpha[k] * Ti;
-              float dL_dalpha = (cd[k].x * Ti - B[0] * rinv[k]) * dpix[0] + (cd[k].y * Ti - B[1] * rinv[k]) * dpix[1] +
-                                (cd[k].z * Ti - B[2] * rinv[k]) * dpix[2];
-              B[0] += cd[k].x * w; B[1] += cd[k].y * w; B[2] += cd[k].z * w;
-              float gz = 0.f;
-              if (EXTRAS) {
-                dL_dalpha += (cd[k].w * Ti - Bz * rinv[k]) * ddep;
-                gz = w * ddep;
-                Bz += cd[k].w * w;
-              }
-              T = Ti;
-              dL_dalpha += (-T_final * rinv[k]) * tail;
-
-              const float dL_dG = con_o[k].w * dL_dalpha;
-              const float gdx = G[k] * d[k].x;
-              const float gdy = G[k] * d[k].y;
-              const float dG_ddelx = -gdx * con_o[k].x - gdy * con_o[k].y;
-              const float dG_ddely = -gdy * con_o[k].z - gdx * con_o[k].y;
-              // Every contributing pixel commits its own partials to the packed accumulator row with three
-              // 16-byte vector reductions (red.global.add.v4.f32, sm_90+).  Measured on B200: faster than any
-              // warp-shuffle pre-reduction (16-shuffle butterfly: 585 us; direct: 429 us) — the L2 reduction
-              // units absorb the same-address traffic, the SM issue slots were the bottleneck.
-              float* row = grad_acc + (size_t)s_id[stage][j[k]] * GRAD_ACC;
-              red_add_v4(row + 0, dL_dG * dG_ddelx * ddelx_dx, dL_dG * dG_ddely * ddely_dy, -0.5f * gdx * d[k].x * dL_dG,
-                         -0.5f * gdx * d[k].y * dL_dG);
-              red_add_v4(row + 4, -0.5f * gdy * d[k].y * dL_dG, G[k] * dL_dalpha, w * dpix[0], w * dpix[1]);
-              if (EXTRAS) red_add_v2(row + 8, w * dpix[2], gz);
-              else atomicAdd(row + 8, w * dpix[2]);
-            }
-          }
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const int start = incl - n;
+        const int cand_total = __shfl_sync(0xffffffffu, incl, 31);
+        for (int base = 0; base < cand_total; base += 32) {
+          uint32_t w_hit;
+          int k;
+          bool ok = expand_candidate(hw, n, start, cand_total, base, lane, w_hit, k);
+          const int j = (int)(w_hit & 127u);
+          const int rw = (int)((w_hit >> 12) & 7u) + 1;
+          const int ry = (k * (int)(((w_hit >> 17) & 255u) + 1u)) >> 8;
+          const int lx = (int)((w_hit >> 7) & 7u) + (k - ry * rw);
+          const int ly = (int)((w_hit >> 10) & 3u) + ry;
+          const int pix = ly * 8 + lx;
+          const int pos = batch_first_pos - j;   // 0-based list position of the entry
+          ok = ok && pos < ws.last[pix & 31];
+          const float4 g = s_xy[stage][j];
+          const float4 con_o = s_co[stage][j];
+          const float dx = g.x - (float)(bx0 + lx), dy = g.y - (float)(by0 + ly);
+          const float power = -0.5f * (con_o.x * dx * dx + con_o.z * dy * dy) - con_o.y * dx * dy;
+          const float G = ex2_approx(power * 1.4426950408889634f);
+          const float alpha = min(0.99f, con_o.w * G);
+          ok = ok && (power <= 0.0f) && (alpha >= 1.0f / 255.0f);
+          const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+          if (ok) ws.pairs[(phead + npairs + __popc(bal & lt)) & (PB_CAP - 1)] = make_uint2((uint32_t)j | ((uint32_t)pix << 7), __float_as_uint(G));
+          npairs += __popc(bal);
+          __syncwarp();
+          if (npairs >= 32) commit(stage, batch_first_pos);
         }
       }
+      while (npairs > 0) commit(stage, batch_first_pos);   // the stage is released below: nothing may refer to it any more
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&s_empty[stage]);
@@ -242,8 +305,15 @@ int launch_blend_bwd(const RenderBatch& rb, bool extras, bool debug, cudaStream_
   for (int v = 0; v < rb.V; ++v) ucap = std::max(ucap, rb.v[v].units_cap);
   if (ucap == 0) return 0;
   const dim3 grid(ucap, rb.V, 1);
-  if (extras) blend_bwd_kernel<true><<<grid, BL_THREADS, 0, s>>>(rb);
-  else blend_bwd_kernel<false><<<grid, BL_THREADS, 0, s>>>(rb);
+  constexpr int dyn = 8 * (int)sizeof(BwdWarpState);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(blend_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    cudaFuncSetAttribute(blend_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    attr_set = true;
+  }
+  if (extras) blend_bwd_kernel<true><<<grid, BL_THREADS, dyn, s>>>(rb);
+  else blend_bwd_kernel<false><<<grid, BL_THREADS, dyn, s>>>(rb);
   count_launch();
   return check_launch("blend_bwd", debug, s);
 }

@@ -225,6 +225,71 @@ __device__ __forceinline__ int cons_classify(int first_included, int first_exclu
   return mine;
 }
 
+// ---- pair-centric evaluation: hits -> candidates -> pairs ------------------------------------------------
+// The splats of a dense avatar are a few pixels wide: with pixels mapped to lanes (above), ncu showed the blend
+// instructions of the backward running with 5.8 of 32 lanes active inside the gradient block and ~13 % of the evaluated
+// (pixel, Gaussian) slots passing the alpha test.  The pair-centric kernels turn the loop inside out: a consumer warp
+// still owns an 8x4 pixel block, but its lanes no longer stand for pixels.  Per batch of staged list entries it
+//   1. classifies the entries against its block (one ballot per 32 entries) and compacts the HITS — entry index plus
+//      the integer pixel rectangle (footprint box of {alpha >= 1/255} clipped to the block) — into shared memory;
+//   2. expands the hits into CANDIDATES, one (entry, pixel) per lane, 32 per round, every lane busy: the rectangles are
+//      laid end to end by a warp scan and a lane finds its hit with a reduce-or / popc over the rectangle starts;
+//   3. evaluates alpha per candidate and compacts the survivors into a ring of PAIRS;
+//   4. commits 32 pairs at a time to the per-pixel recurrence state, which lives in shared memory; pairs of one round
+//      that fall on the same pixel are serialised in list order (match.any + rank), everything else runs at full width.
+// Lane l of a consumer warp owns pixel (l & 7, l >> 3) of the block for initialisation / write-out of that state.
+constexpr int PB_CAP = 64;                                  // pair ring per warp (>= 32 carried + 32 new)
+constexpr uint64_t DIV_LUT = 0x1F242A333F557FFFull;         // byte w-1: ceil(256 / w) - 1 for w = 1..8: k / w == (k * inv) >> 8, k < 32
+
+// hit word: entry 0..127 | x0 << 7 (3) | y0 << 10 (2) | (w-1) << 12 (3) | (h-1) << 15 (2) | (inv-1) << 17 (8)
+__device__ __forceinline__ int hit_pixels(uint32_t hw) { return (int)(((hw >> 12) & 7u) + 1u) * (int)(((hw >> 15) & 3u) + 1u); }
+
+// Entries [first_included, first_excluded) of the landed batch against the block with pixel origin (bx0, by0); writes
+// the hit words in list order and returns their number.  The rectangle holds the integer pixels p with
+// x - hx <= p <= x + hx (same in y): hx, hy bound {alpha >= 1/255} conservatively (preprocess.cu), so every pixel
+// outside would have failed the reference's alpha test (forward.cu:343-345).
+__device__ __forceinline__ int classify_hits(int first_included, int first_excluded, const float4* s_xy, uint32_t* hits,
+                                             int bx0, int by0, int lane) {
+  int cnt = 0;
+  const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int c = 0; c < BL_CHUNKS; ++c) {
+    const int e = c * 32 + lane;
+    bool hit = false;
+    uint32_t word = 0;
+    if (e >= first_included && e < first_excluded) {
+      const float4 q = s_xy[e];
+      if (q.z >= 0.f) {
+        const int x0 = max(__float2int_ru(q.x - q.z), bx0), x1 = min(__float2int_rd(q.x + q.z), bx0 + 7);
+        const int y0 = max(__float2int_ru(q.y - q.w), by0), y1 = min(__float2int_rd(q.y + q.w), by0 + 3);
+        hit = x0 <= x1 && y0 <= y1;
+        const uint32_t w1 = (uint32_t)(x1 - x0), h1 = (uint32_t)(y1 - y0);
+        const uint32_t inv1 = (uint32_t)(DIV_LUT >> (8u * (w1 & 7u))) & 0xffu;
+        word = (uint32_t)e | ((uint32_t)(x0 - bx0) << 7) | ((uint32_t)(y0 - by0) << 10) | (w1 << 12) | (h1 << 15) | (inv1 << 17);
+      }
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+    if (hit) hits[cnt + __popc(bal & lt)] = word;
+    cnt += __popc(bal);
+  }
+  __syncwarp();
+  return cnt;
+}
+
+// One expansion round.  Lane i holds hit i of the current group (`hw`, n = 0 beyond the group), `start` = exclusive
+// prefix of the hits' pixel counts.  Candidate `base + lane` -> its hit word and its index k inside the rectangle.
+__device__ __forceinline__ bool expand_candidate(uint32_t hw, int n, int start, int total, int base, int lane, uint32_t& hit_word,
+                                                 int& k) {
+  const bool starts_here = n > 0 && start >= base && start < base + 32;
+  const uint32_t m = __reduce_or_sync(0xffffffffu, starts_here ? (1u << (start - base)) : 0u);
+  const int before = __popc(__ballot_sync(0xffffffffu, n > 0 && start < base));
+  const int idx = before + __popc(m & (0xffffffffu >> (31 - lane))) - 1;   // last hit starting at or before this candidate
+  hit_word = __shfl_sync(0xffffffffu, hw, idx & 31);
+  const int hs = __shfl_sync(0xffffffffu, start, idx & 31);
+  k = base + lane - hs;
+  return base + lane < total;
+}
+
 constexpr uint32_t PAD_WORD = 0x01010101u * (uint32_t)PAD_ENTRY;  // four PAD_ENTRY indices
 
 // ---- producer loop -----------------------------------------------------------------------------------
