@@ -9,8 +9,8 @@
 //     become ~3-4 k independent units that the block scheduler balances dynamically, and the never-blended
 //     tail beyond the tile's last contributor (tile_last) is not even staged;
 //   * same producer warp / mbarrier ring as the forward;
-//   * PAIR-CENTRIC consumers (pipeline.cuh): a warp owns an 8x4 pixel block, but its lanes stand for (entry, pixel)
-//     candidates and then for surviving pairs, not for pixels.  The first version mapped pixels to lanes and walked
+//   * PAIR-CENTRIC consumers (pipeline.cuh): a warp owns two pixel rows of the tile, but its lanes stand for (entry,
+//     pixel) candidates inside the entry's ellipse and then for surviving pairs, not for pixels.  The first version mapped pixels to lanes and walked
 //     the candidates in a loop: ncu showed its gradient block running with 5.8 of 32 lanes active and 1.5 G warp
 //     instructions per 8-view batch (2.17 ms).  Here the alpha evaluation runs on 32 candidates per instruction and
 //     the gradient arithmetic + reductions on 32 surviving pairs per instruction; the per-pixel recurrences
@@ -120,21 +120,20 @@ __global__ void __launch_bounds__(BL_THREADS, 4) blend_bwd_kernel(const __grid_c
 
   // ========================= CONSUMERS =========================
   BwdWarpState& ws = s_warp[warp];
-  const int bx0 = (int)(tile_bx * TILE) + (warp & 1) * 8;   // pixel origin of this warp's 8x4 block
-  const int by0 = (int)(tile_by * TILE) + (warp >> 1) * 4;
+  const int bx0 = (int)(tile_bx * TILE);                    // pixel origin of this warp's 16x2 rows
+  const int by0 = (int)(tile_by * TILE) + warp * 2;
   const float ddelx_dx = 0.5f * W;
   const float ddely_dy = 0.5f * H;
-  int warp_last;
+  int warp_last, my_last;
   {
-    // lane l owns pixel (l & 7, l >> 3) of the block for the set-up of the per-pixel state
-    const int lx = lane & 7, ly = lane >> 3;
+    // lane l owns pixel (l & 15, l >> 4) of the two rows for the set-up of the per-pixel state
+    const int lx = lane & 15, ly = lane >> 4;
     const uint32_t px = (uint32_t)(bx0 + lx), py = (uint32_t)(by0 + ly);
     const bool inside = px < (uint32_t)W && py < (uint32_t)H;
     const uint32_t pix_id = (uint32_t)W * py + px;
-    // the forward numbers the pixels of a block by ITS lane layout (lane_pixel, pipeline.cuh)
-    const int fwd_lane = (((ly / SUB_H) * SUB_GX + lx / SUB_W) * SUB_LANES) + (ly % SUB_H) * SUB_W + (lx % SUB_W);
-    const int pix_in_tile = warp * 32 + fwd_lane;
+    const int pix_in_tile = (warp * 2 + ly) * TILE + lx;     // checkpoints are stored in tile raster order
     const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
+    my_last = last_contributor;
     warp_last = __reduce_max_sync(0xffffffffu, last_contributor);
 
     // State of the forward recurrence at the END of this segment.  Behind-colour B = sum_{j >= seg_hi} c_j a_j T_j
@@ -216,7 +215,7 @@ __global__ void __launch_bounds__(BL_THREADS, 4) blend_bwd_kernel(const __grid_c
     if (act) {
       const float4 dp = ws.dpix[pix];
       const float4 g = s_xy[stage][j];
-      const float dx = g.x - (float)(bx0 + (pix & 7)), dy = g.y - (float)(by0 + (pix >> 3));
+      const float dx = g.x - (float)(bx0 + (pix & 15)), dy = g.y - (float)(by0 + (pix >> 4));
       const float w = alpha * Ti;
       // dC/dalpha_i = c_i*Ti - B/(1-alpha_i)   (same quantity as backward.cu:515-525's (c - accum_rec)*T)
       float dL_dalpha = (cd.x * Ti - Bb0 * rinv) * dp.x + (cd.y * Ti - Bb1 * rinv) * dp.y + (cd.z * Ti - Bb2 * rinv) * dp.z;
@@ -251,8 +250,11 @@ __global__ void __launch_bounds__(BL_THREADS, 4) blend_bwd_kernel(const __grid_c
     if (batch_first_pos - (BL_BATCH - 1) < warp_last) {  // else: whole batch lies behind this block's last contributor
       // entries at list positions >= warp_last lie behind this block's last contributor: batch entry e sits at
       // position batch_first_pos - e, so only e > batch_first_pos - warp_last can matter
+      // live columns: pixels whose last contributor lies at or before the batch's nearest entry
+      const int batch_near_pos = batch_first_pos - min(BL_BATCH, count - b * BL_BATCH) + 1;
+      const RowWindow rw = row_window(__ballot_sync(0xffffffffu, batch_near_pos < my_last), bx0);
       const int nhits = classify_hits(max(0, batch_first_pos - warp_last + 1), min(BL_BATCH, count - b * BL_BATCH),
-                                      s_xy[stage], ws.hits, bx0, by0, lane);
+                                      s_xy[stage], s_co[stage], ws.hits, bx0, by0, rw, lane);
       for (int h0 = 0; h0 < nhits; h0 += 32) {
         // lane i <- hit h0 + i; rectangles laid end to end: start = exclusive prefix of the pixel counts
         const uint32_t hw = (h0 + lane < nhits) ? ws.hits[h0 + lane] : 0u;
@@ -266,20 +268,14 @@ __global__ void __launch_bounds__(BL_THREADS, 4) blend_bwd_kernel(const __grid_c
         const int start = incl - n;
         const int cand_total = __shfl_sync(0xffffffffu, incl, 31);
         for (int base = 0; base < cand_total; base += 32) {
-          uint32_t w_hit;
-          int k;
-          bool ok = expand_candidate(hw, n, start, cand_total, base, lane, w_hit, k);
-          const int j = (int)(w_hit & 127u);
-          const int rw = (int)((w_hit >> 12) & 7u) + 1;
-          const int ry = (k * (int)(((w_hit >> 17) & 255u) + 1u)) >> 8;
-          const int lx = (int)((w_hit >> 7) & 7u) + (k - ry * rw);
-          const int ly = (int)((w_hit >> 10) & 3u) + ry;
-          const int pix = ly * 8 + lx;
+          int j, pix;
+          bool ok = expand_candidate(hw, n, start, cand_total, base, lane, j, pix);
+          pix &= 31;
           const int pos = batch_first_pos - j;   // 0-based list position of the entry
-          ok = ok && pos < ws.last[pix & 31];
+          ok = ok && pos < ws.last[pix];
           const float4 g = s_xy[stage][j];
           const float4 con_o = s_co[stage][j];
-          const float dx = g.x - (float)(bx0 + lx), dy = g.y - (float)(by0 + ly);
+          const float dx = g.x - (float)(bx0 + (pix & 15)), dy = g.y - (float)(by0 + (pix >> 4));
           const float power = -0.5f * (con_o.x * dx * dx + con_o.z * dy * dy) - con_o.y * dx * dy;
           const float G = ex2_approx(power * 1.4426950408889634f);
           const float alpha = min(0.99f, con_o.w * G);

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(BL_THREADS, 4) blend_fwd_kernel(const __grid_c
   float Dz = 0.f;
 
   const uint32_t ckpt_base = seg_base[tile_id];
-  const int pix_in_tile = warp * 32 + lane;
+  const int pix_in_tile = ly * TILE + lx;   // checkpoints are stored in tile raster order
   for (int b = 0; b < rounds; ++b) {
     const int stage = b % BL_STAGES;
     // checkpoint of the recurrence state at every SEG-th list position: lets the backward replay the

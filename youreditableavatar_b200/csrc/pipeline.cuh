@@ -226,46 +226,91 @@ __device__ __forceinline__ int cons_classify(int first_included, int first_exclu
 }
 
 // ---- pair-centric evaluation: hits -> candidates -> pairs ------------------------------------------------
-// The splats of a dense avatar are a few pixels wide: with pixels mapped to lanes (above), ncu showed the blend
-// instructions of the backward running with 5.8 of 32 lanes active inside the gradient block and ~13 % of the evaluated
-// (pixel, Gaussian) slots passing the alpha test.  The pair-centric kernels turn the loop inside out: a consumer warp
-// still owns an 8x4 pixel block, but its lanes no longer stand for pixels.  Per batch of staged list entries it
-//   1. classifies the entries against its block (one ballot per 32 entries) and compacts the HITS — entry index plus
-//      the integer pixel rectangle (footprint box of {alpha >= 1/255} clipped to the block) — into shared memory;
-//   2. expands the hits into CANDIDATES, one (entry, pixel) per lane, 32 per round, every lane busy: the rectangles are
-//      laid end to end by a warp scan and a lane finds its hit with a reduce-or / popc over the rectangle starts;
+// The splats of a dense avatar are a few pixels wide and mostly thin (surface-aligned discs seen at an angle): with
+// pixels mapped to lanes (above), ncu showed the blend instructions of the backward running with 5.8 of 32 lanes
+// active inside the gradient block and ~13 % of the evaluated (pixel, Gaussian) slots passing the alpha test.  The
+// pair-centric kernels turn the loop inside out: a consumer warp still owns 32 pixels of the tile, but its lanes no
+// longer stand for pixels.  Per batch of staged list entries it
+//   1. classifies the entries against its pixels and compacts the HITS — entry index plus, per pixel row, the span of
+//      integer pixels inside the ellipse {alpha >= 1/255} (not its bounding box: a thin ellipse at 45 degrees fills
+//      a fifth of its box) — into shared memory;
+//   2. expands the hits into CANDIDATES, one (entry, pixel) per lane, 32 per round, every lane busy: the spans are
+//      laid end to end by a warp scan and a lane finds its hit with a reduce-or / popc over the span starts;
 //   3. evaluates alpha per candidate and compacts the survivors into a ring of PAIRS;
 //   4. commits 32 pairs at a time to the per-pixel recurrence state, which lives in shared memory; pairs of one round
 //      that fall on the same pixel are serialised in list order (match.any + rank), everything else runs at full width.
-// Lane l of a consumer warp owns pixel (l & 7, l >> 3) of the block for initialisation / write-out of that state.
+// Consumer warp w owns tile rows 2w and 2w+1 (16 x 2 pixels), so the 16 row spans of an entry are computed exactly
+// once per tile — by the warp that owns the row.  Pixel index inside the warp: (row << 4) | x; lane l owns pixel l for
+// the initialisation / write-out of the state.
 constexpr int PB_CAP = 64;                                  // pair ring per warp (>= 32 carried + 32 new)
-constexpr uint64_t DIV_LUT = 0x1F242A333F557FFFull;         // byte w-1: ceil(256 / w) - 1 for w = 1..8: k / w == (k * inv) >> 8, k < 32
 
-// hit word: entry 0..127 | x0 << 7 (3) | y0 << 10 (2) | (w-1) << 12 (3) | (h-1) << 15 (2) | (inv-1) << 17 (8)
-__device__ __forceinline__ int hit_pixels(uint32_t hw) { return (int)(((hw >> 12) & 7u) + 1u) * (int)(((hw >> 15) & 3u) + 1u); }
+// hit word: entry 0..127 | x0 of row 0 << 7 (4) | w of row 0 << 11 (5, 0..16) | x0 of row 1 << 16 (4) | w of row 1 << 20 (5)
+__device__ __forceinline__ int hit_pixels(uint32_t hw) { return (int)((hw >> 11) & 31u) + (int)((hw >> 20) & 31u); }
 
-// Entries [first_included, first_excluded) of the landed batch against the block with pixel origin (bx0, by0); writes
-// the hit words in list order and returns their number.  The rectangle holds the integer pixels p with
-// x - hx <= p <= x + hx (same in y): hx, hy bound {alpha >= 1/255} conservatively (preprocess.cu), so every pixel
-// outside would have failed the reference's alpha test (forward.cu:343-345).
-__device__ __forceinline__ int classify_hits(int first_included, int first_excluded, const float4* s_xy, uint32_t* hits,
-                                             int bx0, int by0, int lane) {
+// Span of integer pixel columns of tile row `v` (relative to the Gaussian's centre: v = row - y) that lie inside the
+// ellipse A u^2 + 2 B u v + C v^2 <= 2 tau:  u in kB v -+ sqrt(s (hy^2 - v^2)),  kB = -B / A,  s = det / A^2, and
+// hy^2 = 2 tau A / det is the half-height of the ellipse's bounding box as stored by the preprocess kernel (with its
+// margins: tau inflated by 1 %, hy by 0.1 % + 0.01 px); 0.02 px are added to the half-width for the fp32 rounding of
+// centre and root.  Returns the width (0 = row not reached) and the first column, both clipped to the pixel columns
+// [lo, hi] (the live part of the row, see RowWindow).
+__device__ __forceinline__ int row_span(float x, float v, float hy, float kB, float s, int lo, int hi, int& x0) {
+  const float t = hy * hy - v * v;
+  if (!(t >= 0.f)) return 0;
+  const float hw = sqrtf(s * t) + 0.02f;
+  const float c = fmaf(kB, v, x);
+  x0 = max(__float2int_ru(c - hw), lo);
+  const int x1 = min(__float2int_rd(c + hw), hi);
+  return max(x1 - x0 + 1, 0);
+}
+
+// The columns of the warp's two rows that can still take part in the current batch: [lo, hi] per row in absolute pixel
+// columns, lo > hi = row switched off.  The forward passes the columns whose pixels have not terminated yet, the
+// backward those whose last contributor lies at or before the batch: a tile on the silhouette keeps a few columns
+// alive deep into its list, and only those are enumerated.
+struct RowWindow {
+  int lo0, hi0, lo1, hi1;
+};
+__device__ __forceinline__ RowWindow row_window(uint32_t live_mask, int tx0) {   // bit (row << 4 | x) set = pixel live
+  RowWindow w;
+  const uint32_t m0 = live_mask & 0xffffu, m1 = live_mask >> 16;
+  w.lo0 = m0 ? tx0 + (__ffs(m0) - 1) : 1;
+  w.hi0 = m0 ? tx0 + (31 - __clz(m0)) : 0;
+  w.lo1 = m1 ? tx0 + (__ffs(m1) - 1) : 1;
+  w.hi1 = m1 ? tx0 + (31 - __clz(m1)) : 0;
+  return w;
+}
+
+// Entries [first_included, first_excluded) of the landed batch against tile rows ty0, ty0 + 1 (pixel rows) of the tile
+// whose first pixel column is tx0, restricted to the live columns `rw`.  Writes the hit words in list order and returns
+// their number.
+__device__ __forceinline__ int classify_hits(int first_included, int first_excluded, const float4* s_xy, const float4* s_co,
+                                             uint32_t* hits, int tx0, int ty0, const RowWindow rw, int lane) {
   int cnt = 0;
   const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
   for (int c = 0; c < BL_CHUNKS; ++c) {
     const int e = c * 32 + lane;
-    bool hit = false;
     uint32_t word = 0;
+    bool hit = false;
     if (e >= first_included && e < first_excluded) {
       const float4 q = s_xy[e];
-      if (q.z >= 0.f) {
-        const int x0 = max(__float2int_ru(q.x - q.z), bx0), x1 = min(__float2int_rd(q.x + q.z), bx0 + 7);
-        const int y0 = max(__float2int_ru(q.y - q.w), by0), y1 = min(__float2int_rd(q.y + q.w), by0 + 3);
-        hit = x0 <= x1 && y0 <= y1;
-        const uint32_t w1 = (uint32_t)(x1 - x0), h1 = (uint32_t)(y1 - y0);
-        const uint32_t inv1 = (uint32_t)(DIV_LUT >> (8u * (w1 & 7u))) & 0xffu;
-        word = (uint32_t)e | ((uint32_t)(x0 - bx0) << 7) | ((uint32_t)(y0 - by0) << 10) | (w1 << 12) | (h1 << 15) | (inv1 << 17);
+      const float v0 = (float)ty0 - q.y;                       // row 0 relative to the centre; row 1 is v0 + 1
+      if (q.z >= 0.f && v0 + 1.f >= -q.w && v0 <= q.w) {       // opacity >= 1/255 and the box reaches one of the rows
+        int x00 = tx0, x01 = tx0, w0, w1;
+        if (q.w < 1e29f) {
+          const float4 co = s_co[e];
+          const float invA = 1.0f / co.x;
+          const float kB = -co.y * invA;
+          const float s = (co.x * co.z - co.y * co.y) * invA * invA;
+          w0 = row_span(q.x, v0, q.w, kB, s, rw.lo0, rw.hi0, x00);
+          w1 = row_span(q.x, v0 + 1.f, q.w, kB, s, rw.lo1, rw.hi1, x01);
+        } else {                                               // ill-conditioned conic: no culling (preprocess.cu)
+          x00 = rw.lo0; w0 = max(rw.hi0 - rw.lo0 + 1, 0);
+          x01 = rw.lo1; w1 = max(rw.hi1 - rw.lo1 + 1, 0);
+        }
+        hit = (w0 + w1) > 0;
+        word = (uint32_t)e | ((uint32_t)((x00 - tx0) & 15) << 7) | ((uint32_t)w0 << 11) | ((uint32_t)((x01 - tx0) & 15) << 16) |
+               ((uint32_t)w1 << 20);
       }
     }
     const uint32_t bal = __ballot_sync(0xffffffffu, hit);
@@ -277,16 +322,18 @@ __device__ __forceinline__ int classify_hits(int first_included, int first_exclu
 }
 
 // One expansion round.  Lane i holds hit i of the current group (`hw`, n = 0 beyond the group), `start` = exclusive
-// prefix of the hits' pixel counts.  Candidate `base + lane` -> its hit word and its index k inside the rectangle.
-__device__ __forceinline__ bool expand_candidate(uint32_t hw, int n, int start, int total, int base, int lane, uint32_t& hit_word,
-                                                 int& k) {
+// prefix of the hits' pixel counts.  Candidate `base + lane` -> entry index `j` and pixel (row << 4 | x) `pix`.
+__device__ __forceinline__ bool expand_candidate(uint32_t hw, int n, int start, int total, int base, int lane, int& j, int& pix) {
   const bool starts_here = n > 0 && start >= base && start < base + 32;
   const uint32_t m = __reduce_or_sync(0xffffffffu, starts_here ? (1u << (start - base)) : 0u);
   const int before = __popc(__ballot_sync(0xffffffffu, n > 0 && start < base));
   const int idx = before + __popc(m & (0xffffffffu >> (31 - lane))) - 1;   // last hit starting at or before this candidate
-  hit_word = __shfl_sync(0xffffffffu, hw, idx & 31);
+  const uint32_t w_hit = __shfl_sync(0xffffffffu, hw, idx & 31);
   const int hs = __shfl_sync(0xffffffffu, start, idx & 31);
-  k = base + lane - hs;
+  const int k = base + lane - hs;
+  const int w0 = (int)((w_hit >> 11) & 31u);
+  j = (int)(w_hit & 127u);
+  pix = (k < w0) ? ((int)((w_hit >> 7) & 15u) + k) : (16 + (int)((w_hit >> 16) & 15u) + (k - w0));
   return base + lane < total;
 }
 
