@@ -66,6 +66,11 @@ __global__ void __launch_bounds__(1024) emit_scan_kernel(const __grid_constant__
   // this CTA is the one per-view launch that precedes the tile sort: it also clears the view's tile ranges
   // (ranges_kernel only writes the boundaries it finds), which saves a memset node per view
   for (uint32_t t = threadIdx.x; t < rv.T; t += blockDim.x) rv.ranges[t] = make_uint2(0u, 0u);
+  // ... and the temp area of the tile sort (histograms, tickets, look-back flags): another memset node per view less
+  {
+    uint4* t4 = reinterpret_cast<uint4*>(rv.tile_sort_temp);
+    for (uint32_t i = threadIdx.x; i * 4 < rv.tile_sort_zero_words; i += blockDim.x) t4[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
   const uint32_t ntiles = ((uint32_t)rv.P + EMIT_TILE - 1) / EMIT_TILE;
   if (ntiles == 0) return;
   uint32_t* __restrict__ st = rv.scan_state;
@@ -267,6 +272,7 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const __grid_constant_
   __shared__ uint32_t s_warp[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < TO_BUCKETS; i += 1024) s_cnt[i] = 0;
+  if (tid == 0) rv.unit_count[3] = 0;   // the forward that follows clears the packed gradient rows (blend_fwd.cu)
   if (queue_counters != nullptr && tid < MAX_QUEUES) queue_counters[tid] = 0;
   __syncthreads();
   auto bucket_of = [&](uint32_t t) {
@@ -349,7 +355,15 @@ __global__ void __launch_bounds__(1024) unit_build_kernel(const __grid_constant_
   __shared__ uint32_t s_carry;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_carry = 0;
+  // The packed gradient rows are cleared by the forward (blend_fwd.cu).  A second backward on the same forward
+  // (retain_graph) finds them used: it clears them here — one CTA, slow, but only on that rare path.
+  if (unit_count[3] != 0u) {
+    float4* g4 = reinterpret_cast<float4*>(rv.grad_acc);
+    const size_t n4 = (size_t)rv.P * GRAD_ACC / 4;
+    for (size_t i = tid; i < n4; i += 1024) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   __syncthreads();
+  if (tid == 0) unit_count[3] = 1u;
   for (uint32_t t0 = 0; t0 < T; t0 += 1024) {
     const uint32_t t = t0 + tid;
     uint32_t n = 0;

@@ -154,7 +154,7 @@ static int depth_sort_views(const tgr_params* views, int32_t n, cudaStream_t s) 
     }
     bool in_b = false;
     prof_begin(TGR_STAGE_DEPTH_SORT, s);
-    if (int rc = launch_sort_pairs_batch(sb, true, 0, 32, s, &in_b)) return rc;
+    if (int rc = launch_sort_pairs_batch(sb, true, 0, 32, s, &in_b, /*temp_is_zero=*/true)) return rc;   // preprocess_kernel
     prof_end(TGR_STAGE_DEPTH_SORT, s);
     if (in_b) { set_error("internal: depth sort must end in buffer A"); return 3; }
   }
@@ -173,6 +173,8 @@ static RenderView make_render_view(const tgr_params& p, uint64_t cap, bool tile_
   r.header = g.header; r.order = g.order; r.rect = g.rect;
   r.xy_ext = g.xy_ext; r.conic_opacity = g.conic_opacity; r.rgb_depth = g.rgb_depth; r.scan_state = g.scan_state;
   r.key_a = b.key_a; r.val_a = b.val_a;
+  r.tile_sort_temp = b.sort_temp;
+  r.tile_sort_zero_words = (uint32_t)sort_zero_words(cap, make_sort_plan(0, tile_bits(r.T)).npasses);
   r.sorted_keys = tile_sorted_in_b ? b.key_b : b.key_a;
   r.point_list = tile_sorted_in_b ? b.val_b : b.val_a;
   r.grad_acc = b.grad_acc; r.ckpt = b.ckpt; r.ckpt_z = b.ckpt_z; r.units = b.units;
@@ -219,7 +221,7 @@ static int render_group(const tgr_params* views, const uint64_t* caps, int32_t n
       sb.s[k] = SortSeg{b.key_a, b.val_a, b.key_b, b.val_b, b.sort_temp, &g.header->num_rendered, rb.v[k].cap};
     }
     prof_begin(TGR_STAGE_TILE_SORT, s);
-    if (int rc = launch_sort_pairs_batch(sb, false, 0, tile_bits(T0), s, nullptr)) return rc;
+    if (int rc = launch_sort_pairs_batch(sb, false, 0, tile_bits(T0), s, nullptr, /*temp_is_zero=*/true)) return rc;   // emit_scan_kernel
     prof_end(TGR_STAGE_TILE_SORT, s);
   }
   prof_begin(TGR_STAGE_RANGES, s);
@@ -246,6 +248,15 @@ static int for_each_group(const tgr_params* views, const uint64_t* caps, int32_t
 }
 }  // extern "C++"
 
+struct HeaderBatch {
+  int32_t V;
+  GeomHeader* h[MAX_BATCH];
+};
+__global__ void header_init_kernel(const __grid_constant__ HeaderBatch hb) {
+  const int v = threadIdx.x >> 5, w = threadIdx.x & 31;
+  if (v < hb.V) reinterpret_cast<uint32_t*>(hb.h[v])[w] = 0u;   // 128-byte header = 32 words
+}
+
 // One preprocess launch per chunk of <= TGR_MAX_BATCH views; instance counts go to each view's pinned slot.
 static int preprocess_views(const tgr_params* views, int32_t n, const tgr_binding* bind, cudaStream_t s) {
   for (int32_t v = 0; v < n; ++v) {
@@ -264,11 +275,15 @@ static int preprocess_views(const tgr_params* views, int32_t n, const tgr_bindin
     vb.V = std::min<int32_t>(MAX_BATCH, n - v0);
     vb.first = 0;
     vb.end = p0->P;
+    HeaderBatch hb{};
+    hb.V = vb.V;
     for (int32_t k = 0; k < vb.V; ++k) {
       GeomView g = carve_geom(views[v0 + k].geom_buffer, p0->P);
-      cudaMemsetAsync(g.header, 0, sizeof(GeomHeader), s);
+      hb.h[k] = g.header;
       vb.v[k] = make_view_desc(views[v0 + k], g, nullptr);
     }
+    header_init_kernel<<<1, 32 * MAX_BATCH, 0, s>>>(hb);   // one launch where V memset nodes used to be
+    count_launch();
     prof_begin(TGR_STAGE_PREPROCESS, s);
     if (int rc = launch_preprocess(*p0, bind, vb, s)) return rc;
     prof_end(TGR_STAGE_PREPROCESS, s);
@@ -355,7 +370,6 @@ static int backward_blend_group(const tgr_params* views, const uint64_t* caps, i
     if (!views[k].dL_dout_color) { set_error("dL_dout_color missing"); return 1; }
     rb.v[k] = make_render_view(views[k], caps[k], in_b);
     rb.T_max = std::max(rb.T_max, rb.v[k].T);
-    cudaMemsetAsync(rb.v[k].grad_acc, 0, (size_t)views[k].P * GRAD_ACC * sizeof(float), s);
     extras = extras || (views[k].extras && (views[k].dL_dout_depth || views[k].dL_dout_alpha));
   }
   prof_begin(TGR_STAGE_BLEND_BWD, s);

@@ -52,6 +52,10 @@ __host__ __device__ inline SortPlan make_sort_plan(int begin_bit, int end_bit) {
 
 // temp: [ghist: RS_MAX_PASSES*256 u32][tickets: 32 u32][lookback: RS_MAX_PASSES * ntiles * 256 u32]
 __host__ __device__ inline uint64_t sort_ntiles(uint64_t n) { return (n + RS_TILE - 1) / RS_TILE; }
+// words of the temp area that must be zero before a sort of n pairs with `npasses` passes starts
+__host__ __device__ inline uint64_t sort_zero_words(uint64_t n, int npasses) {
+  return (uint64_t)RS_MAX_PASSES * RS_BINS + 32 + (uint64_t)npasses * sort_ntiles(n) * RS_BINS;
+}
 __host__ __device__ inline uint64_t sort_temp_bytes(uint64_t n) {
   uint64_t words = (uint64_t)RS_MAX_PASSES * RS_BINS + 32 + (uint64_t)RS_MAX_PASSES * sort_ntiles(n) * RS_BINS;
   return align_up(words * 4, 128);
@@ -132,7 +136,8 @@ struct ImageView {
   float4* final_state;   // [N] (T_final, C_r, C_g, C_b) without background: end state of the forward recurrence
   float* final_z;        // [N] depth accumulator at the end of the forward (extras)
   uint32_t* seg_base;    // [T+1] first checkpoint slot of each tile (exclusive scan of ceil(len/SEG))
-  uint32_t* unit_count;  // [32] [0] number of backward work units of this view
+  uint32_t* unit_count;  // [32] [0] number of backward work units of this view, [3] set once a backward has used the
+                         //      packed gradient rows (a repeated backward has to clear them itself)
   uint64_t bytes;
 };
 
@@ -187,7 +192,9 @@ struct ViewDesc {
   const float* campos;
   float tan_fovx, tan_fovy;
   int32_t W, H;
-  int32_t prefiltered, pad0;
+  int32_t prefiltered;
+  uint32_t sort_zero_words;   // leading words of sort_temp the preprocess kernel clears for the depth sort
+  uint32_t* sort_temp;
   // forward outputs of this view
   int32_t* radii;
   GeomHeader* header;
@@ -229,6 +236,8 @@ struct RenderView {
   // binning
   uint32_t* key_a;
   uint32_t* val_a;
+  uint32_t* tile_sort_temp;      // temp area of the tile sort; its leading tile_sort_zero_words are cleared by emit_scan
+  uint32_t tile_sort_zero_words;
   const uint32_t* sorted_keys;   // tile ids after the tile sort
   const uint32_t* point_list;    // Gaussian ids after the tile sort
   float* grad_acc;
@@ -401,7 +410,7 @@ int launch_sort_pairs(uint64_t n_host, const uint32_t* n_dev, uint32_t* keys_a, 
                       uint32_t* vals_b, bool iota_vals, int begin_bit, int end_bit, uint32_t* temp, cudaStream_t s,
                       bool* result_in_b);
 int launch_sort_pairs_batch(const SortBatch& sb, bool iota_vals, int begin_bit, int end_bit, cudaStream_t s,
-                            bool* result_in_b);
+                            bool* result_in_b, bool temp_is_zero = false);
 int launch_emit(const RenderBatch& rb, cudaStream_t s);
 int launch_ranges(const RenderBatch& rb, bool zero_first, cudaStream_t s);
 int launch_tile_order(const RenderBatch& rb, cudaStream_t s);

@@ -144,6 +144,15 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const tgr_params p, con
     s_cam[v][k] = x;
   }
   if (threadIdx.x < 2 * MAX_BATCH) s_cnt[threadIdx.x >> 1][threadIdx.x & 1] = 0;
+  // on the side: clear the temp area of the depth sort that follows (histograms, tickets, look-back flags); block b
+  // takes slice b — this replaces one memset node per view
+  for (int v = 0; v < V; ++v) {
+    const uint32_t words = vb.v[v].sort_zero_words;
+    const uint32_t per = ((words + gridDim.x - 1) / gridDim.x + 3u) & ~3u;
+    const uint32_t lo = blockIdx.x * per, hi = min(lo + per, words);
+    uint4* t4 = reinterpret_cast<uint4*>(vb.v[v].sort_temp);
+    for (uint32_t i = lo / 4 + threadIdx.x; i * 4 < hi; i += blockDim.x) t4[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
   if (STAGED) {
     const int block_first = blockIdx.x * blockDim.x;
     const int nrows = min((int)blockDim.x, P - block_first);
@@ -310,6 +319,8 @@ ViewDesc make_view_desc(const tgr_params& p, const GeomView& g, const float* gra
   ViewDesc d{};
   d.viewmatrix = p.viewmatrix; d.projmatrix = p.projmatrix; d.campos = p.campos;
   d.tan_fovx = p.tan_fovx; d.tan_fovy = p.tan_fovy; d.W = p.W; d.H = p.H; d.prefiltered = p.prefiltered;
+  d.sort_temp = g.sort_temp;
+  d.sort_zero_words = (uint32_t)sort_zero_words((uint64_t)(p.P > 0 ? p.P : 0), RS_MAX_PASSES);
   d.radii = p.radii; d.header = g.header; d.depth_key = g.depth_key; d.rect = g.rect;
   d.xy_ext = g.xy_ext; d.conic_opacity = g.conic_opacity; d.rgb_depth = g.rgb_depth; d.clamped = g.clamped;
   d.grad_acc = grad_acc;

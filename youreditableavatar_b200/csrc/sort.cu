@@ -66,6 +66,17 @@ __global__ void __launch_bounds__(256) radix_hist_kernel(const __grid_constant__
     if (sh[i]) atomicAdd(&ghist[i], sh[i]);
 }
 
+// clears the leading words of every segment's temp area (histograms, tickets, look-back): one launch for the batch
+// where V cudaMemsetAsync nodes used to be.  The rasterizer's own sorts do not even need it: the kernel in front of
+// them clears the area on the side (preprocess_kernel for the depth sort, emit_scan_kernel for the tile sort).
+__global__ void __launch_bounds__(256) radix_zero_kernel(const __grid_constant__ SortBatch sb, int npasses) {
+  const SortSeg& seg = sb.s[blockIdx.y];
+  if (seg.n_host == 0) return;
+  const uint32_t words = (uint32_t)sort_zero_words(seg.n_host, npasses);
+  uint4* t4 = reinterpret_cast<uint4*>(seg.temp);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i * 4 < words; i += gridDim.x * blockDim.x) t4[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 // ---- one digit pass ------------------------------------------------------------------------------
 template <bool IOTA>
 __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) radix_pass_kernel(const __grid_constant__ SortBatch sb, int pass, int flip,
@@ -244,7 +255,7 @@ constexpr size_t RS_SMEM = (size_t)(2 * RS_TILE + (RS_THREADS / 32) * RS_BINS + 
 // Sorts every segment of `sb` (same bit range for all).  Results land in the B buffers when the plan has an odd
 // number of passes (*result_in_b), else in A.
 int launch_sort_pairs_batch(const SortBatch& sb, bool iota_vals, int begin_bit, int end_bit, cudaStream_t s,
-                            bool* result_in_b) {
+                            bool* result_in_b, bool temp_is_zero) {
   SortPlan plan = make_sort_plan(begin_bit, end_bit);
   if (result_in_b) *result_in_b = (plan.npasses & 1) != 0;
   uint64_t n_max = 0;
@@ -258,11 +269,9 @@ int launch_sort_pairs_batch(const SortBatch& sb, bool iota_vals, int begin_bit, 
     attr_set = true;
   }
   const uint64_t ntiles = sort_ntiles(n_max);
-  for (int i = 0; i < sb.V; ++i) {
-    if (sb.s[i].n_host == 0) continue;
-    const size_t zero_bytes =
-        ((size_t)RS_MAX_PASSES * RS_BINS + 32 + (size_t)plan.npasses * sort_ntiles(sb.s[i].n_host) * RS_BINS) * 4;
-    cudaMemsetAsync(sb.s[i].temp, 0, zero_bytes, s);
+  if (!temp_is_zero) {
+    radix_zero_kernel<<<dim3(64, sb.V), 256, 0, s>>>(sb, plan.npasses);
+    count_launch();
   }
   const int hist_blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>((n_max + 256 * 16 - 1) / (256 * 16),
                                                                          (uint64_t)NUM_SM * 8 / sb.V));
