@@ -47,6 +47,13 @@ typedef struct tgr_params {
   int32_t extras;       /* 1: also produce depth/alpha images (new) */
   int32_t accumulate;   /* backward: 1 = add into the output gradient tensors instead of overwriting them
                            (multi-view gradient accumulation without an extra pass; new) */
+  int32_t depth_key_bits; /* forward: number of low bits of the fp32 depth keys the depth sort has to look at, 0 = all 32.
+                           The visible depths of an avatar share sign, exponent and often leading mantissa bits; words
+                           [4], [5] of the header mirror (OR / AND over the visible keys) tell how many bits differ, and a
+                           caller that renders the same scene again passes that (+ slack) to save a radix pass.  Too few
+                           bits give a wrong order, never a fault: check the mirror after the call (the Python operator
+                           does and re-renders) */
+  int32_t reserved_;
   /* camera (device pointers) */
   const float* background; /* [3] */
   const float* viewmatrix; /* [16] */
@@ -83,8 +90,9 @@ typedef struct tgr_params {
   float* dL_dsh;        /* [P,M,3] or NULL when M == 0 */
   float* dL_dscales;    /* [P,3] or NULL */
   float* dL_drotations; /* [P,4] or NULL */
-  /* pinned host mirror of the geom header, FOUR words {num_rendered, overflow, num_visible, prefilter_violation},
-   * written asynchronously by tgr_forward_preprocess (may be NULL) */
+  /* pinned host mirror of the geom header, EIGHT words {num_rendered, overflow, num_visible, prefilter_violation,
+   * OR of the visible depth keys, AND of the visible depth keys, 0, 0}, written asynchronously by
+   * tgr_forward_preprocess (may be NULL) */
   uint32_t* host_num_rendered;
 } tgr_params;
 

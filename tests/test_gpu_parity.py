@@ -515,7 +515,7 @@ def test_multiview_capacity_hints_sync_free_path_and_overflow_fallback():
             assert rel_l2(a, b) <= 2e-6
         # a hint far too small: the kernels flag the overflow on the device, the batch is redone synchronously
         for k in list(mv._capacity["hints"]):
-            mv._capacity["hints"][k] = 1
+            mv._capacity["hints"][k] = (1, mv._capacity["hints"][k][1])
         margin = mv._capacity["margin"]
         mv._capacity["margin"] = 0
         try:
@@ -532,5 +532,50 @@ def test_multiview_capacity_hints_sync_free_path_and_overflow_fallback():
         st3 = mv.c_rasterize_views(*args, extras=True)[0]
         st4 = mv.c_rasterize_views(*args, extras=True)[0]
         assert st3.caps == st3.counts and st4.caps == st4.counts
+    finally:
+        mv.set_capacity_hints(True)
+
+
+@pytest.mark.gpu
+def test_depth_sort_key_bit_hints_and_their_fallback():
+    """The depth sort only looks at the low bits in which the visible depth keys differ (OR / AND of the keys in the
+    header): calls that follow a first one of the same scene sort hint + 1 bits.  A hint that is too small gives a
+    wrong order on the device; the host notices it from the header mirror and renders again — same bits as a full
+    32-bit sort, single-view operator and multi-view batch."""
+    from youreditableavatar_b200 import multiview as mv, rasterizer as rz
+    from youreditableavatar_b200.parallel import settings_from_cam
+    _, inp, cam = small_scene(20000, 48, 256, 1)
+    P = inp["means3D"].shape[0]
+    dev = torch.cuda.current_device()
+    rz._depth_bits_hint.pop((dev, P), None)
+    full = ours_forward(inp, cam, 3)                      # no hint yet: all 32 bits
+    need = rz._depth_bits_hint[(dev, P)]
+    assert 9 <= need <= 30                                # an avatar at distance 3: exponent and sign are shared
+    hinted = ours_forward(inp, cam, 3)                    # need + 1 bits
+    k_full, i_full, r_full = export_binning(P, 256, 256, full)
+    k_hint, i_hint, r_hint = export_binning(P, 256, 256, hinted)
+    assert torch.equal(k_full, k_hint) and torch.equal(i_full, i_hint) and torch.equal(r_full, r_hint)
+    assert torch.equal(full[1], hinted[1])
+    rz._depth_bits_hint[(dev, P)] = 4                     # far too few bits: must be noticed and redone
+    redo = ours_forward(inp, cam, 3)
+    k_redo, i_redo, _ = export_binning(P, 256, 256, redo)
+    assert torch.equal(k_full, k_redo) and torch.equal(i_full, i_redo) and torch.equal(full[1], redo[1])
+    assert rz._depth_bits_hint[(dev, P)] == need
+    # batch path
+    V = 3
+    cams = [to_dev(scene.orbit_camera(v, V, 256, 256, device="cpu"), "cuda") for v in range(V)]
+    sets = [settings_from_cam(c, 3) for c in cams]
+    e = torch.Tensor([])
+    args = (sets, inp["means3D"], e, inp["opacities"], inp["scales"], inp["rotations"], e, inp["shs"])
+    mv.set_capacity_hints(True)
+    try:
+        st0, color0, radii0 = mv.c_rasterize_views(*args)
+        for k in list(mv._capacity["hints"]):
+            mv._capacity["hints"][k] = (mv._capacity["hints"][k][0], 3)
+        st1, color1, radii1 = mv.c_rasterize_views(*args)
+        assert st1.caps == st1.counts == st0.counts        # redone the synchronous way
+        assert torch.equal(color1, color0) and torch.equal(radii1, radii0)
+        st2, color2, _ = mv.c_rasterize_views(*args)       # and the hint is healthy again
+        assert min(st2.caps) > max(st2.counts) and torch.equal(color2, color0)
     finally:
         mv.set_capacity_hints(True)

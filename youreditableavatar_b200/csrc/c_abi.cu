@@ -143,7 +143,15 @@ static int check_same_gaussians(const tgr_params* a, const tgr_params* b) {
 
 // (depth bits, id) order of the Gaussians of every view: positive floats compare like their bit patterns (bit 31
 // is 0).  One batched launch sequence for all views.
-static int depth_sort_views(const tgr_params* views, int32_t n, cudaStream_t s) {
+static int depth_bits_of(const tgr_params& p) { return (p.depth_key_bits > 0 && p.depth_key_bits < 32) ? p.depth_key_bits : 32; }
+// where the (depth, id) order of the Gaussians ends up: an odd number of radix passes leaves it in the alternate buffer
+static bool depth_order_in_alt(const tgr_params& p) { return (make_sort_plan(0, depth_bits_of(p)).npasses & 1) != 0; }
+
+static int depth_sort_views(const tgr_params* views, int32_t n, cudaStream_t s, bool temp_is_zero) {
+  int bits = 1;
+  for (int32_t v = 0; v < n; ++v) bits = std::max(bits, depth_bits_of(views[v]));
+  for (int32_t v = 0; v < n; ++v)
+    if (depth_bits_of(views[v]) != bits) { set_error("batch: all views must use the same depth_key_bits"); return 1; }
   for (int32_t v0 = 0; v0 < n; v0 += MAX_BATCH) {
     SortBatch sb{};
     sb.V = std::min<int32_t>(MAX_BATCH, n - v0);
@@ -154,9 +162,9 @@ static int depth_sort_views(const tgr_params* views, int32_t n, cudaStream_t s) 
     }
     bool in_b = false;
     prof_begin(TGR_STAGE_DEPTH_SORT, s);
-    if (int rc = launch_sort_pairs_batch(sb, true, 0, 32, s, &in_b, /*temp_is_zero=*/true)) return rc;   // preprocess_kernel
+    if (int rc = launch_sort_pairs_batch(sb, true, 0, bits, s, &in_b, temp_is_zero)) return rc;   // cleared by preprocess_kernel
     prof_end(TGR_STAGE_DEPTH_SORT, s);
-    if (in_b) { set_error("internal: depth sort must end in buffer A"); return 3; }
+    if (in_b != depth_order_in_alt(views[v0])) { set_error("internal: depth order is not where the binning expects it"); return 3; }
   }
   return 0;
 }
@@ -170,7 +178,7 @@ static RenderView make_render_view(const tgr_params& p, uint64_t cap, bool tile_
   r.T = (uint32_t)((p.W + TILE - 1) / TILE) * ((p.H + TILE - 1) / TILE);
   r.cap = (uint32_t)std::min<uint64_t>(cap, 0xffffffffull);
   r.units_cap = (uint32_t)std::min<uint64_t>(b.units_cap, 0x7fffffffull);
-  r.header = g.header; r.order = g.order; r.rect = g.rect;
+  r.header = g.header; r.order = depth_order_in_alt(p) ? g.val_alt : g.order; r.rect = g.rect;
   r.xy_ext = g.xy_ext; r.conic_opacity = g.conic_opacity; r.rgb_depth = g.rgb_depth; r.scan_state = g.scan_state;
   r.key_a = b.key_a; r.val_a = b.val_a;
   r.tile_sort_temp = b.sort_temp;
@@ -254,7 +262,7 @@ struct HeaderBatch {
 };
 __global__ void header_init_kernel(const __grid_constant__ HeaderBatch hb) {
   const int v = threadIdx.x >> 5, w = threadIdx.x & 31;
-  if (v < hb.V) reinterpret_cast<uint32_t*>(hb.h[v])[w] = 0u;   // 128-byte header = 32 words
+  if (v < hb.V) reinterpret_cast<uint32_t*>(hb.h[v])[w] = (w == 5) ? 0xffffffffu : 0u;   // 128-byte header = 32 words; [5] = key_and
 }
 
 // One preprocess launch per chunk of <= TGR_MAX_BATCH views; instance counts go to each view's pinned slot.
@@ -266,7 +274,7 @@ static int preprocess_views(const tgr_params* views, int32_t n, const tgr_bindin
   const tgr_params* p0 = &views[0];
   if (p0->P == 0) {
     for (int32_t v = 0; v < n; ++v)
-      if (views[v].host_num_rendered) for (int k = 0; k < 4; ++k) views[v].host_num_rendered[k] = 0;
+      if (views[v].host_num_rendered) for (int k = 0; k < 8; ++k) views[v].host_num_rendered[k] = 0;
     return 0;
   }
   if (int rc = check_gaussians(p0, bind)) return rc;
@@ -292,8 +300,8 @@ static int preprocess_views(const tgr_params* views, int32_t n, const tgr_bindin
   for (int32_t v = 0; v < n; ++v) {
     if (!views[v].host_num_rendered) continue;
     GeomView g = carve_geom(views[v].geom_buffer, p0->P);
-    // {num_rendered, overflow (still 0 here), num_visible, prefilter_violation}
-    cudaMemcpyAsync(views[v].host_num_rendered, &g.header->num_rendered, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s);
+    // {num_rendered, overflow (still 0 here), num_visible, prefilter_violation, key_or, key_and, -, -}
+    cudaMemcpyAsync(views[v].host_num_rendered, &g.header->num_rendered, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s);
     any = true;
   }
   if (any) cudaEventRecord(count_event(), s);
@@ -305,7 +313,7 @@ int tgr_forward_preprocess(const tgr_params* p, const tgr_binding* bind, void* s
   if (!p) { set_error("null params"); return 1; }
   if (int rc = preprocess_views(p, 1, bind, s)) return rc;
   if (p->P == 0) return 0;
-  if (int rc = depth_sort_views(p, 1, s)) return rc;
+  if (int rc = depth_sort_views(p, 1, s, true)) return rc;
   return check_launch("forward_preprocess", p->debug != 0, s);
 }
 
@@ -320,7 +328,7 @@ int tgr_forward_depth_sort(const tgr_params* p, void* stream) {
   if (int rc = validate(p, false, 0)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (p->P == 0) return 0;
-  if (int rc = depth_sort_views(p, 1, s)) return rc;
+  if (int rc = depth_sort_views(p, 1, s, true)) return rc;    // temp cleared by the preprocess kernel
   return check_launch("forward_depth_sort", p->debug != 0, s);
 }
 
@@ -351,7 +359,7 @@ int tgr_forward_render_batch(const tgr_params* views, const uint64_t* caps, int3
   for (int32_t v = 0; v < n_views; ++v)
     if (int rc = validate(&views[v], true, caps[v])) return rc;
   if (views[0].P > 0)
-    if (int rc = depth_sort_views(views, n_views, s)) return rc;
+    if (int rc = depth_sort_views(views, n_views, s, true)) return rc;
   if (int rc = for_each_group(views, caps, n_views,
                               [&](const tgr_params* g, const uint64_t* c, int32_t n) { return render_group(g, c, n, s); }))
     return rc;

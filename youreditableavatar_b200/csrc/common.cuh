@@ -71,7 +71,9 @@ struct GeomHeader {        // 128 bytes
   uint32_t num_visible;    // Gaussians with radius > 0
   uint32_t prefilter_violation;  // set when tgr_params.prefiltered != 0 and a Gaussian failed the near-plane test: the
                                  // reference prints and __trap()s there (auxiliary.h:154-160); here the host raises
-  uint32_t pad[28];
+  uint32_t key_or;         // OR / AND over the depth keys of the visible Gaussians: the bits in which they differ are
+  uint32_t key_and;        // all the depth sort has to look at (initialised to 0 / 0xffffffff by header_init_kernel)
+  uint32_t pad[26];
 };
 
 struct GeomView {

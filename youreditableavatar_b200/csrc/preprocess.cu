@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const tgr_params p, con
                                                          const __grid_constant__ ViewBatch vb) {
   extern __shared__ float s_rows[];
   __shared__ float s_cam[MAX_BATCH][CAM_FLOATS];
-  __shared__ uint32_t s_cnt[MAX_BATCH][2];
+  __shared__ uint32_t s_cnt[MAX_BATCH][4];   // instances, visible Gaussians, OR / AND of the visible depth keys
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int P = p.P;
   const int V = vb.V;
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const tgr_params p, con
     else if (k < 35) x = vb.v[v].campos[k - 32];
     s_cam[v][k] = x;
   }
-  if (threadIdx.x < 2 * MAX_BATCH) s_cnt[threadIdx.x >> 1][threadIdx.x & 1] = 0;
+  if (threadIdx.x < 4 * MAX_BATCH) s_cnt[threadIdx.x >> 2][threadIdx.x & 3] = (threadIdx.x & 3) == 3 ? 0xffffffffu : 0u;
   // on the side: clear the temp area of the depth sort that follows (histograms, tickets, look-back flags); block b
   // takes slice b — this replaces one memset node per view
   for (int v = 0; v < V; ++v) {
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const tgr_params p, con
     const ViewDesc& vd = vb.v[v];
     const float* view = s_cam[v];
     const float* proj = s_cam[v] + 16;
-    uint32_t my_tiles = 0, my_vis = 0;
+    uint32_t my_tiles = 0, my_vis = 0, my_key = 0;
     if (live) {
       int radius_out = 0;
       ushort4 rect_out = make_ushort4(0, 0, 0, 0);
@@ -292,6 +292,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const tgr_params p, con
             key_out = __float_as_uint(p_view.z);
             my_tiles = ntiles;
             my_vis = 1;
+            my_key = key_out;
           }
         }
       }
@@ -302,16 +303,22 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const tgr_params p, con
     // instance count of this view: warp reduce -> shared atomics -> one global atomic per block (below)
     const uint32_t wt = __reduce_add_sync(0xffffffffu, my_tiles);
     const uint32_t wv = __reduce_add_sync(0xffffffffu, my_vis);
+    const uint32_t wo = __reduce_or_sync(0xffffffffu, my_key);
+    const uint32_t wa = __reduce_and_sync(0xffffffffu, my_vis ? my_key : 0xffffffffu);
     if ((threadIdx.x & 31) == 0) {
       if (wt) atomicAdd(&s_cnt[v][0], wt);
-      if (wv) atomicAdd(&s_cnt[v][1], wv);
+      if (wv) { atomicAdd(&s_cnt[v][1], wv); atomicOr(&s_cnt[v][2], wo); atomicAnd(&s_cnt[v][3], wa); }
     }
   }
   __syncthreads();
   if (threadIdx.x < V) {
     const uint32_t t = s_cnt[threadIdx.x][0], n = s_cnt[threadIdx.x][1];
     if (t) atomicAdd(&vb.v[threadIdx.x].header->num_rendered, t);
-    if (n) atomicAdd(&vb.v[threadIdx.x].header->num_visible, n);
+    if (n) {
+      atomicAdd(&vb.v[threadIdx.x].header->num_visible, n);
+      atomicOr(&vb.v[threadIdx.x].header->key_or, s_cnt[threadIdx.x][2]);
+      atomicAnd(&vb.v[threadIdx.x].header->key_and, s_cnt[threadIdx.x][3]);
+    }
   }
 }
 

@@ -40,22 +40,23 @@ _pinned_counts = {}
 
 
 def _count_slots(device: torch.device, n: int) -> torch.Tensor:
-    """Pinned 4-word slots {num_rendered, overflow, num_visible, prefilter_violation} for the asynchronous header
-    read-back of a batch (double-buffered)."""
+    """Pinned 8-word slots {num_rendered, overflow, num_visible, prefilter_violation, key_or, key_and, -, -} for the
+    asynchronous header read-back of a batch (double-buffered)."""
     key = device.index if device.index is not None else torch.cuda.current_device()
     ent = _pinned_counts.get(key)
     if ent is None or ent[0].shape[1] < n:
-        ent = [torch.zeros(2, max(n, 64), 4, dtype=torch.int32).pin_memory(), 0]
+        ent = [torch.zeros(2, max(n, 64), 8, dtype=torch.int32).pin_memory(), 0]
         _pinned_counts[key] = ent
     ent[1] ^= 1
     return ent[0][ent[1], :n]
 
 
-def _read_counts(slots: torch.Tensor) -> List[int]:
+def _read_counts(slots: torch.Tensor):
+    """-> (instance counts per view, depth-key bits the batch's depth sorts have to look at)."""
     rows = slots.tolist()
     for r in rows:
         rz.check_prefilter(r)
-    return [int(r[0]) for r in rows]
+    return [int(r[0]) for r in rows], max(rz.depth_bits_needed(r) for r in rows)
 
 
 class ViewBatchState:
@@ -178,11 +179,14 @@ def c_rasterize_views(settings: Sequence, means3D, colors, opacity, scales, rota
         if hint is None:
             # the one host<->device sync of the batch (the reference has one per view, rasterizer_impl.cu:281)
             check(L.tgr_wait_num_rendered(), "tgr_wait_num_rendered")
-            counts = _read_counts(slots)
+            counts, depth_bits = _read_counts(slots)
             cap_list = counts
         else:
             counts = None
-            cap_list = [int(hint * _capacity["slack"]) + _capacity["margin"]] * V
+            cap_list = [int(hint[0] * _capacity["slack"]) + _capacity["margin"]] * V
+            depth_bits = min(32, hint[1] + 1)       # one bit of slack over what the previous batch of this shape needed
+        for v in range(V):
+            params[v].depth_key_bits = depth_bits
 
         binnings = []
         view_events = []
@@ -196,13 +200,15 @@ def c_rasterize_views(settings: Sequence, means3D, colors, opacity, scales, rota
             if counts is None:
                 # launched ahead of the counts: read them now (the GPU is already sorting / blending) and verify
                 check(L.tgr_wait_num_rendered(), "tgr_wait_num_rendered")
-                counts = _read_counts(slots)
-                if max(counts) > cap_list[0]:
-                    _capacity["hints"].pop(hkey, None)   # outgrown: redo this batch with exactly sized buffers
+                counts, need_bits = _read_counts(slots)
+                if max(counts) > cap_list[0] or need_bits > depth_bits:
+                    _capacity["hints"].pop(hkey, None)   # outgrown: redo this batch with exactly sized buffers / sort bits
                     return c_rasterize_views(settings, means3D, colors, opacity, scales, rotations, cov3D_precomp, sh,
                                              extras=extras, n_streams=n_streams, binding=binding, _use_hint=False)
+            else:
+                need_bits = depth_bits
             if _capacity["enabled"]:
-                _capacity["hints"][hkey] = max(counts)
+                _capacity["hints"][hkey] = (max(counts), need_bits)
             ev = torch.cuda.Event()
             ev.record(main)
             view_events = [ev] * V

@@ -31,15 +31,28 @@ PREFILTER_MESSAGE = "Point is filtered although prefiltered is set. This shouldn
 
 
 def _pinned_slot(device: torch.device) -> torch.Tensor:
-    """Ring of pinned 4-word slots per device for the asynchronous read-back of the geom header
-    {num_rendered, overflow, num_visible, prefilter_violation}."""
+    """Ring of pinned 8-word slots per device for the asynchronous read-back of the geom header
+    {num_rendered, overflow, num_visible, prefilter_violation, key_or, key_and, -, -}."""
     key = device.index if device.index is not None else torch.cuda.current_device()
     ent = _pinned.get(key)
     if ent is None:
-        ent = [torch.zeros(64, 4, dtype=torch.int32).pin_memory(), 0]
+        ent = [torch.zeros(64, 8, dtype=torch.int32).pin_memory(), 0]
         _pinned[key] = ent
     ent[1] = (ent[1] + 1) % 64
     return ent[0][ent[1]]
+
+
+def depth_bits_needed(header_words) -> int:
+    """Number of low bits in which the fp32 depth keys of the visible Gaussians differ (words [4], [5] of the header
+    mirror are their OR / AND): all the depth sort has to look at."""
+    diff = (int(header_words[4]) ^ int(header_words[5])) & 0xffffffff
+    return max(1, diff.bit_length())
+
+
+# depth-key bits of the previous call per (device, P): the depth sort of a single-view call is launched before the
+# header comes back, so it sorts as many bits (+ 1 of slack) as the last view of the same scene needed; should this view
+# need more, the forward starts over with the exact number before anything consumes the wrong order
+_depth_bits_hint = {}
 
 
 def check_prefilter(header_words) -> None:
@@ -161,6 +174,8 @@ def c_rasterize_gaussians(bg, means3D, colors, opacity, scales, rotations, scale
         p.host_num_rendered = slot.data_ptr()
         stream = _stream(device)
         bptr = C.byref(binding) if binding is not None else None
+        hkey = (device.index if device.index is not None else torch.cuda.current_device(), P)
+        p.depth_key_bits = min(32, _depth_bits_hint.get(hkey, 31) + 1)
 
         check(L.tgr_forward_preprocess(C.byref(p), bptr, stream), "tgr_forward_preprocess")
         # the one host<->device sync of a forward (the reference has the same one, rasterizer_impl.cu:281);
@@ -168,6 +183,14 @@ def c_rasterize_gaussians(bg, means3D, colors, opacity, scales, rotations, scale
         check(L.tgr_wait_num_rendered(), "tgr_wait_num_rendered")
         R = int(slot[0])
         check_prefilter(slot)
+        need = depth_bits_needed(slot)
+        _depth_bits_hint[hkey] = need
+        if need > p.depth_key_bits:        # this view spans more depth bits than the hint covered: the order is wrong.
+            # Start over (the hint now holds what this view needs); rare — the camera would have to move from a view
+            # where all visible depths share their leading bits to one where they do not
+            return c_rasterize_gaussians(bg, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
+                                         viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree,
+                                         campos, prefiltered, debug, extras=extras, binding=binding)
         binning = torch.empty(L.tgr_binning_bytes(P, R, W, H), **u8)
         p.binning_buffer, p.binning_bytes = binning.data_ptr(), binning.numel()
         check(L.tgr_forward_render(C.byref(p), R, stream), "tgr_forward_render")
