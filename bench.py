@@ -50,14 +50,15 @@ def parse():
     ap.add_argument("--streams", type=int, default=0,
                     help="0 (default): fused schedule, every per-view stage is one launch for the whole batch; "
                          "n >= 1: per-view launches round-robin on n CUDA streams")
-    ap.add_argument("--comm", default="auto", choices=["auto", "nvls", "nccl", "rows", "sh"],
+    ap.add_argument("--comm", default="auto", choices=["auto", "nvls", "nvls_sh", "nccl", "rows", "sh"],
                     help="N > 1, gradient exchange: nvls = own in-switch all-reduce kernel on a symmetric-memory buffer, "
-                         "nccl = one NCCL all-reduce, auto (default) = nccl at N = 2 and nvls from N = 4, "
-                         "rows / sh = NCCL per Gaussian range overlapped with the backward")
+                         "nvls_sh = the same kernel per range of Gaussians (SH rows) on a side stream, overlapped with the "
+                         "backward's per-Gaussian kernel, nccl = one NCCL all-reduce, auto (default) = nccl at N = 2 and "
+                         "nvls_sh from N = 4, rows / sh = NCCL per Gaussian range overlapped with the backward")
     ap.add_argument("--legs", default="C1,C2,C5",
                     help="other BASELINE.json configs measured compactly after the headline config (N = 1: all listed; "
                          "N > 1: only C5, the config BASELINE.json quotes at 8 GPUs); empty string = none")
-    ap.add_argument("--comm-chunks", type=int, default=4, help="Gaussian ranges for --comm rows / sh")
+    ap.add_argument("--comm-chunks", type=int, default=2, help="Gaussian ranges for --comm rows / sh")
     ap.add_argument("--no-train-step", action="store_true",
                     help="skip the train_step leg (render + image loss + backward + Adam, SURVEY §8 f1-f3)")
     ap.add_argument("--per-view-api", action="store_true",
@@ -331,7 +332,7 @@ class OursRunner:
         # all-reduce kernel (falls back to NCCL without multicast support); "nccl": one NCCL all-reduce;
         # "rows" / "sh": NCCL all-reduces of Gaussian ranges overlapped with the backward
         self.bucket = bucket if bucket is not None else \
-            (SymmGradBucket if comm == "nvls" else GradBucket)(P, 16, "cuda", names=GradBucket.TRAINING)
+            (SymmGradBucket if comm in ("nvls", "nvls_sh") else GradBucket)(P, 16, "cuda", names=GradBucket.TRAINING)
         self.loss_ws = None   # workspace of the image-loss kernels (e2e leg), allocated on first use
 
     def step(self, cams, ups, world, feeder=None):
@@ -362,9 +363,10 @@ class OursRunner:
             box["loss"] = loss
             return dLc, dLd, dLa
 
-        if self.comm in ("rows", "sh"):   # NCCL all-reduces issued range by range from inside the backward
+        if self.comm in ("rows", "sh", "nvls_sh"):   # all-reduces issued range by range from inside the backward
             render_views_fwd_bwd(self.act, cams, 3, upstream, self.bucket, extras=self.extras, n_streams=self.n_streams,
-                                 all_reduce=True, comm_chunks=self.comm_chunks, comm_mode=self.comm)
+                                 all_reduce=True, comm_chunks=self.comm_chunks,
+                                 comm_mode="sh" if self.comm == "nvls_sh" else self.comm)
         else:
             render_views_fwd_bwd(self.act, cams, 3, upstream, self.bucket, extras=self.extras, n_streams=self.n_streams)
             self.bucket.all_reduce()
@@ -457,8 +459,14 @@ def timed(runner, cams, ups, world, steps, warmup, feeder=None):
     barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    from youreditableavatar_b200 import multiview as _mv
+    t0, w0 = time.perf_counter(), _mv.host_wait_seconds
     for _ in range(steps):
         runner.step(cams, ups, world, feeder)
+    # host time to issue a step, and the part of it that was CPU work (the rest: blocked on the instance counts of the
+    # step just issued, i.e. waiting for the GPU to catch up)
+    timed.host_ms_per_step = (time.perf_counter() - t0) * 1e3 / steps
+    timed.host_cpu_ms_per_step = timed.host_ms_per_step - (_mv.host_wait_seconds - w0) * 1e3 / steps
     if feeder is not None:
         feeder.drain()                       # the last step's result has reached the host
     e1.record()
@@ -689,7 +697,7 @@ def pick_comm(args, world):
     kernel on 236 MB), this library's in-switch all-reduce kernel from N = 4."""
     if args.comm != "auto":
         return args.comm
-    return "nvls" if world >= 4 else "nccl"
+    return "nvls_sh" if world >= 4 else "nccl"
 
 
 def allreduce_check(bucket, world):
@@ -712,6 +720,23 @@ def allreduce_check(bucket, world):
     allsame = bool(flag[0].item() == 1.0)
     return "bit-identical to NCCL all_reduce (%d floats, every rank)" % bucket.flat.numel() if allsame else \
         "MISMATCH vs NCCL: max-abs %.3g on rank 0" % worst
+
+
+def exchange_check(runner, P, act, cams, ups, world):
+    """Outside the timed region: one whole step through the runner's exchange (also the range-wise, overlapped one)
+    against the same step's local gradients summed with one NCCL all_reduce.  Two backward runs differ in the order of
+    their floating-point reductions, so this is a relative-L2 figure, not a bit comparison."""
+    import torch.distributed as dist
+    from youreditableavatar_b200.parallel import GradBucket, render_views_fwd_bwd
+    ref = GradBucket(P, 16, "cuda", names=GradBucket.TRAINING)
+    render_views_fwd_bwd(act, cams, 3, lambda c, d, a: ups, ref, extras=True)
+    dist.all_reduce(ref.flat)
+    runner.step(cams, ups, world)
+    torch.cuda.synchronize()
+    rel = float((runner.bucket.flat.double() - ref.flat.double()).norm() / ref.flat.double().norm())
+    t = torch.tensor([rel], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return "whole step vs local gradients + NCCL all_reduce: rel-L2 %.2e (max over ranks)" % float(t.item())
 
 
 def measure(cfg, V, args, world, rank, local, steps, warmup, full):
@@ -754,7 +779,9 @@ def measure(cfg, V, args, world, rank, local, steps, warmup, full):
                  for i, n in enumerate(_lib.STAGE_NAMES)}
         L.tgr_profile_enable(0)
     views = V * world * steps
+    host_ms = getattr(timed, "host_ms_per_step", None)
     out = {"P": P, "res": res, "views_per_step_per_gpu": V, "value": views / (ms / 1000.0), "ms_per_step": ms / steps,
+           "host_issue_ms_per_step": host_ms, "host_cpu_ms_per_step": getattr(timed, "host_cpu_ms_per_step", None),
            "gpu_launches": None if launches is None else int(launches), "clocks": clocks, "stages": stage}
 
     host_cams = [cam_to_host(c) for c in cams]
@@ -762,7 +789,9 @@ def measure(cfg, V, args, world, rank, local, steps, warmup, full):
     ms_e2e = timed(runner, cams, ups, world, steps, max(warmup, 3), feeder)
     cam_bytes = sum(v.numel() * 4 for v in host_cams[0].values() if isinstance(v, torch.Tensor))
     out["e2e"] = {"value": views / (ms_e2e / 1000.0), "unit": UNIT, "h2d_bytes_per_step": V * cam_bytes + targets_host.numel(),
-                  "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / steps}
+                  "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / steps,
+                  "host_issue_ms_per_step": getattr(timed, "host_ms_per_step", None),
+                  "host_cpu_ms_per_step": getattr(timed, "host_cpu_ms_per_step", None)}
     if batched:
         pv = OursPerViewRunner(P, res, act, bucket=runner.bucket)
         k = max(2, steps // 4)
@@ -771,8 +800,11 @@ def measure(cfg, V, args, world, rank, local, steps, warmup, full):
                                "note": "same workload through GaussianRasterizer-style single-view calls in a loop, one stream"}
         if world > 1 and full:
             out["allreduce_check"] = allreduce_check(runner.bucket, world)
+            out["exchange_check"] = exchange_check(runner, P, act, cams, ups, world)
         out["comm"] = ("in-switch NVLS all-reduce kernel of this library" if getattr(runner.bucket, "nvls", False) else
-                       "NCCL" if comm in ("nvls", "nccl") else "NCCL, %d ranges overlapped" % args.comm_chunks) if world > 1 else None
+                       "NCCL" if comm in ("nvls", "nvls_sh", "nccl") else "NCCL, %d ranges overlapped" % args.comm_chunks) if world > 1 else None
+        if out["comm"] and comm == "nvls_sh" and getattr(runner.bucket, "nvls", False):
+            out["comm"] += ", SH rows in %d ranges on a side stream overlapped with the backward's per-Gaussian kernel" % args.comm_chunks
     out["_keep"] = (P, res, act, cams, targets_host, runner)
     return out
 
@@ -876,6 +908,7 @@ def main():
                      ("fused per-stage launches" if args.streams == 0 else "%d streams" % args.streams)) if batched
                     else "single-view calls in a loop"),
             "e2e": m["e2e"], "gpu_launches": m["gpu_launches"], "clocks": m["clocks"],
+            "host_issue_ms_per_step": m["host_issue_ms_per_step"], "host_cpu_ms_per_step": m["host_cpu_ms_per_step"],
         }
         out["e2e"]["note"] = ("both arms: cameras + uint8 targets from pinned host memory, colour MSE (+ depth / coverage terms "
                               "where rendered) formed on the device, loss read back every step.  Ours evaluates the MSE and "
@@ -886,6 +919,7 @@ def main():
             out["config"]["parallelism"] += " (%s)" % m["comm"]
         if m.get("allreduce_check"):
             out["allreduce_check"] = m["allreduce_check"]
+            out["exchange_check"] = m.get("exchange_check")
     if ours and rank == 0:
         from youreditableavatar_b200 import multiview as mv
         from youreditableavatar_b200.parallel import settings_from_cam

@@ -209,6 +209,10 @@ int tgr_dist2(int32_t P, const float* points, float* mean_dist2, void* workspace
  * (multimem.st).  `multicast_ptr` is the multicast address of the buffer's first element, n_floats a multiple
  * of 4.  The caller brackets the call with cross-rank barriers on the same stream. */
 int tgr_multimem_allreduce_f32(void* multicast_ptr, uint64_t n_floats, int32_t rank, int32_t world, void* stream);
+/* Same, with the grid capped at max_ctas CTAs (0 = no cap): for slices exchanged on a side stream while the backward
+ * still computes the next range of Gaussians (tgr_backward_preprocess_batch with gaussian_first / gaussian_count). */
+int tgr_multimem_allreduce_f32_capped(void* multicast_ptr, uint64_t n_floats, int32_t rank, int32_t world,
+                                      int32_t max_ctas, void* stream);
 
 /* ---- per-stage device timing (CUDA events recorded on the launching stream) ----
  * tgr_profile_enable(1) makes every subsequent stage launch bracket itself with events;

@@ -78,6 +78,7 @@ SYMBOLS = {
     "tgr_backward_preprocess_batch": (C.c_int, [C.POINTER(TgrParams), C.POINTER(C.c_uint64), C.c_int32,
                                                 C.POINTER(TgrBinding), C.c_int32, C.c_int32, C.c_void_p]),
     "tgr_multimem_allreduce_f32": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p]),
+    "tgr_multimem_allreduce_f32_capped": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "tgr_read_header": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32 * 4), C.c_void_p]),
     "tgr_mark_visible": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tgr_knn_bytes": (C.c_uint64, [C.c_int32]),

@@ -46,7 +46,14 @@ __global__ void __launch_bounds__(256) multimem_allreduce_f32_kernel(float* __re
 
 }  // namespace tgr
 
+extern "C" int tgr_multimem_allreduce_f32_capped(void* multicast_ptr, uint64_t n_floats, int32_t rank, int32_t world,
+                                                 int32_t max_ctas, void* stream);
 extern "C" int tgr_multimem_allreduce_f32(void* multicast_ptr, uint64_t n_floats, int32_t rank, int32_t world, void* stream) {
+  return tgr_multimem_allreduce_f32_capped(multicast_ptr, n_floats, rank, world, 0, stream);
+}
+
+extern "C" int tgr_multimem_allreduce_f32_capped(void* multicast_ptr, uint64_t n_floats, int32_t rank, int32_t world,
+                                                 int32_t max_ctas, void* stream) {
   using namespace tgr;
   if (!multicast_ptr || world <= 0 || rank < 0 || rank >= world) { set_error("multimem_allreduce: bad arguments"); return 1; }
   if ((n_floats & 3) != 0 || (reinterpret_cast<uintptr_t>(multicast_ptr) & 15) != 0) {
@@ -59,7 +66,10 @@ extern "C" int tgr_multimem_allreduce_f32(void* multicast_ptr, uint64_t n_floats
   const uint64_t per = (n4 + world - 1) / world;
   // many small threads beat few unrolled ones here (N = 8, 236 MB: 0.56 ms with SMs x 8 CTAs of 256 threads,
   // 0.64 ms with an eighth of them and 8 reductions in flight per thread; NCCL: 0.64 ms)
-  const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((per + 255) / 256, (uint64_t)NUM_SM * 8));
+  // max_ctas > 0 caps the grid: a slice exchanged WHILE the backward still computes the next range of Gaussians must
+  // not take the SMs away from it (the in-switch round trip is latency, not SM work: MM_UNROLL requests per thread)
+  const uint64_t cap = max_ctas > 0 ? (uint64_t)max_ctas : (uint64_t)NUM_SM * 8;
+  const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((per + 255) / 256, cap));
   multimem_allreduce_f32_kernel<<<blocks, 256, 0, s>>>(static_cast<float*>(multicast_ptr), n4, rank, world);
   count_launch();
   return check_launch("multimem_allreduce", false, s);

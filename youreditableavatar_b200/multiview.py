@@ -88,6 +88,15 @@ def _align(x: int, a: int = 256) -> int:
 # GPU already renders) and, should a view have outgrown its capacity (the kernels detect that on the device and
 # render nothing), the batch is redone the synchronous way.
 _capacity = {"enabled": True, "slack": 1.2, "margin": 65536, "hints": {}}
+host_wait_seconds = 0.0   # time the host spent blocked in tgr_wait_num_rendered (diagnostics: issue time minus this is CPU work)
+
+
+def _wait_counts(L):
+    global host_wait_seconds
+    import time
+    t0 = time.perf_counter()
+    check(L.tgr_wait_num_rendered(), "tgr_wait_num_rendered")
+    host_wait_seconds += time.perf_counter() - t0
 
 
 def set_capacity_hints(enabled: bool = True, slack: float = 1.2) -> None:
@@ -178,7 +187,7 @@ def c_rasterize_views(settings: Sequence, means3D, colors, opacity, scales, rota
         hint = _capacity["hints"].get(hkey) if (_capacity["enabled"] and _use_hint and S == 0) else None
         if hint is None:
             # the one host<->device sync of the batch (the reference has one per view, rasterizer_impl.cu:281)
-            check(L.tgr_wait_num_rendered(), "tgr_wait_num_rendered")
+            _wait_counts(L)
             counts, depth_bits = _read_counts(slots)
             cap_list = counts
         else:
@@ -199,7 +208,7 @@ def c_rasterize_views(settings: Sequence, means3D, colors, opacity, scales, rota
             check(L.tgr_forward_render_batch(params, caps, V, main.cuda_stream), "tgr_forward_render_batch")
             if counts is None:
                 # launched ahead of the counts: read them now (the GPU is already sorting / blending) and verify
-                check(L.tgr_wait_num_rendered(), "tgr_wait_num_rendered")
+                _wait_counts(L)
                 counts, need_bits = _read_counts(slots)
                 if max(counts) > cap_list[0] or need_bits > depth_bits:
                     _capacity["hints"].pop(hkey, None)   # outgrown: redo this batch with exactly sized buffers / sort bits

@@ -148,17 +148,71 @@ class SymmGradBucket(GradBucket):
             self.hdl = symm_mem.rendezvous(self.flat, g)
             self.nvls = bool(getattr(self.hdl, "multicast_ptr", 0))
 
+    def _mc(self, offset_floats: int = 0) -> int:
+        h = self.hdl
+        return h.multicast_ptr + (self.flat.data_ptr() - h.buffer_ptrs[h.rank]) + 4 * offset_floats
+
     def all_reduce(self, group=None):
         if not self.nvls:
             return super().all_reduce(group if group is not None else self.group)
         from . import _lib
         h = self.hdl
-        mc = h.multicast_ptr + (self.flat.data_ptr() - h.buffer_ptrs[h.rank])
         stream = torch.cuda.current_stream(self.flat.device).cuda_stream
         h.barrier(channel=0)   # every rank's gradients are written (stream-ordered on each rank)
-        _lib.check(_lib.lib().tgr_multimem_allreduce_f32(mc, self.flat.numel(), h.rank, h.world_size, stream),
+        _lib.check(_lib.lib().tgr_multimem_allreduce_f32(self._mc(), self.flat.numel(), h.rank, h.world_size, stream),
                    "tgr_multimem_allreduce_f32")
         h.barrier(channel=1)   # every rank's slice has been broadcast
+        return self
+
+    # -- overlapped variant: the SH rows of a range of Gaussians are summed in the switch, on a high-priority side stream
+    #    with a capped grid, while the backward's per-Gaussian kernel computes the next range ---------------------------
+    import os as _os
+    MAX_CTAS_OVERLAPPED = int(_os.environ.get("TGR_NVLS_CTAS", "32"))
+
+    def _side(self) -> torch.cuda.Stream:
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = torch.cuda.Stream(device=self.flat.device, priority=-1)
+            self._channel = 0
+        return self._side_stream
+
+    def _next_channel(self) -> int:
+        self._channel = (self._channel + 1) % 8
+        return self._channel
+
+    def all_reduce_sh_rows_async(self, first: int, count: int, group=None):
+        if not self.nvls:
+            return super().all_reduce_sh_rows_async(first, count, group if group is not None else self.group)
+        if self.sh_offset is None:
+            return
+        from . import _lib
+        h, side = self.hdl, self._side()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.flat.device))        # this range's rows are written (stream order)
+        row = self.M * 3
+        with torch.cuda.stream(side):
+            side.wait_event(ev)
+            h.barrier(channel=self._next_channel())                   # ... on every rank
+            _lib.check(_lib.lib().tgr_multimem_allreduce_f32_capped(self._mc(self.sh_offset + first * row), count * row,
+                                                                    h.rank, h.world_size, self.MAX_CTAS_OVERLAPPED,
+                                                                    side.cuda_stream), "tgr_multimem_allreduce_f32_capped")
+
+    def all_reduce_rest_and_wait(self, group=None):
+        if not self.nvls:
+            return super().all_reduce_rest_and_wait(group if group is not None else self.group)
+        from . import _lib
+        h, side = self.hdl, self._side()
+        main = torch.cuda.current_stream(self.flat.device)
+        ev = torch.cuda.Event()
+        ev.record(main)                                               # the last range (and with it every small tensor) is written
+        end = self.sh_offset if self.sh_offset is not None else self.flat.numel()
+        with torch.cuda.stream(side):
+            side.wait_event(ev)
+            h.barrier(channel=self._next_channel())
+            if end > 0:                                               # everything that is not SH: one contiguous slice
+                _lib.check(_lib.lib().tgr_multimem_allreduce_f32(self._mc(0), end, h.rank, h.world_size, side.cuda_stream),
+                           "tgr_multimem_allreduce_f32")
+            h.barrier(channel=self._next_channel())                   # every rank's slices have been broadcast
+        main.wait_stream(side)
         return self
 
 
