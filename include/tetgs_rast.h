@@ -132,6 +132,11 @@ const char* tgr_last_error(void);     /* thread-local message of the last non-ze
 uint64_t tgr_geom_bytes(int32_t P);
 uint64_t tgr_image_bytes(int32_t W, int32_t H);
 uint64_t tgr_binning_bytes(int32_t P, uint64_t num_rendered_capacity, int32_t W, int32_t H);
+/* Inverse of tgr_binning_bytes: the instance capacity a binning buffer of `binning_bytes` bytes was sized for (the
+ * largest capacity whose layout fits; every capacity that rounds to the same size has the same layout).  Lets the
+ * backward of a forward that was launched from a capacity hint (buffer larger than num_rendered) recover the layout from
+ * the buffer alone, the way rasterizer_impl.cu:371-373 recovers it from R. */
+uint64_t tgr_binning_capacity(int32_t P, uint64_t binning_bytes, int32_t W, int32_t H);
 
 /* ---- forward: replaces CudaRasterizer::Rasterizer::forward (rasterizer_impl.cu:198-336) ----
  * Stage 1: per-Gaussian preprocess (forward.cu:155-256), depth ordering, total instance count.

@@ -67,7 +67,7 @@ def _params_for_export(P, W, H, geom, binning, img):
 
 
 def export_binning(P, W, H, fwd, cap=None):
-    """cap: instance capacity the binning buffer was sized for (defaults to R: the single-view calls size it exactly)."""
+    """cap: instance capacity the binning buffer was sized for (default: recovered from the buffer's size)."""
     R, color, radii, geom, binning, img = fwd[:6]
     dev = geom.device
     T = ((W + 15) // 16) * ((H + 15) // 16)
@@ -76,7 +76,9 @@ def export_binning(P, W, H, fwd, cap=None):
     ranges = torch.empty(T, 2, dtype=torch.int32, device=dev)
     p = _params_for_export(P, W, H, geom, binning, img)
     st = torch.cuda.current_stream(dev).cuda_stream
-    check(_lib.lib().tgr_export_binning(C.byref(p), R if cap is None else cap, R, keys.data_ptr(), ids.data_ptr(),
+    if cap is None:   # a forward launched from a capacity hint has a buffer larger than R: the layout follows from its size
+        cap = _lib.lib().tgr_binning_capacity(P, binning.numel(), W, H)
+    check(_lib.lib().tgr_export_binning(C.byref(p), cap, R, keys.data_ptr(), ids.data_ptr(),
                                         ranges.data_ptr(), st))
     torch.cuda.synchronize()
     return keys, ids, ranges

@@ -579,3 +579,48 @@ def test_depth_sort_key_bit_hints_and_their_fallback():
         assert min(st2.caps) > max(st2.counts) and torch.equal(color2, color0)
     finally:
         mv.set_capacity_hints(True)
+
+
+@pytest.mark.gpu
+def test_single_view_capacity_hints_launch_ahead_and_overflow_fallback():
+    """The drop-in single-view operator: the first call of a shape waits for num_rendered before it sizes the binning
+    buffer (as the reference does, rasterizer_impl.cu:277-281); later calls launch binning / sort / blending from the
+    previous count x slack and read the count afterwards.  Same bits either way, the backward recovers the buffer layout
+    from its size, and a view that outgrows its hint (device-side check) is redone synchronously."""
+    from youreditableavatar_b200 import _lib, rasterizer as rz
+    L = _lib.lib()
+    _, inp, cam = small_scene(20000, 48, 256, 1)
+    P = inp["means3D"].shape[0]
+    g = torch.Generator().manual_seed(3)
+    dL = (torch.randn(3, 256, 256, generator=g) / (3 * 256 * 256)).cuda()
+    rz.set_capacity_hints(True)
+    try:
+        a = ours_forward(inp, cam, 3, extras=True)                     # no hint yet: exact size
+        cap_a = L.tgr_binning_capacity(P, a[4].numel(), 256, 256)    # every layout component is monotone in the capacity:
+        assert a[0] <= cap_a < a[0] + 32 and L.tgr_binning_bytes(P, cap_a, 256, 256) == a[4].numel()   # same size = same layout
+        ga = ours_backward(inp, cam, 3, a, dL)
+        b = ours_forward(inp, cam, 3, extras=True)                     # launched ahead of the count
+        assert b[0] == a[0] and b[4].numel() > a[4].numel()
+        for x, y in zip(a[1:3] + a[6:8], b[1:3] + b[6:8]):
+            assert torch.equal(x, y)
+        ka, ia, ra = export_binning(P, 256, 256, a)
+        kb, ib, rb = export_binning(P, 256, 256, b)
+        assert torch.equal(ka, kb) and torch.equal(ia, ib) and torch.equal(ra, rb)
+        gb = ours_backward(inp, cam, 3, b, dL)
+        for x, y in zip(ga, gb):
+            assert rel_l2(y, x) <= 2e-6
+        # a hint that is far too small: the device renders nothing, the host notices and redoes the call
+        for k in list(rz._capacity["hints"]):
+            rz._capacity["hints"][k] = 1
+        margin = rz._capacity["margin"]
+        rz._capacity["margin"] = 0
+        try:
+            c = ours_forward(inp, cam, 3, extras=True)
+        finally:
+            rz._capacity["margin"] = margin
+        assert c[0] == a[0] and torch.equal(c[1], a[1]) and c[4].numel() == a[4].numel()
+        # the cheaper reading of the reference's signature still holds: R and the buffers are all the backward needs
+        with pytest.raises(RuntimeError, match="too small"):
+            ours_backward(inp, cam, 3, (a[0],) + a[1:4] + (a[4][:1024],) + a[5:], dL)
+    finally:
+        rz.set_capacity_hints(True)

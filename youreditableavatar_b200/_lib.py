@@ -66,6 +66,7 @@ SYMBOLS = {
     "tgr_geom_bytes": (C.c_uint64, [C.c_int32]),
     "tgr_image_bytes": (C.c_uint64, [C.c_int32, C.c_int32]),
     "tgr_binning_bytes": (C.c_uint64, [C.c_int32, C.c_uint64, C.c_int32, C.c_int32]),
+    "tgr_binning_capacity": (C.c_uint64, [C.c_int32, C.c_uint64, C.c_int32, C.c_int32]),
     "tgr_forward_preprocess": (C.c_int, [C.POINTER(TgrParams), C.POINTER(TgrBinding), C.c_void_p]),
     "tgr_forward_render": (C.c_int, [C.POINTER(TgrParams), C.c_uint64, C.c_void_p]),
     "tgr_wait_num_rendered": (C.c_int, []),

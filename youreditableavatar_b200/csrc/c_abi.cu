@@ -120,6 +120,16 @@ uint64_t tgr_geom_bytes(int32_t P) { return carve_geom(nullptr, P).bytes; }
 uint64_t tgr_image_bytes(int32_t W, int32_t H) { return carve_image(nullptr, W, H).bytes; }
 uint64_t tgr_binning_bytes(int32_t P, uint64_t cap, int32_t W, int32_t H) { return carve_bin(nullptr, P, cap, W, H).bytes; }
 uint64_t tgr_sort_temp_bytes(uint64_t n) { return sort_temp_bytes(n); }
+uint64_t tgr_binning_capacity(int32_t P, uint64_t bytes, int32_t W, int32_t H) {
+  // tgr_binning_bytes is non-decreasing in the capacity: binary search for the largest one that fits
+  if (carve_bin(nullptr, P, 0, W, H).bytes > bytes) return 0;
+  uint64_t lo = 0, hi = (1ull << 30) - 1;
+  while (lo < hi) {
+    const uint64_t mid = lo + (hi - lo + 1) / 2;
+    if (carve_bin(nullptr, P, mid, W, H).bytes <= bytes) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
 
 static int check_gaussians(const tgr_params* p, const tgr_binding* bind) {
   if (!bind) {

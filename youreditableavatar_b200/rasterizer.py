@@ -54,6 +54,19 @@ def depth_bits_needed(header_words) -> int:
 # need more, the forward starts over with the exact number before anything consumes the wrong order
 _depth_bits_hint = {}
 
+# Capacity hints of the single-view calls, per (device, P, W, H): the reference stalls the GPU once per forward — it
+# reads num_rendered back to size the binning buffer before it can launch the sort (rasterizer_impl.cu:277-281).  Here
+# the first call of a shape does the same; every later one sizes the buffer from the previous count x slack and launches
+# binning / sort / blending right behind the preprocess kernel.  The host still reads the count (the operator returns
+# it), but only AFTER everything is queued: the GPU renders while the host waits, and should the view have outgrown
+# its buffer (the kernels notice on the device and render nothing) the call is redone the synchronous way.
+_capacity = {"enabled": True, "slack": 1.25, "margin": 32768, "hints": {}}
+
+
+def set_capacity_hints(enabled: bool = True) -> None:
+    _capacity["enabled"] = bool(enabled)
+    _capacity["hints"].clear()
+
 
 def check_prefilter(header_words) -> None:
     """The reference prints this message and __trap()s (which kills the CUDA context) when `prefiltered=True` was
@@ -117,7 +130,7 @@ def _fill_common(p: TgrParams, bg, means3D, colors, opacity, scales, rotations, 
 
 def c_rasterize_gaussians(bg, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
                           viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos,
-                          prefiltered, debug, extras=False, binding=None):
+                          prefiltered, debug, extras=False, binding=None, _use_hint=True):
     """`_C.rasterize_gaussians` (rasterize_points.cu:35-115): same 19 positional args, same 6-tuple result
     (num_rendered, color[3,H,W], radii[P] int32, geomBuffer, binningBuffer, imgBuffer); with extras=True the
     tuple is extended by (depth[1,H,W], alpha[1,H,W])."""
@@ -175,25 +188,41 @@ def c_rasterize_gaussians(bg, means3D, colors, opacity, scales, rotations, scale
         stream = _stream(device)
         bptr = C.byref(binding) if binding is not None else None
         hkey = (device.index if device.index is not None else torch.cuda.current_device(), P)
+        ckey = hkey + (W, H)
         p.depth_key_bits = min(32, _depth_bits_hint.get(hkey, 31) + 1)
+        hint = _capacity["hints"].get(ckey) if (_capacity["enabled"] and _use_hint) else None
 
         check(L.tgr_forward_preprocess(C.byref(p), bptr, stream), "tgr_forward_preprocess")
-        # the one host<->device sync of a forward (the reference has the same one, rasterizer_impl.cu:281);
-        # the GPU keeps sorting Gaussians by depth while the host waits for the count
+        cap = None
+        if hint is not None:
+            # launch-ahead: binning buffer from the previous count, everything queued before the host looks at the count
+            cap = (int(hint * _capacity["slack"]) + _capacity["margin"] + 31) // 32 * 32
+            binning = torch.empty(L.tgr_binning_bytes(P, cap, W, H), **u8)
+            p.binning_buffer, p.binning_bytes = binning.data_ptr(), binning.numel()
+            check(L.tgr_forward_render(C.byref(p), cap, stream), "tgr_forward_render")
+        # the host reads the count: the operator returns it (the reference stalls the GPU here, rasterizer_impl.cu:281;
+        # with a hint the GPU is already sorting and blending while the host waits)
         check(L.tgr_wait_num_rendered(), "tgr_wait_num_rendered")
         R = int(slot[0])
         check_prefilter(slot)
         need = depth_bits_needed(slot)
         _depth_bits_hint[hkey] = need
+        if _capacity["enabled"]:
+            _capacity["hints"][ckey] = R
+        if cap is not None and R > cap:    # outgrown: nothing was rendered (device-side check); redo with the exact size
+            return c_rasterize_gaussians(bg, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
+                                         viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree,
+                                         campos, prefiltered, debug, extras=extras, binding=binding, _use_hint=False)
         if need > p.depth_key_bits:        # this view spans more depth bits than the hint covered: the order is wrong.
             # Start over (the hint now holds what this view needs); rare — the camera would have to move from a view
             # where all visible depths share their leading bits to one where they do not
             return c_rasterize_gaussians(bg, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
                                          viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree,
-                                         campos, prefiltered, debug, extras=extras, binding=binding)
-        binning = torch.empty(L.tgr_binning_bytes(P, R, W, H), **u8)
-        p.binning_buffer, p.binning_bytes = binning.data_ptr(), binning.numel()
-        check(L.tgr_forward_render(C.byref(p), R, stream), "tgr_forward_render")
+                                         campos, prefiltered, debug, extras=extras, binding=binding, _use_hint=_use_hint)
+        if cap is None:
+            binning = torch.empty(L.tgr_binning_bytes(P, R, W, H), **u8)
+            p.binning_buffer, p.binning_bytes = binning.data_ptr(), binning.numel()
+            check(L.tgr_forward_render(C.byref(p), R, stream), "tgr_forward_render")
 
     out = (R, out_color, radii, geom, binning, img)
     if extras:
@@ -276,7 +305,12 @@ def c_rasterize_gaussians_backward(bg, means3D, radii, colors, scales, rotations
         p.dL_dscales = _ptr(dL_dscales)
         p.dL_drotations = _ptr(dL_drotations)
         bptr = C.byref(binding) if binding is not None else None
-        check(L.tgr_backward(C.byref(p), bptr, int(R), _stream(device)), "tgr_backward")
+        # the binning buffer may be larger than R asks for (forward launched from a capacity hint): its layout follows
+        # from its size, as the reference's follows from R (rasterizer_impl.cu:371-373)
+        cap = L.tgr_binning_capacity(P, binningBuffer.numel(), W, H)
+        if cap < int(R):
+            raise RuntimeError("binningBuffer (%d bytes) is too small for %d rendered instances" % (binningBuffer.numel(), int(R)))
+        check(L.tgr_backward(C.byref(p), bptr, cap, _stream(device)), "tgr_backward")
 
     return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
 
