@@ -255,6 +255,12 @@ int tgr_export_image_state(const tgr_params* p, float* final_T, uint32_t* n_cont
  * hand-written onesweep that replaces cub::DeviceRadixSort::SortPairs (rasterizer_impl.cu:303-308,
  * simple_knn.cu:207-213).  Exposed for tests and micro-benchmarks. Result is in keys_out/vals_out. */
 uint64_t tgr_sort_temp_bytes(uint64_t n);
+/* Batched form — what the rasterizer itself uses for the V views of a batch: up to TGR_MAX_BATCH independent sorts, the
+ * same bit range for all, every radix pass ONE launch (blockIdx.y = segment).  Segment i sorts n[i] pairs in place
+ * between its a / b buffers; *result_in_b tells where the results are (1: b buffers, 0: a buffers). */
+int tgr_sort_pairs_u32_batch(int32_t n_segments, const uint64_t* n, uint32_t* const* keys_a, uint32_t* const* vals_a,
+                             uint32_t* const* keys_b, uint32_t* const* vals_b, int begin_bit, int end_bit,
+                             void* const* temps, int32_t* result_in_b, void* stream);
 int tgr_sort_pairs_u32(uint64_t n, uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
                        int begin_bit, int end_bit, void* temp, uint64_t temp_bytes, void* stream);
 

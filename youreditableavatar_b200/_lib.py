@@ -92,6 +92,9 @@ SYMBOLS = {
     "tgr_profile_enable": (C.c_int, [C.c_int]),
     "tgr_profile_collect": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "tgr_sort_temp_bytes": (C.c_uint64, [C.c_uint64]),
+    "tgr_sort_pairs_u32_batch": (C.c_int, [C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int,
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_void_p]),
     "tgr_sort_pairs_u32": (C.c_int, [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                      C.c_void_p, C.c_uint64, C.c_void_p]),
     "tgr_image_loss_bytes": (C.c_uint64, [C.c_int32, C.c_int32, C.c_int32]),
