@@ -671,6 +671,48 @@ def train_step_reference(P, res, act, cams, targets_host, V, steps, warmup):
             "adam": {"ms": ms_adam}}
 
 
+def bound_path_leg(cfg, reps=10):
+    """SURVEY §8 a1 on a measured path: one view, forward + backward from the RAW scene parameters (offsets along the
+    normals, log-scales, un-normalised quaternions, opacity logits, SH) — (a) the way the reference's scene models do it:
+    eager torch binding + activations with autograd around the rasterizer (tetgs_model.py:252-286), here around this
+    library's drop-in operator; (b) `rasterize_bound`: binding, activations and their chain rule inside the preprocess
+    kernels (csrc/preprocess.cu / preprocess_bwd.cu, BOUND variants)."""
+    from youreditableavatar_b200 import scene
+    from youreditableavatar_b200.binding import MeshBinding, rasterize_bound
+    from youreditableavatar_b200.rasterizer import GaussianRasterizer
+    from youreditableavatar_b200.parallel import settings_from_cam
+    P, res, _, _ = scene.CONFIGS[cfg]
+    gs = scene.make_scene(cfg, device="cuda")
+    cam = scene.orbit_camera(0, 8, res, res, device="cuda")
+    st = settings_from_cam(cam, 3)
+    mesh = MeshBinding.from_scene(gs)
+    names = ("delta", "log_scales", "raw_quats", "opacity_logits", "shs")
+    raw = {k: gs[k].cuda().clone().requires_grad_(True) for k in names}
+    dL = torch.randn(3, res, res, device="cuda") / (3 * res * res)
+    rast = GaussianRasterizer(st)
+
+    def eager():
+        g = dict(gs)
+        g.update(raw)
+        act = scene.activate(g)
+        m2 = torch.zeros_like(act["means3D"], requires_grad=True)
+        color, _ = rast(means3D=act["means3D"], means2D=m2, opacities=act["opacities"], shs=act["shs"], scales=act["scales"],
+                        rotations=act["rotations"])
+        (color * dL).sum().backward()
+        for v in raw.values():
+            v.grad = None
+
+    def fused():
+        color, _ = rasterize_bound(raw["delta"], raw["log_scales"], raw["raw_quats"], raw["opacity_logits"], raw["shs"], mesh, st)
+        (color * dL).sum().backward()
+        for v in raw.values():
+            v.grad = None
+
+    ms_e, ms_f = _time_events(eager, reps), _time_events(fused, reps)
+    return {"config": cfg, "what": "one view fwd+bwd from the raw parameters through autograd", "eager_binding_ms": ms_e,
+            "fused_binding_ms": ms_f, "speedup": ms_e / ms_f}
+
+
 _result_fd = None
 
 
@@ -955,6 +997,10 @@ def main():
         if m.get("per_view_api"):
             out["per_view_api"] = m["per_view_api"]
     if ours and batched and world == 1 and not args.no_train_step:
+        try:
+            out["bound_path"] = bound_path_leg(cfg)
+        except Exception as ex:
+            out["bound_path"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
         try:
             out["train_step"] = train_step_ours(P, res, act, cams, targets_host, V, max(4, args.steps // 2),
                                                 max(args.warmup, 3), peak)

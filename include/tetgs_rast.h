@@ -122,6 +122,18 @@ typedef struct tgr_binding {
   float* dL_draw_quats;        /* [P,4] */
   float* dL_dopacity_logits;   /* [P]   */
   float* dL_dverts;            /* [n_verts,3] or NULL; accumulated with atomics, caller zeroes */
+  /* Direct form (origins != NULL; the mesh fields above are then ignored): mean = origins + normals * delta with
+   * per-Gaussian constants, which is how every scene model of the reference holds its binding between re-meshings —
+   * TetGS.ori_points / .normals (tetgs_model.py:156-172, points = ori_points + normals * _points, :252-258), the edit
+   * models' cat(keep_points, ori_edit_points + _edit_normals * _edit_points) (tetgs_edit_3d.py:272-280) and the fixed
+   * points of the flat 2-D Gaussians (tetgs_edit_2d.py:279-282: normals == NULL).  delta may be NULL (zero offsets). */
+  const float* origins;        /* [P,3] or NULL */
+  const float* normals;        /* [P,3] or NULL */
+  /* Gaussians [0, n_frozen) are frozen — the `keep_*` part of the edit models, requires_grad=False
+   * (tetgs_edit_2d.py:237-267, tetgs_edit_3d.py:160-200): the backward writes zero gradient rows for them without
+   * computing anything. */
+  int32_t n_frozen;
+  int32_t reserved_;
 } tgr_binding;
 
 /* ---- library ---- */

@@ -624,3 +624,79 @@ def test_single_view_capacity_hints_launch_ahead_and_overflow_fallback():
             ours_backward(inp, cam, 3, (a[0],) + a[1:4] + (a[4][:1024],) + a[5:], dL)
     finally:
         rz.set_capacity_hints(True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["edit3d", "edit2d"])
+def test_fused_direct_binding_of_the_edit_models(variant):
+    """DirectBinding through the BOUND kernels: the keep + edit concatenation of the edit stages rendered straight from
+    the raw tensors.  edit3d: points = cat(keep_xyz, ori_edit + n * delta) (tetgs_edit_3d.py:272-280); edit2d: fixed points,
+    flat Gaussians in the triangle frame with scales (1e-8, d, d) (tetgs_edit_2d.py:172-208, 279-282).  Image = the eager
+    concatenation fed to the plain operator; gradients of the edit part vs the float64 restatement (oracle.bind_direct),
+    gradient rows of the frozen keep part exactly zero."""
+    from oracle import oracle
+    from youreditableavatar_b200 import formats
+    from youreditableavatar_b200.binding import DirectBinding, rasterize_bound
+    from youreditableavatar_b200.rasterizer import GaussianRasterizationSettings
+    gs, act, cam = small_scene(2400, 32, 96, 1)
+    P = 2400
+    K = 1500                                              # keep part: the first K Gaussians, taken over activated
+    keep_xyz = act["means3D"][:K].clone()
+    fi = gs["face_index"].long()
+    tri = gs["verts"][gs["faces"].long()[fi]]
+    w = gs["bary"][..., None]
+    ori = (tri * w).sum(1).cuda()
+    nrm = (gs["vert_normals"][gs["faces"].long()[fi]] * w).sum(1).cuda()
+    raw = {k: gs[k].cuda().clone() for k in ("delta", "log_scales", "raw_quats", "opacity_logits", "shs")}
+    if variant == "edit2d":
+        # fresh flat Gaussians on the edit faces: quaternion of the triangle frame, scales (1e-8, d, d)
+        flat = formats.bind_edit_gaussians(gs["verts"], gs["faces"].long(), sh_coeffs=16)
+        sel = torch.arange(K, P) % flat["log_scales"].shape[0]
+        raw["log_scales"][K:] = flat["log_scales"][sel].cuda()
+        raw["raw_quats"][K:] = flat["raw_quats"][sel].cuda()
+        binding = DirectBinding.from_keep_edit(keep_xyz, ori[K:], None)
+        delta_in = None
+    else:
+        binding = DirectBinding.from_keep_edit(keep_xyz, ori[K:], nrm[K:])
+        delta_in = raw["delta"].reshape(-1, 1).clone().requires_grad_(True)      # [P,1] like `_edit_points`
+    leaves = {k: raw[k].clone().requires_grad_(True) for k in ("log_scales", "raw_quats", "shs")}
+    leaves["opacity_logits"] = raw["opacity_logits"].reshape(-1, 1).clone().requires_grad_(True)   # [P,1] like all_densities
+    settings = GaussianRasterizationSettings(96, 96, cam["tanfovx"], cam["tanfovy"], cam["bg"], 1.0, cam["viewmatrix"],
+                                             cam["projmatrix"], 3, cam["campos"], False, False)
+    color, radii = rasterize_bound(delta_in, leaves["log_scales"], leaves["raw_quats"], leaves["opacity_logits"],
+                                   leaves["shs"], binding, settings)
+    # eager concatenation -> plain operator
+    b64 = oracle.bind_direct(binding.origins.cpu(), None if binding.normals is None else binding.normals.cpu(),
+                             None if delta_in is None else raw["delta"].cpu(), raw["log_scales"].cpu(), raw["raw_quats"].cpu(),
+                             raw["opacity_logits"].cpu(), n_keep=K)
+    eager_in = {k: v.float().cuda().contiguous() for k, v in b64.items()}
+    eager_in["shs"] = raw["shs"]
+    eager = ours_forward(eager_in, cam, 3)
+    d = (color - eager[1]).abs()
+    assert (d > IMG_TOL).float().mean().item() <= 1e-4 and d.max().item() <= 1e-2
+    assert (radii != eager[2]).float().mean().item() <= 1e-3
+
+    g = torch.Generator().manual_seed(1)
+    dL = torch.randn(3, 96, 96, generator=g) / (3 * 96 * 96)
+    (color * dL.cuda()).sum().backward()
+    # float64 restatement with autograd; the keep rows enter detached
+    o_leaves = {k: raw[k].double().cpu().clone().requires_grad_(True) for k in ("delta", "log_scales", "raw_quats", "opacity_logits", "shs")}
+    bound = oracle.bind_direct(binding.origins.cpu(), None if binding.normals is None else binding.normals.cpu(),
+                               None if delta_in is None else o_leaves["delta"], o_leaves["log_scales"], o_leaves["raw_quats"],
+                               o_leaves["opacity_logits"], n_keep=K)
+    bound["shs"] = torch.cat([o_leaves["shs"][:K].detach(), o_leaves["shs"][K:]])
+    geo = export_geom(P, 96, 96, eager)
+    out = oracle.rasterize(bound, to_dev(cam, "cpu"), 3,
+                           xy_radii_override=(geo["means2D"].cpu().numpy(), eager[2].cpu().numpy()),
+                           depth_override=geo["depths"].cpu().numpy())
+    (out["color"] * dL.double()).sum().backward()
+    mine = {"log_scales": leaves["log_scales"].grad, "raw_quats": leaves["raw_quats"].grad,
+            "opacity_logits": leaves["opacity_logits"].grad.reshape(-1), "shs": leaves["shs"].grad}
+    if delta_in is not None:
+        assert delta_in.grad.shape == (P, 1)
+        mine["delta"] = delta_in.grad.reshape(-1)
+    assert leaves["opacity_logits"].grad.shape == (P, 1)
+    for k, gm in mine.items():
+        assert float(gm[:K].abs().max()) == 0.0, "%s: frozen keep rows must get zero gradient" % k
+        e = rel_l2(gm[K:], o_leaves[k].grad[K:])
+        assert e <= 3 * GRAD_TOL, "%s rel-L2 vs oracle %g" % (k, e)

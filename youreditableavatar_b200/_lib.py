@@ -47,6 +47,7 @@ class TgrBinding(C.Structure):
         ("out_opacities", C.c_void_p),
         ("dL_ddelta", C.c_void_p), ("dL_dlog_scales", C.c_void_p), ("dL_draw_quats", C.c_void_p),
         ("dL_dopacity_logits", C.c_void_p), ("dL_dverts", C.c_void_p),
+        ("origins", C.c_void_p), ("normals", C.c_void_p), ("n_frozen", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 

@@ -28,17 +28,47 @@ class MeshBinding(NamedTuple):
                            f("face_index", torch.int32), f("bary", torch.float32))
 
 
-def _binding_struct(mesh: MeshBinding, delta, log_scales, raw_quats, opacity_logits, act, grads=None) -> TgrBinding:
+class DirectBinding(NamedTuple):
+    """mean = origins + normals * delta with per-Gaussian constants — how every scene model of the reference holds its
+    binding between re-meshings: `TetGS.ori_points` / `.normals` (tetgs_model.py:156-172, 252-258), the edit models'
+    cat(keep_points, ori_edit_points + _edit_normals * _edit_points) (tetgs_edit_3d.py:272-280; keep Gaussians: their
+    world position as origin, zero normal) and the fixed points of the flat 2-D Gaussians (tetgs_edit_2d.py:279-282:
+    normals=None).  Gaussians [0, n_frozen) are the frozen `keep_*` part (requires_grad=False,
+    tetgs_edit_2d.py:237-267): they get zero gradient rows and cost the backward nothing."""
+    origins: torch.Tensor                 # [P,3] f32
+    normals: Optional[torch.Tensor]       # [P,3] f32 or None
+    n_frozen: int = 0
+
+    @staticmethod
+    def from_keep_edit(keep_xyz: torch.Tensor, edit_origins: torch.Tensor, edit_normals: Optional[torch.Tensor] = None,
+                       device="cuda") -> "DirectBinding":
+        """keep Gaussians first (frozen), then the edit Gaussians — the order of the reference's torch.cat calls."""
+        f = lambda t: t.to(device=device, dtype=torch.float32)
+        origins = torch.cat([f(keep_xyz), f(edit_origins)]).contiguous()
+        normals = None
+        if edit_normals is not None:
+            normals = torch.cat([torch.zeros_like(f(keep_xyz)), f(edit_normals)]).contiguous()
+        return DirectBinding(origins, normals, int(keep_xyz.shape[0]))
+
+
+def _binding_struct(mesh, delta, log_scales, raw_quats, opacity_logits, act, grads=None) -> TgrBinding:
     b = TgrBinding()
-    b.n_verts, b.n_faces = mesh.verts.shape[0], mesh.faces.shape[0]
-    b.verts, b.vert_normals = mesh.verts.data_ptr(), mesh.vert_normals.data_ptr()
-    b.faces, b.face_index, b.bary = mesh.faces.data_ptr(), mesh.face_index.data_ptr(), mesh.bary.data_ptr()
-    b.delta, b.log_scales = delta.data_ptr(), log_scales.data_ptr()
+    if isinstance(mesh, DirectBinding):
+        b.origins = mesh.origins.data_ptr()
+        b.normals = mesh.normals.data_ptr() if mesh.normals is not None else None
+        b.n_frozen = int(mesh.n_frozen)
+    else:
+        b.n_verts, b.n_faces = mesh.verts.shape[0], mesh.faces.shape[0]
+        b.verts, b.vert_normals = mesh.verts.data_ptr(), mesh.vert_normals.data_ptr()
+        b.faces, b.face_index, b.bary = mesh.faces.data_ptr(), mesh.face_index.data_ptr(), mesh.bary.data_ptr()
+    b.delta = delta.data_ptr() if delta is not None else None
+    b.log_scales = log_scales.data_ptr()
     b.raw_quats, b.opacity_logits = raw_quats.data_ptr(), opacity_logits.data_ptr()
     b.out_means3D, b.out_scales = act["means3D"].data_ptr(), act["scales"].data_ptr()
     b.out_rotations, b.out_opacities = act["rotations"].data_ptr(), act["opacities"].data_ptr()
     if grads is not None:
-        b.dL_ddelta, b.dL_dlog_scales = grads["delta"].data_ptr(), grads["log_scales"].data_ptr()
+        b.dL_ddelta = grads["delta"].data_ptr() if grads.get("delta") is not None else None
+        b.dL_dlog_scales = grads["log_scales"].data_ptr()
         b.dL_draw_quats, b.dL_dopacity_logits = grads["raw_quats"].data_ptr(), grads["opacity_logits"].data_ptr()
         if grads.get("verts") is not None:
             b.dL_dverts = grads["verts"].data_ptr()
@@ -48,14 +78,15 @@ def _binding_struct(mesh: MeshBinding, delta, log_scales, raw_quats, opacity_log
 class _RasterizeBound(torch.autograd.Function):
     @staticmethod
     def forward(ctx, delta, log_scales, raw_quats, opacity_logits, shs, mesh, raster_settings, extras, verts_grad):
-        P = delta.shape[0]
-        dev = delta.device
+        P = log_scales.shape[0]
+        dev = log_scales.device
         # the reference keeps delta and the opacity logits as [P,1] (`_points`, `all_densities`, tetgs_model.py:172,202);
-        # gradients go back in whatever shape / dtype the caller's tensors have
-        ctx.in_meta = tuple((t.shape, t.dtype) for t in (delta, log_scales, raw_quats, opacity_logits, shs))
+        # gradients go back in whatever shape / dtype the caller's tensors have.  delta=None: no offsets (the flat 2-D
+        # Gaussians of tetgs_edit_2d.py sit at fixed points)
+        ctx.in_meta = tuple((t.shape, t.dtype) if t is not None else None for t in (delta, log_scales, raw_quats, opacity_logits, shs))
         c = lambda t: t.detach().contiguous().float()
-        delta, log_scales, raw_quats, opacity_logits, shs = map(c, (delta.reshape(-1), log_scales, raw_quats,
-                                                                    opacity_logits.reshape(-1), shs))
+        log_scales, raw_quats, opacity_logits, shs = map(c, (log_scales, raw_quats, opacity_logits.reshape(-1), shs))
+        delta = c(delta.reshape(-1)) if delta is not None else None
         f32 = dict(dtype=torch.float32, device=dev)
         act = {"means3D": torch.empty(P, 3, **f32), "scales": torch.empty(P, 3, **f32),
                "rotations": torch.empty(P, 4, **f32), "opacities": torch.empty(P, 1, **f32)}
@@ -68,8 +99,9 @@ class _RasterizeBound(torch.autograd.Function):
                                        extras=extras, binding=b)
         R, color, radii, geom, binning, img = res[:6]
         ctx.settings, ctx.R, ctx.extras, ctx.mesh, ctx.verts_grad = s, R, extras, mesh, verts_grad
-        ctx.save_for_backward(delta, log_scales, raw_quats, opacity_logits, shs, radii, geom, binning, img,
-                              act["means3D"], act["scales"], act["rotations"], act["opacities"])
+        ctx.has_delta = delta is not None
+        ctx.save_for_backward(delta if delta is not None else log_scales.new_empty(0), log_scales, raw_quats, opacity_logits,
+                              shs, radii, geom, binning, img, act["means3D"], act["scales"], act["rotations"], act["opacities"])
         ctx.mark_non_differentiable(radii)
         if extras:
             return color, radii, res[6], res[7]
@@ -80,11 +112,13 @@ class _RasterizeBound(torch.autograd.Function):
         (delta, log_scales, raw_quats, opacity_logits, shs, radii, geom, binning, img, means3D, scales, rotations,
          opacities) = ctx.saved_tensors
         s, mesh = ctx.settings, ctx.mesh
-        P, dev = delta.shape[0], delta.device
+        P, dev = log_scales.shape[0], log_scales.device
         f32 = dict(dtype=torch.float32, device=dev)
-        grads = {"delta": torch.empty(P, **f32), "log_scales": torch.empty(P, 3, **f32),
+        if not ctx.has_delta:
+            delta = None
+        grads = {"delta": torch.empty(P, **f32) if ctx.has_delta else None, "log_scales": torch.empty(P, 3, **f32),
                  "raw_quats": torch.empty(P, 4, **f32), "opacity_logits": torch.empty(P, **f32),
-                 "verts": torch.zeros_like(mesh.verts) if ctx.verts_grad else None}
+                 "verts": torch.zeros_like(mesh.verts) if (ctx.verts_grad and not isinstance(mesh, DirectBinding)) else None}
         act = {"means3D": means3D, "scales": scales, "rotations": rotations, "opacities": opacities}
         b = _binding_struct(mesh, delta, log_scales, raw_quats, opacity_logits, act, grads)
         e = torch.Tensor([])
@@ -96,7 +130,7 @@ class _RasterizeBound(torch.autograd.Function):
         ctx.extra_grads = grads
         _RasterizeBound.last_vertex_grad = grads["verts"]
         back = (grads["delta"], grads["log_scales"], grads["raw_quats"], grads["opacity_logits"], out[5])
-        back = tuple(g.reshape(shape).to(dtype) for g, (shape, dtype) in zip(back, ctx.in_meta))
+        back = tuple(g.reshape(m[0]).to(m[1]) if (g is not None and m is not None) else None for g, m in zip(back, ctx.in_meta))
         return back + (None, None, None, None)
 
 

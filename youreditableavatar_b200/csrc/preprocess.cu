@@ -178,16 +178,26 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const tgr_params p, con
   float hx_tau = 0.f;
   if (live) {
     if (BOUND) {
-      // mean = sum_k w_k V[f_k] + (sum_k w_k N[f_k]) * delta      (tetgs_model.py:252-258, 335-377)
-      const int f = bind.face_index[idx];
-      const int i0 = bind.faces[3 * f + 0], i1 = bind.faces[3 * f + 1], i2 = bind.faces[3 * f + 2];
-      const float w0 = bind.bary[3 * idx + 0], w1 = bind.bary[3 * idx + 1], w2 = bind.bary[3 * idx + 2];
-      const float d = bind.delta[idx];
+      const float d = bind.delta ? bind.delta[idx] : 0.f;
       float o[3], n[3];
+      if (bind.origins != nullptr) {
+        // direct form: mean = origin + normal * delta with per-Gaussian constants (tetgs_model.py:252-258 on the stored
+        // ori_points / normals; tetgs_edit_3d.py:272-280)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        o[c] = w0 * bind.verts[3 * i0 + c] + w1 * bind.verts[3 * i1 + c] + w2 * bind.verts[3 * i2 + c];
-        n[c] = w0 * bind.vert_normals[3 * i0 + c] + w1 * bind.vert_normals[3 * i1 + c] + w2 * bind.vert_normals[3 * i2 + c];
+        for (int c = 0; c < 3; ++c) {
+          o[c] = bind.origins[3 * idx + c];
+          n[c] = bind.normals ? bind.normals[3 * idx + c] : 0.f;
+        }
+      } else {
+        // mean = sum_k w_k V[f_k] + (sum_k w_k N[f_k]) * delta      (tetgs_model.py:252-258, 335-377)
+        const int f = bind.face_index[idx];
+        const int i0 = bind.faces[3 * f + 0], i1 = bind.faces[3 * f + 1], i2 = bind.faces[3 * f + 2];
+        const float w0 = bind.bary[3 * idx + 0], w1 = bind.bary[3 * idx + 1], w2 = bind.bary[3 * idx + 2];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          o[c] = w0 * bind.verts[3 * i0 + c] + w1 * bind.verts[3 * i1 + c] + w2 * bind.verts[3 * i2 + c];
+          n[c] = w0 * bind.vert_normals[3 * i0 + c] + w1 * bind.vert_normals[3 * i1 + c] + w2 * bind.vert_normals[3 * i2 + c];
+        }
       }
       p_orig = {o[0] + n[0] * d, o[1] + n[1] * d, o[2] + n[2] * d};
       scale = {expf(bind.log_scales[3 * idx + 0]), expf(bind.log_scales[3 * idx + 1]), expf(bind.log_scales[3 * idx + 2])};

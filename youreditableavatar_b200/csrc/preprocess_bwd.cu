@@ -54,8 +54,11 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
   const int block_first = vb.first + blockIdx.x * blockDim.x;
   const int idx = block_first + threadIdx.x;
   const int nrows = min((int)blockDim.x, vb.end - block_first);
-  const int V = MULTI ? vb.V : 1;
-  for (int e = threadIdx.x; e < V * CAM_FLOATS; e += blockDim.x) {
+  // frozen Gaussians (tgr_binding.n_frozen, the keep part of the edit models) take no part: zero gradient rows, no work
+  const bool frozen = BOUND && idx < bind.n_frozen;
+  const bool block_frozen = BOUND && block_first + (int)blockDim.x <= bind.n_frozen;
+  const int V = frozen ? 0 : (MULTI ? vb.V : 1);
+  for (int e = threadIdx.x; e < (MULTI ? vb.V : 1) * CAM_FLOATS; e += blockDim.x) {
     const int v = e / CAM_FLOATS, k = e % CAM_FLOATS;
     float x = 0.f;
     if (k < 16) x = vb.v[v].viewmatrix[k];
@@ -63,7 +66,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
     else if (k < 35) x = vb.v[v].campos[k - 32];
     s_cam[v][k] = x;
   }
-  if (STAGED) {
+  if (STAGED && !block_frozen) {
     const float4* src = reinterpret_cast<const float4*>(p.shs + (size_t)block_first * SH_ROW);
     for (int v = threadIdx.x; v < nrows * (SH_ROW / 4); v += blockDim.x) {
       const float4 q = __ldg(src + v);
@@ -138,6 +141,10 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
       if (k < ncoef * 3) sh_local[k] = __ldg(base + k);
   }
   bool any_visible = false;
+  if (STAGED && !MULTI && frozen) {   // single view: the SH row doubles as its gradient row — a frozen Gaussian's is zero
+#pragma unroll
+    for (int k = 0; k < SH_ROW; ++k) orow[k] = 0.f;
+  }
 
   for (int vi = 0; vi < V; ++vi) {
   const ViewDesc& vd = vb.v[vi];
@@ -363,13 +370,21 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
 
   if (BOUND) {
     // chain rule through points = ori + n*delta, scale = exp(.), q = normalize(.), o = sigmoid(.)
-    const int f = bind.face_index[idx];
-    const int i0 = bind.faces[3 * f + 0], i1 = bind.faces[3 * f + 1], i2 = bind.faces[3 * f + 2];
-    const float w0 = bind.bary[3 * i + 0], w1 = bind.bary[3 * i + 1], w2 = bind.bary[3 * i + 2];
+    const bool direct = bind.origins != nullptr;
+    int i0 = 0, i1 = 0, i2 = 0;
+    float w0 = 0.f, w1 = 0.f, w2 = 0.f;
     float n[3];
+    if (direct) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-      n[c] = w0 * bind.vert_normals[3 * i0 + c] + w1 * bind.vert_normals[3 * i1 + c] + w2 * bind.vert_normals[3 * i2 + c];
+      for (int c = 0; c < 3; ++c) n[c] = bind.normals ? bind.normals[3 * i + c] : 0.f;
+    } else {
+      const int f = bind.face_index[idx];
+      i0 = bind.faces[3 * f + 0]; i1 = bind.faces[3 * f + 1]; i2 = bind.faces[3 * f + 2];
+      w0 = bind.bary[3 * i + 0]; w1 = bind.bary[3 * i + 1]; w2 = bind.bary[3 * i + 2];
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        n[c] = w0 * bind.vert_normals[3 * i0 + c] + w1 * bind.vert_normals[3 * i1 + c] + w2 * bind.vert_normals[3 * i2 + c];
+    }
     if (bind.dL_ddelta) put(bind.dL_ddelta + i, n[0] * dmean[0] + n[1] * dmean[1] + n[2] * dmean[2], acc);
     if (bind.dL_dlog_scales) store3(bind.dL_dlog_scales, i, dscale[0] * scale.x, dscale[1] * scale.y, dscale[2] * scale.z, acc);
     if (bind.dL_draw_quats) {
@@ -386,7 +401,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const tgr_params p,
       const float o = bind.out_opacities[i];
       put(bind.dL_dopacity_logits + i, dop * o * (1.f - o), acc);
     }
-    if (bind.dL_dverts && any_visible) {
+    if (bind.dL_dverts && any_visible && !direct) {
       const int vi[3] = {i0, i1, i2};
       const float wv[3] = {w0, w1, w2};
 #pragma unroll
