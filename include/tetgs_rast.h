@@ -359,6 +359,30 @@ int tgr_adam_step(const tgr_adam_group* groups, int32_t n_groups, int32_t step /
 int tgr_build_cameras(int32_t n_views, const float* camera_to_worlds, const float* intrinsics, float znear,
                       float zfar, float* out_cameras, void* stream);
 
+/* ---- f4: marching tetrahedra (re-meshing after a geometry edit) ----
+ * Replaces MarchingTetrahedraHelper._forward (Edit_core/tetgs_spatial/models/isosurface.py:112-184: boolean masks,
+ * torch.unique(dim=0, return_inverse=True) over the sorted edge pairs, gathers through the triangle table).  Outputs are
+ * identical to the reference's, ordering included: one vertex per unique grid edge with exactly one occupied end, in
+ * lexicographic (min id, max id) order, position by the reference's fp32 expression; faces of the one-triangle tets
+ * first, then of the two-triangle tets; face_to_tet = the tet of every face (what the keep / edit inheritance keys on,
+ * tetgs_model.py:679-726); interp_v = the two grid vertices of every mesh vertex.
+ * Three phases, because the output sizes only exist on the device (each of the first two synchronises the stream once —
+ * this is set-up work per re-meshing, not the per-iteration path):
+ *   tgr_mt_classify   counts[4] <- {valid tets, tets with one triangle, tets with two, -}
+ *   tgr_mt_edges      counts[2] <- {unique edges of the valid tets, mesh vertices}
+ *   tgr_mt_emit       verts [n_mesh_verts,3] f32, interp_v [n_mesh_verts,2] i64 (or NULL), faces [n_one + 2 n_two, 3] i64,
+ *                     face_to_tet [n_one + 2 n_two] i64
+ * level [n_verts] f32 (> 0 = inside), pos [n_verts,3] f32, tets [n_tets,4] i32; work1 / work2: device workspaces of
+ * tgr_mt_classify_bytes(n_tets) / tgr_mt_edges_bytes(valid tets) bytes, handed from phase to phase. */
+uint64_t tgr_mt_classify_bytes(int64_t n_tets);
+uint64_t tgr_mt_edges_bytes(int64_t n_valid_tets);
+int tgr_mt_classify(int32_t n_verts, int64_t n_tets, const float* level, const int32_t* tets, void* work1,
+                    uint64_t work1_bytes, uint32_t* counts_host, void* stream);
+int tgr_mt_edges(int32_t n_verts, int64_t n_tets, uint32_t n_valid, const float* level, const int32_t* tets, void* work1,
+                 void* work2, uint64_t work2_bytes, uint32_t* counts_host, void* stream);
+int tgr_mt_emit(int64_t n_tets, uint32_t n_valid, uint32_t n_one, uint32_t n_unique, const float* pos, const float* level,
+                void* work1, void* work2, float* verts, int64_t* interp_v, int64_t* faces, int64_t* face_to_tet, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -110,6 +110,14 @@ SYMBOLS = {
                                  C.c_void_p]),
     "tgr_adam_step": (C.c_int, [C.POINTER(TgrAdamGroup), C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
                                 C.c_float, C.c_void_p]),
+    "tgr_mt_classify_bytes": (C.c_uint64, [C.c_int64]),
+    "tgr_mt_edges_bytes": (C.c_uint64, [C.c_int64]),
+    "tgr_mt_classify": (C.c_int, [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                  C.POINTER(C.c_uint32), C.c_void_p]),
+    "tgr_mt_edges": (C.c_int, [C.c_int32, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                               C.POINTER(C.c_uint32), C.c_void_p]),
+    "tgr_mt_emit": (C.c_int, [C.c_int64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tgr_build_cameras": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
 }
 

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtetgs_rast.so")
 STAMP = os.path.join(HERE, ".libtetgs_rast.stamp")
 SOURCES = ["c_abi.cu", "preprocess.cu", "sort.cu", "binning.cu", "blend_fwd.cu", "blend_bwd.cu",
-           "preprocess_bwd.cu", "knn.cu", "collective.cu", "loss.cu", "adam.cu", "cameras.cu"]
+           "preprocess_bwd.cu", "knn.cu", "marching_tets.cu", "collective.cu", "loss.cu", "adam.cu", "cameras.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
