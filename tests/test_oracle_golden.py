@@ -10,7 +10,7 @@ import torch
 from oracle import oracle
 
 GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-                if not os.path.basename(p).startswith("train_"))   # train_*.npz: tests/test_train_oracle.py
+                if not os.path.basename(p).startswith(("train_", "marching_")))   # those: tests/test_train_oracle.py, test_marching_tets.py
 
 
 def _load(path):
