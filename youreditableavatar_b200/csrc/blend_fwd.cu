@@ -155,7 +155,13 @@ __global__ void __launch_bounds__(BL_THREADS, 4) blend_fwd_kernel(const __grid_c
     if (!warp_done) {
       const uint32_t base_pos = (uint32_t)(b * BL_BATCH);
       int longest;
-      const int ncand = cons_classify(0, min(BL_BATCH, total - b * BL_BATCH), s_xy[stage], s_list[warp], bx0, by0, lane, longest);
+      // sub-blocks all of whose pixels have terminated take no more candidates
+      const uint32_t live = ~__ballot_sync(0xffffffffu, done);
+      uint32_t group_live = 0;
+#pragma unroll
+      for (int g = 0; g < SUB_GROUPS; ++g) group_live |= ((live >> (g * SUB_LANES)) & ((1u << SUB_LANES) - 1u)) ? (1u << g) : 0u;
+      const int ncand = cons_classify(0, min(BL_BATCH, total - b * BL_BATCH), s_xy[stage], s_list[warp], bx0, by0, lane, longest,
+                                      group_live);
       const uint8_t* cand8 = s_list[warp] + group * LIST_BYTES;
       // Candidates are taken CAND_GROUP at a time (one 32-bit load = four batch-local indices): their loads,
       // power and exp are independent (ILP), only the transmittance update is a serial chain.  Profiling showed

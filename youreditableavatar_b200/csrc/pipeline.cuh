@@ -189,8 +189,10 @@ __device__ __forceinline__ void lane_pixel(int warp, int lane, int& x, int& y, i
 // entries behind the block's last contributor, see blend_bwd.cu).  first_included: entries below are ignored.
 // (bx0, by0) is the pixel origin of the warp's 8x4 block.  Writes SUB_GROUPS lists (lists[g*LIST_BYTES ...]) and
 // returns, per lane, the padded length of ITS group's list; `longest` is the warp-wide maximum.
+// group_live: bit g set = sub-block g still has a pixel that can take contributions (the forward switches a sub-block
+// off once all of its pixels have terminated: a tile on the silhouette keeps a few pixels alive deep into its list).
 __device__ __forceinline__ int cons_classify(int first_included, int first_excluded, const float4* s_xy, uint8_t* lists,
-                                             float bx0, float by0, int lane, int& longest) {
+                                             float bx0, float by0, int lane, int& longest, uint32_t group_live = 0xfu) {
   uint32_t cnt[SUB_GROUPS];
 #pragma unroll
   for (int g = 0; g < SUB_GROUPS; ++g) cnt[g] = 0;
@@ -206,7 +208,8 @@ __device__ __forceinline__ int cons_classify(int first_included, int first_exclu
 #pragma unroll
     for (int g = 0; g < SUB_GROUPS; ++g) {
       const float sx0 = (float)((g % SUB_GX) * SUB_W), sy0 = (float)((g / SUB_GX) * SUB_H);
-      const bool hit = (x_lo <= sx0 + (float)(SUB_W - 1)) && (x_hi >= sx0) && (y_lo <= sy0 + (float)(SUB_H - 1)) && (y_hi >= sy0);
+      const bool hit = ((group_live >> g) & 1u) && (x_lo <= sx0 + (float)(SUB_W - 1)) && (x_hi >= sx0) &&
+                       (y_lo <= sy0 + (float)(SUB_H - 1)) && (y_hi >= sy0);
       const uint32_t bal = __ballot_sync(0xffffffffu, hit);
       if (hit) lists[g * LIST_BYTES + cnt[g] + __popc(bal & lt)] = (uint8_t)e;
       cnt[g] += __popc(bal);
