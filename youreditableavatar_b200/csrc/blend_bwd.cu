@@ -27,7 +27,8 @@
 
 namespace tgr {
 
-constexpr int BL_STAGES = 4;  // shared-memory ring depth (how far consumers may drift apart)
+constexpr int BL_STAGES = 4;  // shared-memory ring depth = batches of a work unit: every batch of a unit has its own stage
+static_assert(BL_STAGES * BL_BATCH >= SEG, "a work unit must fit the ring: pairs carried over batches refer to their stage");
 
 __device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(BL_THREADS, 4) blend_bwd_kernel(const __grid_c
 
   // Commits the oldest min(32, npairs) pairs of the ring: ordered update of the per-pixel recurrences, then the
   // gradient arithmetic and the reductions at full width.
-  auto commit = [&](int stage, int batch_first_pos) {
+  auto commit = [&]() {
     const int n = min(npairs, 32);
     const bool act = lane < n;
     uint32_t pw = 0;
@@ -189,6 +190,7 @@ __global__ void __launch_bounds__(BL_THREADS, 4) blend_bwd_kernel(const __grid_c
     }
     const int j = (int)(pw & 127u);
     const int pix = (int)((pw >> 7) & 31u);
+    const int stage = (int)((pw >> 12) & 3u);   // the ring stage the pair's records sit in (pairs are carried over batches)
     const float4 con_o = s_co[stage][j];
     const float4 cd = s_cd[stage][j];
     const float alpha = min(0.99f, con_o.w * G);
@@ -238,7 +240,6 @@ __global__ void __launch_bounds__(BL_THREADS, 4) blend_bwd_kernel(const __grid_c
       if (EXTRAS) red_add_v2(row + 8, w * dp.z, gz);
       else atomicAdd(row + 8, w * dp.z);
     }
-    (void)batch_first_pos;
     phead = (phead + n) & (PB_CAP - 1);
     npairs -= n;
   };
@@ -281,17 +282,18 @@ __global__ void __launch_bounds__(BL_THREADS, 4) blend_bwd_kernel(const __grid_c
           const float alpha = min(0.99f, con_o.w * G);
           ok = ok && (power <= 0.0f) && (alpha >= 1.0f / 255.0f);
           const uint32_t bal = __ballot_sync(0xffffffffu, ok);
-          if (ok) ws.pairs[(phead + npairs + __popc(bal & lt)) & (PB_CAP - 1)] = make_uint2((uint32_t)j | ((uint32_t)pix << 7), __float_as_uint(G));
+          if (ok) ws.pairs[(phead + npairs + __popc(bal & lt)) & (PB_CAP - 1)] = make_uint2((uint32_t)j | ((uint32_t)pix << 7) | ((uint32_t)stage << 12), __float_as_uint(G));
           npairs += __popc(bal);
           __syncwarp();
-          if (npairs >= 32) commit(stage, batch_first_pos);
+          if (npairs >= 32) commit();
         }
       }
-      while (npairs > 0) commit(stage, batch_first_pos);   // the stage is released below: nothing may refer to it any more
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&s_empty[stage]);
+    // Pairs that do not fill a commit round are carried into the next batch.  Their records stay valid: a work unit is
+    // at most SEG = BL_STAGES * BL_BATCH entries long, so no ring stage is ever refilled within a unit (the producer
+    // never has to wait for empty[], which is why nothing arrives on it here).
   }
+  while (npairs > 0) commit();
 }
 
 int launch_blend_bwd(const RenderBatch& rb, bool extras, bool debug, cudaStream_t s) {
