@@ -24,6 +24,10 @@ NVCC_FLAGS = [
 ]
 
 
+# experiments only (e.g. TGR_NVCC_DEFINES="-DTGR_MEASURE_STAGING"): extra -D flags, part of the build digest
+EXTRA = os.environ.get("TGR_NVCC_DEFINES", "").split()
+
+
 def _digest() -> str:
     h = hashlib.sha256()
     files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
@@ -31,7 +35,7 @@ def _digest() -> str:
     for f in files:
         with open(f, "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + EXTRA).encode())
     return h.hexdigest()
 
 
@@ -53,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc()] + NVCC_FLAGS + EXTRA + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, pr in procs:

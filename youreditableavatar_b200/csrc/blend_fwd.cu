@@ -24,6 +24,14 @@
 
 namespace tgr {
 
+#ifdef TGR_MEASURE_STAGING
+// Experiment (profiles/r02_staging_wait.txt): how long do the consumer warps of the forward wait for staged data?  That
+// is the most any faster staging — a tile-ordered packed record stream moved by cp.async.bulk / TMA instead of 16-byte
+// LDGSTS gathers — could win.  [0] cycles consumers spent blocked on full[], [1] all consumer cycles, [2] cycles the
+// producer spent blocked on empty[] (back-pressure: data was ready earlier than needed), [3] all producer cycles.
+__device__ unsigned long long g_staging_cycles[4];
+#endif
+
 constexpr int BL_STAGES = 4;  // shared-memory ring depth (how far consumers may drift apart)
 
 
@@ -105,6 +113,10 @@ __global__ void __launch_bounds__(BL_THREADS, 4) blend_fwd_kernel(const __grid_c
   if (tid < BL_STAGES) init_pad_record(s_xy[tid], s_co[tid], s_cd[tid]);
   __syncthreads();
 
+#ifdef TGR_MEASURE_STAGING
+  const long long t_begin = clock64();
+  long long t_wait = 0;
+#endif
   if (warp == 8) {
     // ======================= PRODUCER: a pure data mover =======================
     auto stop = [&](int stage) {
@@ -114,6 +126,9 @@ __global__ void __launch_bounds__(BL_THREADS, 4) blend_fwd_kernel(const __grid_c
     };
     producer_loop<BL_STAGES, false, false>(point_list + range.x, total, rounds, xy_ext, conic_opacity, rgb_depth, s_xy,
                                              s_co, s_cd, nullptr, s_full, s_empty, lane, stop);
+#ifdef TGR_MEASURE_STAGING
+    if (lane == 0) atomicAdd(&g_staging_cycles[3], (unsigned long long)(clock64() - t_begin));
+#endif
     return;
   }
 
@@ -150,7 +165,13 @@ __global__ void __launch_bounds__(BL_THREADS, 4) blend_fwd_kernel(const __grid_c
       warp_done = true;
       if (lane == 0) atomicAdd(&s_done_warps, 1u);
     }
+#ifdef TGR_MEASURE_STAGING
+    const long long t_w0 = clock64();
+#endif
     mbar_wait(&s_full[stage], (b / BL_STAGES) & 1);
+#ifdef TGR_MEASURE_STAGING
+    t_wait += clock64() - t_w0;
+#endif
     if (*(volatile uint32_t*)&s_stop[stage]) break;
     if (!warp_done) {
       const uint32_t base_pos = (uint32_t)(b * BL_BATCH);
@@ -222,6 +243,12 @@ __global__ void __launch_bounds__(BL_THREADS, 4) blend_fwd_kernel(const __grid_c
       out_alpha[pix_id] = 1.0f - T;
     }
   }
+#ifdef TGR_MEASURE_STAGING
+  if (lane == 0) {
+    atomicAdd(&g_staging_cycles[0], (unsigned long long)t_wait);
+    atomicAdd(&g_staging_cycles[1], (unsigned long long)(clock64() - t_begin));
+  }
+#endif
   // tile-wide maximum of last_contributor: lets the backward start at the last useful list entry
   const uint32_t wl = __reduce_max_sync(0xffffffffu, inside ? last_contributor : 0u);
   if (lane == 0) s_last[warp] = wl;
@@ -233,6 +260,20 @@ __global__ void __launch_bounds__(BL_THREADS, 4) blend_fwd_kernel(const __grid_c
     tile_last[tile_id] = m;
   }
 }
+
+#ifdef TGR_MEASURE_STAGING
+extern "C" int tgr_debug_staging_cycles(unsigned long long out[4], int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_staging_cycles, sizeof(g_staging_cycles));
+  cudaMemcpyFromSymbol(&out[2], g_producer_empty_wait, sizeof(unsigned long long));
+  if (reset) {
+    unsigned long long z[4] = {0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_staging_cycles, z, sizeof(z));
+    cudaMemcpyToSymbol(g_producer_empty_wait, z, sizeof(unsigned long long));
+  }
+  return 0;
+}
+#endif
 
 int launch_blend_fwd(const RenderBatch& rb, bool extras, bool debug, cudaStream_t s) {
   if (int rc = launch_tile_order(rb, s)) return rc;

@@ -359,6 +359,10 @@ __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
 }
 constexpr int BAR_EPILOGUE = 1;
 
+#ifdef TGR_MEASURE_STAGING
+static __device__ unsigned long long g_producer_empty_wait;   // cycles producers spent blocked on empty[] (per translation unit)
+#endif
+
 template <int STAGES, bool REVERSE, bool WITH_IDS, typename StopFn>
 __device__ __forceinline__ void producer_loop(const uint32_t* __restrict__ list, int total, int rounds,
                                               const float4* __restrict__ xy_ext, const float4* __restrict__ conic_opacity,
@@ -370,7 +374,13 @@ __device__ __forceinline__ void producer_loop(const uint32_t* __restrict__ list,
   prod_load_ids(list, total, 0, REVERSE, lane, ids);
   for (int k = 0; k < rounds; ++k) {
     const int st = k % STAGES;
+#ifdef TGR_MEASURE_STAGING
+    const long long t_e0 = clock64();
+#endif
     if (k >= STAGES) mbar_wait(&s_empty[st], ((k / STAGES) - 1) & 1);
+#ifdef TGR_MEASURE_STAGING
+    if (lane == 0) atomicAdd(&g_producer_empty_wait, (unsigned long long)(clock64() - t_e0));
+#endif
     if (stop(st)) {
       cp_async_wait<0>();
       __syncwarp();
