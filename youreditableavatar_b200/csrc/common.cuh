@@ -16,8 +16,14 @@ __host__ __device__ inline uint64_t align_up(uint64_t x, uint64_t a) { return (x
 // ---------------------------------------------------------------------------------------------
 // Radix sort plan / temp layout (sort.cu)
 // ---------------------------------------------------------------------------------------------
-constexpr int RS_THREADS = 256;
-constexpr int RS_IPT = 16;
+#ifndef RS_THREADS_
+#define RS_THREADS_ 256
+#endif
+#ifndef RS_IPT_
+#define RS_IPT_ 16
+#endif
+constexpr int RS_THREADS = RS_THREADS_;
+constexpr int RS_IPT = RS_IPT_;
 constexpr int RS_TILE = RS_THREADS * RS_IPT;  // 4096 pairs per CTA
 constexpr int RS_BINS = 256;
 constexpr int RS_MAX_PASSES = 4;
