@@ -272,9 +272,11 @@ class HostFeeder:
 
 
 class BatchFeeder:
-    """Host->device traffic of the e2e leg for the multi-view batch, double-buffered: while step k renders, the
-    cameras (one packed block) and the uint8 target images of step k+1 are copied from pinned host memory on a side
-    stream; every step consumes its own fresh copy."""
+    """Host->device traffic of the e2e leg for the multi-view batch, double-buffered: while step k runs its backward,
+    the cameras (one packed block) and the uint8 target images of step k+1 are copied from pinned host memory on a
+    side stream; every step consumes its own fresh copy.  (The copy is issued behind the forward, not at the start of the
+    step: concurrent with the forward's HBM-bound per-Gaussian and sort kernels it cost the step ~0.15 ms at N = 1 and
+    0.3-0.5 ms at N = 8, where eight ranks pull from host memory at once; the blend backward is not HBM-bound.)"""
 
     def __init__(self, host_cams, targets_host):
         self.cams, self.targets = host_cams, targets_host
@@ -300,18 +302,23 @@ class BatchFeeder:
         return cams, tgt, ev
 
     def begin_step(self):
-        if self.pending is None:
+        if self.pending is None:          # first step (or a caller that never prefetched)
             self.pending = self._issue()
         self.cur = self.pending
-        # inputs of the NEXT step start streaming now; their buffers must not be recycled under this step's kernels
-        self.s_in.wait_stream(torch.cuda.current_stream())
-        self.pending = self._issue()
+        self.pending = None
         torch.cuda.current_stream().wait_event(self.cur[2])
         self.keep = [self.cur]
         return self.cur[0]
 
     def targets_dev(self):
         return self.cur[1]
+
+    def prefetch_next(self):
+        """Called once forward and loss are queued: inputs of the NEXT step start streaming behind them (under the blend
+        backward, which is not HBM-bound); their buffers must not be recycled under this step's kernels."""
+        if self.pending is None:
+            self.s_in.wait_stream(torch.cuda.current_stream())
+            self.pending = self._issue()
 
     def end_step(self, result):
         return self.reader.push(result)
@@ -335,14 +342,46 @@ class OursRunner:
             (SymmGradBucket if comm in ("nvls", "nvls_sh") else GradBucket)(P, 16, "cuda", names=GradBucket.TRAINING)
         self.loss_ws = None   # workspace of the image-loss kernels (e2e leg), allocated on first use
 
+    # TGR_STEP_DIAG=1: CUDA events at step start / forward done / upstream done / step done, printed per rank at exit
+    diag = os.environ.get("TGR_STEP_DIAG") == "1"
+    diag_events = []
+
+    @classmethod
+    def diag_report(cls, rank):
+        torch.cuda.synchronize()
+        for leg in ("value", "e2e"):
+            ev = [e[1] for e in cls.diag_events if e[0] == leg]
+            ev = ev[len(ev) // 2:]                                # second half: the timed part of the leg
+            if not ev:
+                continue
+            seg = [sum(a.elapsed_time(b) for a, b in zip([e[i] for e in ev], [e[i + 1] for e in ev])) / len(ev) for i in range(3)]
+            gap = sum(ev[k][3].elapsed_time(ev[k + 1][0]) for k in range(len(ev) - 1)) / max(len(ev) - 1, 1)
+            print("[diag rank %d %5s] forward %.3f  upstream %.3f  backward+exchange %.3f  gap to next step %.3f ms (%d steps)" % (
+                rank, leg, seg[0], seg[1], seg[2], gap, len(ev)), file=sys.stderr)
+
+    def _mark(self, evs):
+        if self.diag:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            evs.append(e)
+
     def step(self, cams, ups, world, feeder=None):
         from youreditableavatar_b200.parallel import render_views_fwd_bwd
+        evs = []
+        self._mark(evs)
         if feeder is not None:
             cams = feeder.begin_step()
 
         box = {}
 
         def upstream(color, depth, alpha):
+            self._mark(evs)
+            try:
+                return upstream_(color, depth, alpha)
+            finally:
+                self._mark(evs)
+
+        def upstream_(color, depth, alpha):
             if feeder is None:
                 return ups if self.extras else (ups[0], None, None)
             # same loss as image_loss() below (what the reference arm evaluates with torch ops): the colour MSE against
@@ -361,6 +400,7 @@ class OursRunner:
                 dLd = depth * (1e-3 / depth.numel())
                 dLa = cov * (1.0 / alpha.numel())
             box["loss"] = loss
+            feeder.prefetch_next()
             return dLc, dLd, dLa
 
         if self.comm in ("rows", "sh", "nvls_sh"):   # all-reduces issued range by range from inside the backward
@@ -370,6 +410,9 @@ class OursRunner:
         else:
             render_views_fwd_bwd(self.act, cams, 3, upstream, self.bucket, extras=self.extras, n_streams=self.n_streams)
             self.bucket.all_reduce()
+        self._mark(evs)
+        if self.diag:
+            OursRunner.diag_events.append(("value" if feeder is None else "e2e", evs))
         if feeder is not None:
             return feeder.end_step(box["loss"])   # D2H read of the step's loss
         return None
@@ -559,6 +602,7 @@ def train_step_ours(P, res, act, cams, targets_host, V, steps, warmup, peak):
     def upstream(color, depth, alpha):
         out, grad = loss_utils.image_loss_and_grad(color, feeder.targets_dev(), 0.8, 0.0, 0.2, workspace=ws)
         box["loss"] = out[0]
+        feeder.prefetch_next()
         return grad, None, None
 
     def step():
@@ -925,6 +969,8 @@ def main():
             return
 
     m = measure(cfg, V, args, world, rank, local, args.steps, args.warmup, full=True)
+    if OursRunner.diag:
+        OursRunner.diag_report(rank)
     P, res, act, cams, targets_host, runner = m.pop("_keep")
     batched = ours and not args.per_view_api
 
