@@ -45,6 +45,15 @@ __device__ __forceinline__ EmitItems emit_load(const RenderView& rv, uint32_t ti
 // cycles at the barrier behind the look-back, 0.22 ms for 8 views.  Three dependency-free launches are faster.)
 __global__ void __launch_bounds__(EMIT_THREADS) emit_count_kernel(const __grid_constant__ RenderBatch rb) {
   const RenderView& rv = rb.v[blockIdx.y];
+  // on the side: clear the temp area of the tile sort that follows (histograms, tickets, look-back flags), CTA b its
+  // slice b — a memset node per view less (the grid covers the largest view: every CTA takes part, also the surplus ones)
+  {
+    const uint32_t words = rv.tile_sort_zero_words;
+    const uint32_t per = ((words + gridDim.x - 1) / gridDim.x + 3u) & ~3u;
+    const uint32_t lo = blockIdx.x * per, hi = min(lo + per, words);
+    uint4* t4 = reinterpret_cast<uint4*>(rv.tile_sort_temp);
+    for (uint32_t i = lo / 4 + threadIdx.x; i * 4 < hi; i += blockDim.x) t4[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
   if ((uint32_t)blockIdx.x * EMIT_TILE >= (uint32_t)rv.P) return;   // the grid is sized for the largest view
   __shared__ uint32_t s_warp[EMIT_THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -66,11 +75,6 @@ __global__ void __launch_bounds__(1024) emit_scan_kernel(const __grid_constant__
   // this CTA is the one per-view launch that precedes the tile sort: it also clears the view's tile ranges
   // (ranges_kernel only writes the boundaries it finds), which saves a memset node per view
   for (uint32_t t = threadIdx.x; t < rv.T; t += blockDim.x) rv.ranges[t] = make_uint2(0u, 0u);
-  // ... and the temp area of the tile sort (histograms, tickets, look-back flags): another memset node per view less
-  {
-    uint4* t4 = reinterpret_cast<uint4*>(rv.tile_sort_temp);
-    for (uint32_t i = threadIdx.x; i * 4 < rv.tile_sort_zero_words; i += blockDim.x) t4[i] = make_uint4(0u, 0u, 0u, 0u);
-  }
   const uint32_t ntiles = ((uint32_t)rv.P + EMIT_TILE - 1) / EMIT_TILE;
   if (ntiles == 0) return;
   uint32_t* __restrict__ st = rv.scan_state;

@@ -247,7 +247,7 @@ static int render_group(const tgr_params* views, const uint64_t* caps, int32_t n
       sb.s[k] = SortSeg{b.key_a, b.val_a, b.key_b, b.val_b, b.sort_temp, &g.header->num_rendered, rb.v[k].cap};
     }
     prof_begin(TGR_STAGE_TILE_SORT, s);
-    if (int rc = launch_sort_pairs_batch(sb, false, 0, tile_bits(T0), s, nullptr, /*temp_is_zero=*/true)) return rc;   // emit_scan_kernel
+    if (int rc = launch_sort_pairs_batch(sb, false, 0, tile_bits(T0), s, nullptr, /*temp_is_zero=*/true)) return rc;   // emit_count_kernel
     prof_end(TGR_STAGE_TILE_SORT, s);
   }
   prof_begin(TGR_STAGE_RANGES, s);

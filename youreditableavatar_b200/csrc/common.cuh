@@ -244,7 +244,7 @@ struct RenderView {
   // binning
   uint32_t* key_a;
   uint32_t* val_a;
-  uint32_t* tile_sort_temp;      // temp area of the tile sort; its leading tile_sort_zero_words are cleared by emit_scan
+  uint32_t* tile_sort_temp;      // temp area of the tile sort; its leading tile_sort_zero_words are cleared by emit_count
   uint32_t tile_sort_zero_words;
   const uint32_t* sorted_keys;   // tile ids after the tile sort
   const uint32_t* point_list;    // Gaussian ids after the tile sort

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) radix_hist_kernel(const __grid_constant__
 
 // clears the leading words of every segment's temp area (histograms, tickets, look-back): one launch for the batch
 // where V cudaMemsetAsync nodes used to be.  The rasterizer's own sorts do not even need it: the kernel in front of
-// them clears the area on the side (preprocess_kernel for the depth sort, emit_scan_kernel for the tile sort).
+// them clears the area on the side (preprocess_kernel for the depth sort, emit_count_kernel for the tile sort).
 __global__ void __launch_bounds__(256) radix_zero_kernel(const __grid_constant__ SortBatch sb, int npasses) {
   const SortSeg& seg = sb.s[blockIdx.y];
   if (seg.n_host == 0) return;
