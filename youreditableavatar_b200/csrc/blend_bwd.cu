@@ -10,14 +10,15 @@
 //     tail beyond the tile's last contributor (tile_last) is not even staged;
 //   * same producer warp / mbarrier ring as the forward;
 //   * PAIR-CENTRIC consumers (pipeline.cuh): a warp owns two pixel rows of the tile, but its lanes stand for (entry,
-//     pixel) candidates inside the entry's ellipse and then for surviving pairs, not for pixels.  The first version mapped pixels to lanes and walked
-//     the candidates in a loop: ncu showed its gradient block running with 5.8 of 32 lanes active and 1.5 G warp
-//     instructions per 8-view batch (2.17 ms).  Here the alpha evaluation runs on 32 candidates per instruction and
-//     the gradient arithmetic + reductions on 32 surviving pairs per instruction; the per-pixel recurrences
-//     (transmittance, colour behind) live in shared memory and are the only serialised part;
-//   * the backward evaluates exp / reciprocal with the hardware approximations (ex2.approx, rcp.approx): the gradient
-//     tolerance is relative L2 1e-3, the approximations are good to ~1e-7 relative.  (The forward stays IEEE: its
-//     alpha >= 1/255 and T < 1e-4 decisions define n_contrib, which is compared bit for bit.)
+//     pixel) candidates — the pixels of the entry's ellipse on the rows' live columns — and then for surviving pairs,
+//     not for pixels.  The first version mapped pixels to lanes and walked the candidates in a loop: ncu showed its
+//     gradient block running with 5.8 of 32 lanes active and 1.5 G warp instructions per 8-view batch (2.17 ms).
+//     Here the alpha evaluation runs on 32 candidates per instruction and the gradient arithmetic + reductions on 32
+//     surviving pairs per instruction; the per-pixel recurrences (transmittance, colour behind) live in shared
+//     memory and are the only serialised part (1.08 G warp instructions, 1.69 ms);
+//   * the backward evaluates exp / reciprocal with the hardware approximations (ex2.approx, rcp.approx) and this file
+//     is compiled with fast-math (build.py): the gradient tolerance is relative L2 1e-3, measured ~1e-6.  (The forward
+//     stays IEEE: its alpha >= 1/255 and T < 1e-4 decisions define n_contrib, which is compared bit for bit.)
 //   * gradients are committed per pair with 16-byte VECTOR reductions (red.global.add.v4.f32) into one packed
 //     accumulator row grad_acc[g][12] = {dmean2D.xy, dconic.xx/xy/yy, dopacity, drgb, dz, -, -};
 //   * extras: gradients of the depth / alpha images flow through the same recurrence.
