@@ -252,3 +252,59 @@ def test_fused_adam_host_logic_with_a_recording_library(monkeypatch):
     sd["param_groups"][1]["betas"] = (0.5, 0.999)
     with pytest.raises(RuntimeError, match="shared by all groups"):
         opt.load_state_dict(sd)
+
+
+def test_binning_capacity_inverts_binning_bytes():
+    """tgr_binning_capacity (pure host function): the backward of a forward that was launched from a capacity hint recovers
+    the buffer layout from the buffer's size.  For every capacity c: capacity(bytes(c)) >= c, it reproduces the same size
+    (every layout component is monotone in the capacity, so equal size means equal layout), and it never overshoots into
+    the next size."""
+    import random
+    from youreditableavatar_b200 import _lib
+    L = _lib.lib()
+    rng = random.Random(0)
+    for P, W, H in [(0, 16, 16), (10_000, 256, 256), (1_000_000, 1024, 1024), (4_000_000, 2048, 2048), (777, 77, 45)]:
+        for c in [0, 1, 31, 32, 33, 511, 512, 4095, 4096, 4097, 65_536] + [rng.randrange(0, 20_000_000) for _ in range(40)]:
+            b = L.tgr_binning_bytes(P, c, W, H)
+            back = L.tgr_binning_capacity(P, b, W, H)
+            assert back >= c and L.tgr_binning_bytes(P, back, W, H) == b, (P, W, H, c, back)
+            assert L.tgr_binning_bytes(P, back + 1, W, H) > b
+        assert L.tgr_binning_capacity(P, 0, W, H) == 0
+
+
+def test_depth_key_bits_from_the_header_mirror():
+    from youreditableavatar_b200 import rasterizer as rz
+    import struct
+    bits = lambda f: struct.unpack("<I", struct.pack("<f", f))[0]
+    # depths in [2, 4): sign and exponent shared -> at most 23 bits differ
+    ks = [bits(z) for z in (2.0, 2.5, 3.999, 3.1)]
+    o, a = 0, 0xffffffff
+    for k in ks:
+        o |= k
+        a &= k
+    assert rz.depth_bits_needed([0, 0, 0, 0, o, a, 0, 0]) <= 23
+    # across an exponent boundary more bits differ; identical keys (or none: OR = 0, AND = all ones masks to 32) are handled
+    o, a = bits(1.9) | bits(2.1), bits(1.9) & bits(2.1)
+    assert 24 <= rz.depth_bits_needed([0, 0, 0, 0, o, a, 0, 0]) <= 31
+    assert rz.depth_bits_needed([0, 0, 0, 0, bits(3.0), bits(3.0), 0, 0]) == 1
+    assert rz.depth_bits_needed([0, 0, 0, 0, 0, -1, 0, 0]) == 32       # no visible Gaussian: int32 mirror holds -1
+    with pytest.raises(RuntimeError, match="Point is filtered although prefiltered is set"):
+        rz.check_prefilter([5, 0, 5, 1, 0, 0, 0, 0])
+
+
+def test_direct_binding_struct_and_marching_tets_sizes():
+    from youreditableavatar_b200 import _lib
+    from youreditableavatar_b200.binding import DirectBinding, _binding_struct
+    L = _lib.lib()
+    keep, eo, en = torch.zeros(5, 3), torch.ones(7, 3), torch.ones(7, 3)
+    b = DirectBinding.from_keep_edit(keep, eo, en, device="cpu")
+    assert b.n_frozen == 5 and b.origins.shape == (12, 3) and float(b.normals[:5].abs().sum()) == 0.0
+    act = {k: torch.zeros(12, n) for k, n in (("means3D", 3), ("scales", 3), ("rotations", 4), ("opacities", 1))}
+    s = _binding_struct(b, None, torch.zeros(12, 3), torch.zeros(12, 4), torch.zeros(12), act)
+    assert s.origins == b.origins.data_ptr() and s.normals == b.normals.data_ptr() and s.n_frozen == 5
+    assert not s.delta and not s.faces and not s.verts            # direct form: no mesh, no offsets
+    flat = DirectBinding.from_keep_edit(keep, eo, None, device="cpu")
+    assert flat.normals is None and not _binding_struct(flat, None, torch.zeros(12, 3), torch.zeros(12, 4), torch.zeros(12), act).normals
+    # marching-tets workspaces: pure size functions, monotone
+    assert L.tgr_mt_classify_bytes(0) > 0 and L.tgr_mt_classify_bytes(10_000_000) > L.tgr_mt_classify_bytes(1_000_000)
+    assert L.tgr_mt_edges_bytes(2_000_000) > L.tgr_mt_edges_bytes(1_000)
