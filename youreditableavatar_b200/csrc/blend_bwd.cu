@@ -54,12 +54,16 @@ struct BwdWarpState {
   uint2 pairs[PB_CAP];            // {entry | pixel << 7, G bits}
   float4 tb[32];                  // per pixel: T (after the current entry), colour behind B.rgb
   float4 dpix[32];                // per pixel: dL/dcolour rgb, dL/ddepth
-  float4 misc[32];                // per pixel: Bz (depth behind), tail, T_final, -
+  float2 tf[32];                  // per pixel: tail, T_final (constants of the unit)
+  float bz[32];                   // per pixel: depth behind
   int last[32];                   // per pixel: last contributor (1-based list position)
 };
 
 template <bool EXTRAS>
-__global__ void __launch_bounds__(BL_THREADS, 4) blend_bwd_kernel(const __grid_constant__ RenderBatch rb) {
+#ifndef TGR_BWD_MIN_CTAS
+#define TGR_BWD_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(BL_THREADS, TGR_BWD_MIN_CTAS) blend_bwd_kernel(const __grid_constant__ RenderBatch rb) {
   const RenderView& rv = rb.v[blockIdx.y];   // one launch serves every view of the batch
   const uint2* __restrict__ units = rv.units;
   const uint32_t* __restrict__ unit_count = rv.unit_count;
@@ -168,7 +172,8 @@ __global__ void __launch_bounds__(BL_THREADS, 4) blend_bwd_kernel(const __grid_c
     if (EXTRAS) tail -= dalp;
     ws.tb[lane] = make_float4(T, B0, B1, B2);
     ws.dpix[lane] = make_float4(dp0, dp1, dp2, ddep);
-    ws.misc[lane] = make_float4(Bz, tail, T_final, 0.f);
+    ws.tf[lane] = make_float2(tail, T_final);
+    ws.bz[lane] = Bz;
     ws.last[lane] = last_contributor;
   }
   __syncwarp();
@@ -200,7 +205,7 @@ __global__ void __launch_bounds__(BL_THREADS, 4) blend_bwd_kernel(const __grid_c
     const uint32_t peers = __match_any_sync(0xffffffffu, act ? pix : 32 + lane);
     const int rank = __popc(peers & lt);
     const int maxrank = __reduce_max_sync(0xffffffffu, act ? rank : 0);
-    float Ti = 0.f, Bb0 = 0.f, Bb1 = 0.f, Bb2 = 0.f, Bbz = 0.f, tail = 0.f, T_final = 0.f;
+    float Ti = 0.f, Bb0 = 0.f, Bb1 = 0.f, Bb2 = 0.f, Bbz = 0.f;
     for (int r = 0; r <= maxrank; ++r) {
       if (act && rank == r) {
         // T holds the transmittance AFTER this entry; Ti before it.  B = (unnormalised) colour blended behind it.
@@ -209,14 +214,16 @@ __global__ void __launch_bounds__(BL_THREADS, 4) blend_bwd_kernel(const __grid_c
         const float w = alpha * Ti;
         Bb0 = tb.y; Bb1 = tb.z; Bb2 = tb.w;
         ws.tb[pix] = make_float4(Ti, fmaf(cd.x, w, tb.y), fmaf(cd.y, w, tb.z), fmaf(cd.z, w, tb.w));
-        const float4 mi = ws.misc[pix];
-        Bbz = mi.x; tail = mi.y; T_final = mi.z;
-        if (EXTRAS) ws.misc[pix].x = fmaf(cd.w, w, mi.x);
+        if (EXTRAS) {
+          Bbz = ws.bz[pix];
+          ws.bz[pix] = fmaf(cd.w, w, Bbz);
+        }
       }
       __syncwarp();
     }
     if (act) {
       const float4 dp = ws.dpix[pix];
+      const float2 tf = ws.tf[pix];
       const float4 g = s_xy[stage][j];
       const float dx = g.x - (float)(bx0 + (pix & 15)), dy = g.y - (float)(by0 + (pix >> 4));
       const float w = alpha * Ti;
@@ -227,7 +234,7 @@ __global__ void __launch_bounds__(BL_THREADS, 4) blend_bwd_kernel(const __grid_c
         dL_dalpha += (cd.w * Ti - Bbz * rinv) * dp.w;
         gz = w * dp.w;
       }
-      dL_dalpha += (-T_final * rinv) * tail;
+      dL_dalpha += (-tf.y * rinv) * tf.x;
       // the 0.99 cap is straight-through in the reference (backward.cu:494-497 recomputes alpha with the min)
       const float dL_dG = con_o.w * dL_dalpha;
       const float gdx = G * dx;
