@@ -52,10 +52,8 @@ __device__ __forceinline__ float rcp_approx(float x) {
 struct BwdWarpState {
   uint32_t hits[BL_BATCH];        // hit words of the current batch
   uint2 pairs[PB_CAP];            // {entry | pixel << 7, G bits}
-  float4 tb[32];                  // per pixel: T (after the current entry), colour behind B.rgb
+  float2 ts[32];                  // per pixel: T (after the current entry), S = <dL/dpixel, blended behind> + T_final * tail
   float4 dpix[32];                // per pixel: dL/dcolour rgb, dL/ddepth
-  float2 tf[32];                  // per pixel: tail, T_final (constants of the unit)
-  float bz[32];                   // per pixel: depth behind
   int last[32];                   // per pixel: last contributor (1-based list position)
 };
 
@@ -170,10 +168,13 @@ __global__ void __launch_bounds__(BL_THREADS, TGR_BWD_MIN_CTAS) blend_bwd_kernel
     // d(out)/dalpha_i through the final transmittance: colour gets +T_final*bg, the alpha image -T_final
     float tail = bg[0] * dp0 + bg[1] * dp1 + bg[2] * dp2;
     if (EXTRAS) tail -= dalp;
-    ws.tb[lane] = make_float4(T, B0, B1, B2);
+    // Only the inner product of "blended behind" with the pixel's upstream gradient enters dL/dalpha, so the
+    // recurrence carries that scalar instead of the four channels; the final-transmittance term has the same
+    // 1/(1-alpha) factor and is folded into its start value.
+    float S = B0 * dp0 + B1 * dp1 + B2 * dp2 + T_final * tail;
+    if (EXTRAS) S = fmaf(Bz, ddep, S);
+    ws.ts[lane] = make_float2(T, S);
     ws.dpix[lane] = make_float4(dp0, dp1, dp2, ddep);
-    ws.tf[lane] = make_float2(tail, T_final);
-    ws.bz[lane] = Bz;
     ws.last[lane] = last_contributor;
   }
   __syncwarp();
@@ -201,40 +202,46 @@ __global__ void __launch_bounds__(BL_THREADS, TGR_BWD_MIN_CTAS) blend_bwd_kernel
     const float4 cd = s_cd[stage][j];
     const float alpha = min(0.99f, con_o.w * G);
     const float rinv = rcp_approx(1.f - alpha);
+    const float4 dp = ws.dpix[pix];
+    float cdp = cd.x * dp.x + cd.y * dp.y + cd.z * dp.z;   // <colour (and depth) of the entry, upstream gradient of the pixel>
+    if (EXTRAS) cdp = fmaf(cd.w, dp.w, cdp);
     // pairs of this round that fall on the same pixel go one after the other, in list order (= lane order)
     const uint32_t peers = __match_any_sync(0xffffffffu, act ? pix : 32 + lane);
     const int rank = __popc(peers & lt);
     const int maxrank = __reduce_max_sync(0xffffffffu, act ? rank : 0);
-    float Ti = 0.f, Bb0 = 0.f, Bb1 = 0.f, Bb2 = 0.f, Bbz = 0.f;
-    for (int r = 0; r <= maxrank; ++r) {
-      if (act && rank == r) {
-        // T holds the transmittance AFTER this entry; Ti before it.  B = (unnormalised) colour blended behind it.
-        const float4 tb = ws.tb[pix];
-        Ti = tb.x * rinv;
-        const float w = alpha * Ti;
-        Bb0 = tb.y; Bb1 = tb.z; Bb2 = tb.w;
-        ws.tb[pix] = make_float4(Ti, fmaf(cd.x, w, tb.y), fmaf(cd.y, w, tb.z), fmaf(cd.z, w, tb.w));
-        if (EXTRAS) {
-          Bbz = ws.bz[pix];
-          ws.bz[pix] = fmaf(cd.w, w, Bbz);
-        }
+    // The recurrence of a pixel over its pairs of this round is a chain of affine maps of (T, S):
+    //   T' = m T,  S' = S + v T   with m = 1/(1-alpha), v = <c, dL/dpixel> alpha m;
+    // chains compose as (m1,v1) then (m2,v2) = (m1 m2, v1 + m1 v2), so every pair gets the composite of its pixel's
+    // earlier pairs by pointer jumping over the peer lanes: ceil(log2(longest chain)) shuffle steps instead of one
+    // shared-memory turn per chain link.
+    int prev = act ? 31 - __clz(peers & lt) : -1;     // the pixel's previous pair of this round (lane), -1: none
+    float M = act ? rinv : 1.f;
+    float Vv = act ? cdp * alpha * rinv : 0.f;
+    const float2 ts0 = ws.ts[pix];
+    for (int span = maxrank; span > 0; span >>= 1) {
+      const float Mp = __shfl_sync(0xffffffffu, M, prev);
+      const float Vp = __shfl_sync(0xffffffffu, Vv, prev);
+      const int pp = __shfl_sync(0xffffffffu, prev, prev);
+      if (prev >= 0) {
+        Vv = fmaf(Mp, Vv, Vp);
+        M *= Mp;
+        prev = pp;
       }
-      __syncwarp();
     }
+    const float Ti = ts0.x * M;                        // transmittance in front of the entry
+    const float Sa = fmaf(Vv, ts0.x, ts0.y);           // S with the entry included ...
+    const float Sb = fmaf(-cdp * alpha, Ti, Sa);       // ... and behind it
+    __syncwarp();
+    if (act && (peers >> lane) == 1u) ws.ts[pix] = make_float2(Ti, Sa);   // the pixel's last pair of this round
+    __syncwarp();
     if (act) {
-      const float4 dp = ws.dpix[pix];
-      const float2 tf = ws.tf[pix];
       const float4 g = s_xy[stage][j];
       const float dx = g.x - (float)(bx0 + (pix & 15)), dy = g.y - (float)(by0 + (pix >> 4));
       const float w = alpha * Ti;
-      // dC/dalpha_i = c_i*Ti - B/(1-alpha_i)   (same quantity as backward.cu:515-525's (c - accum_rec)*T)
-      float dL_dalpha = (cd.x * Ti - Bb0 * rinv) * dp.x + (cd.y * Ti - Bb1 * rinv) * dp.y + (cd.z * Ti - Bb2 * rinv) * dp.z;
-      float gz = 0.f;
-      if (EXTRAS) {
-        dL_dalpha += (cd.w * Ti - Bbz * rinv) * dp.w;
-        gz = w * dp.w;
-      }
-      dL_dalpha += (-tf.y * rinv) * tf.x;
+      // dC/dalpha_i = c_i*Ti - B/(1-alpha_i)   (same quantity as backward.cu:515-525's (c - accum_rec)*T), contracted
+      // with the upstream gradient; the -T_final/(1-alpha_i) * tail term (backward.cu:527-533) rides in S
+      const float dL_dalpha = cdp * Ti - Sb * rinv;
+      const float gz = EXTRAS ? w * dp.w : 0.f;
       // the 0.99 cap is straight-through in the reference (backward.cu:494-497 recomputes alpha with the min)
       const float dL_dG = con_o.w * dL_dalpha;
       const float gdx = G * dx;
