@@ -367,7 +367,10 @@ __global__ void __launch_bounds__(1024) unit_build_kernel(const __grid_constant_
     for (size_t i = tid; i < n4; i += 1024) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
-  if (tid == 0) unit_count[3] = 1u;
+  if (tid == 0) {
+    unit_count[3] = 1u;
+    unit_count[1] = 0u;   // ticket counter of blend_bwd's persistent CTAs (the one of view 0 serves the batch)
+  }
   for (uint32_t t0 = 0; t0 < T; t0 += 1024) {
     const uint32_t t = t0 + tid;
     uint32_t n = 0;

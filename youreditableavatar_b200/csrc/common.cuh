@@ -144,7 +144,8 @@ struct ImageView {
   float4* final_state;   // [N] (T_final, C_r, C_g, C_b) without background: end state of the forward recurrence
   float* final_z;        // [N] depth accumulator at the end of the forward (extras)
   uint32_t* seg_base;    // [T+1] first checkpoint slot of each tile (exclusive scan of ceil(len/SEG))
-  uint32_t* unit_count;  // [32] [0] number of backward work units of this view, [3] set once a backward has used the
+  uint32_t* unit_count;  // [32] [0] number of backward work units of this view, [1] ticket counter of blend_bwd's
+                         //      persistent CTAs (view 0's serves the batch), [3] set once a backward has used the
                          //      packed gradient rows (a repeated backward has to clear them itself)
   uint64_t bytes;
 };
