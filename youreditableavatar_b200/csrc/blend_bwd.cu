@@ -118,16 +118,21 @@ __global__ void __launch_bounds__(BL_THREADS, TGR_BWD_MIN_CTAS) blend_bwd_kernel
 
   if (warp == 8) {
     // ======================= PRODUCER =======================
-    // Persistent CTAs: work units (tile, segment) of ALL views of the batch are handed out through one ticket counter
-    // (unit_count[1] of view 0, zeroed by unit_build_kernel).  Per unit: publish its description, then gather its
+    // Persistent CTAs: work units (tile, segment) of ALL views of the batch are numbered through; CTA b starts with
+    // unit b and draws further ones from one ticket counter (unit_count[1] of view 0, zeroed by unit_build_kernel).  Per unit: publish its description, then gather its
     // list back to front — batch entry e <-> list position seg_hi-1-e — into the next stages of the ring.
     uint32_t* ticket = rb.v[0].unit_count + 1;
     const uint32_t n_units = s_prefix[rb.V];
     int g0 = 0;
     for (int k = 0;; ++k) {
-      uint32_t u = 0;
-      if (lane == 0) u = atomicAdd(ticket, 1u);
-      u = __shfl_sync(0xffffffffu, u, 0);
+      // The first unit of a CTA is its block index, later ones come from the ticket counter: a batch with fewer
+      // units than CTAs (small scenes) then runs one unit per CTA, all in parallel — with tickets from the start the
+      // CTAs that launch first ran ahead into a second unit before the last CTAs had drawn their first (C1: +15 %).
+      uint32_t u = blockIdx.x;
+      if (k > 0) {
+        if (lane == 0) u = gridDim.x + atomicAdd(ticket, 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+      }
       if (k >= 2) mbar_wait(&s_uempty[k & 1], ((k >> 1) - 1) & 1);
       if (u >= n_units) {
         if (lane == 0) {
