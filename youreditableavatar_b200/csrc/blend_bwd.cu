@@ -23,7 +23,7 @@
 //     final-transmittance term): dL/dalpha only needs that inner product, not the four blended channels.  A pair is
 //     then an affine map of (T, S) and the pairs of a commit round that fall on the same pixel compose their maps by
 //     pointer jumping over the peer lanes (log2 steps of three shuffles) instead of taking turns through shared
-//     memory (0.90 G warp instructions, 1.41 ms; with the four-channel state and turns: 1.08 G, 1.69 ms);
+//     memory (0.92 G warp instructions, 1.40 ms; with the four-channel state and turns: 1.08 G, 1.69 ms);
 //   * the backward evaluates exp / reciprocal with the hardware approximations (ex2.approx, rcp.approx) and this file
 //     is compiled with fast-math (build.py): the gradient tolerance is relative L2 1e-3, measured ~1e-6.  (The forward
 //     stays IEEE: its alpha >= 1/255 and T < 1e-4 decisions define n_contrib, which is compared bit for bit.)

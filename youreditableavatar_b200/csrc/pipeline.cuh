@@ -240,8 +240,9 @@ __device__ __forceinline__ int cons_classify(int first_included, int first_exclu
 //   2. expands the hits into CANDIDATES, one (entry, pixel) per lane, 32 per round, every lane busy: the spans are
 //      laid end to end by a warp scan and a lane finds its hit with a reduce-or / popc over the span starts;
 //   3. evaluates alpha per candidate and compacts the survivors into a ring of PAIRS;
-//   4. commits 32 pairs at a time to the per-pixel recurrence state, which lives in shared memory; pairs of one round
-//      that fall on the same pixel are serialised in list order (match.any + rank), everything else runs at full width.
+//   4. commits 32 pairs at a time to the per-pixel recurrence state (two scalars per pixel, in shared memory); pairs of
+//      one round that fall on the same pixel compose their updates in list order by pointer jumping over the peer
+//      lanes (match.any -> previous peer, log2 steps of shuffles; blend_bwd.cu), everything else runs at full width.
 // Consumer warp w owns tile rows 2w and 2w+1 (16 x 2 pixels), so the 16 row spans of an entry are computed exactly
 // once per tile — by the warp that owns the row.  Pixel index inside the warp: (row << 4) | x; lane l owns pixel l for
 // the initialisation / write-out of the state.
